@@ -1,0 +1,153 @@
+/*
+ * q1t_engine.h -- inner C ABI of the B200 statevector engine.
+ *
+ * This is the drop-in seam behind q1tsim's `VectorState`: one entry point per
+ * method of the reference's `trait QuState` (src/qustate.rs:5-89) plus the two
+ * constructors of `VectorState` (src/vectorstate.rs:41-83) and a few accessors
+ * the reference keeps private (test hooks).  A Rust `CudaVectorState` that
+ * implements `QuState` by forwarding to these functions is shown in
+ * INTEGRATION.md; the host side above this ABI in this repository is C++
+ * (q1tsim_b200/csrc) because no Rust toolchain exists in the build image.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.
+ *  - complex numbers are interleaved (re, im) doubles; gate matrices are
+ *    row-major 2^k x 2^k with `bits[0]` the most significant bit of the
+ *    matrix index (gates.rs:53-80), exactly what `Gate::matrix()` returns.
+ *  - qubit 0 is the most significant bit of the amplitude index
+ *    (vectorstate.rs:249-250); classical bit i is bit i of the u64 word.
+ *  - every function returns Q1T_OK or a negative error code; the message
+ *    (same text as the reference's `Display for Error`, error.rs:192-255) is
+ *    available from q1t_last_error().
+ *  - random numbers come from the caller: `q1t_rng` is the C mirror of the
+ *    reference's `R: rand::Rng` argument (a Rust shim passes a trampoline that
+ *    calls `rng.next_u64()`), so the caller's generator is consumed in the
+ *    same order as in the reference: one Binomial per column in column order
+ *    (vectorstate.rs:263-275), one Uniform(0,total) draw per shot in column
+ *    order (vectorstate.rs:120-133).
+ *  - the engine is asynchronous internally (gates are queued and fused); every
+ *    call that returns data is synchronous.  One caller thread per state.
+ */
+#ifndef Q1T_ENGINE_H
+#define Q1T_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct q1t_state q1t_state;
+
+typedef uint64_t (*q1t_next_u64_fn)(void *ctx);
+typedef struct {
+    q1t_next_u64_fn next_u64;
+    void *ctx;
+} q1t_rng;
+
+/* error codes (error.rs:134-180 variants that VectorState can return) */
+#define Q1T_OK 0
+#define Q1T_ERR_INVALID_NR_BITS (-1)              /* Error::InvalidNrBits */
+#define Q1T_ERR_INVALID_QBIT (-2)                 /* Error::InvalidQBit */
+#define Q1T_ERR_NOT_ENOUGH_SPACE (-3)             /* Error::NotEnoughSpace */
+#define Q1T_ERR_INVALID_NR_MEASUREMENT_BITS (-4)  /* Error::InvalidNrMeasurementBits */
+#define Q1T_ERR_INVALID_NR_CONTROL_BITS (-5)      /* Error::InvalidNrControlBits */
+#define Q1T_ERR_RNG (-6)                          /* injected generator ran dry */
+#define Q1T_ERR_CUDA (-7)                         /* no device / CUDA failure / out of device memory */
+#define Q1T_ERR_INVALID_ARGUMENT (-8)             /* NULL pointer, duplicate qubit in `bits`, ... */
+#define Q1T_ERR_UNSUPPORTED (-9)
+
+/* ---- construction: VectorState::new / from_qubit_coefs (vectorstate.rs:41-83) ---- */
+int  q1t_state_new(size_t nr_bits, size_t nr_shots, int device, q1t_state **out);
+int  q1t_state_from_qubit_coefs(const double *bit_coefs_re_im /* 2*nr_bits complex */, size_t nr_bits,
+                                size_t nr_shots, int device, q1t_state **out);
+void q1t_state_free(q1t_state *st);
+
+/* ---- trait QuState (qustate.rs:5-89) ---- */
+/* apply_gate (vectorstate.rs:166-178).  `desc` = gate.description(), used in error text. */
+int q1t_apply_gate(q1t_state *st, const double *matrix, size_t matrix_dim, const size_t *bits, size_t nr_bits,
+                   const char *desc);
+/* apply_unary_gate_all (vectorstate.rs:180-189) */
+int q1t_apply_unary_gate_all(q1t_state *st, const double *matrix, size_t matrix_dim, const char *desc);
+/* apply_conditional_gate (vectorstate.rs:193-227); control = one byte per shot */
+int q1t_apply_conditional_gate(q1t_state *st, const uint8_t *control, size_t nr_control, const double *matrix,
+                               size_t matrix_dim, const size_t *bits, size_t nr_bits, const char *desc);
+/* measure (vectorstate.rs:229-235): res must hold nr_shots words, is zeroed first */
+int q1t_measure(q1t_state *st, size_t qbit, uint64_t *res, size_t res_len, q1t_rng rng);
+/* measure_into (vectorstate.rs:237-329) */
+int q1t_measure_into(q1t_state *st, size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng);
+/* measure_all (vectorstate.rs:331-338) */
+int q1t_measure_all(q1t_state *st, uint64_t *res, size_t res_len, q1t_rng rng);
+/* measure_all_into (vectorstate.rs:340-344) */
+int q1t_measure_all_into(q1t_state *st, const size_t *cbits, size_t nr_cbits, uint64_t *res, size_t res_len,
+                         q1t_rng rng);
+/* peek_into (vectorstate.rs:346-393) */
+int q1t_peek_into(q1t_state *st, size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng);
+/* peek_all_into (vectorstate.rs:395-400) */
+int q1t_peek_all_into(q1t_state *st, const size_t *cbits, size_t nr_cbits, uint64_t *res, size_t res_len,
+                      q1t_rng rng);
+/* reset (vectorstate.rs:402-408) */
+int q1t_reset(q1t_state *st, size_t bit, q1t_rng rng);
+/* reset_all (vectorstate.rs:410-415) */
+int q1t_reset_all(q1t_state *st);
+
+/* ---- accessors (the reference keeps these fields private, vectorstate.rs:27-34) ---- */
+size_t q1t_nr_bits(const q1t_state *st);
+size_t q1t_nr_shots(const q1t_state *st);
+size_t q1t_nr_columns(q1t_state *st);                 /* states.cols() */
+int    q1t_counts(q1t_state *st, size_t *counts_out /* nr_columns */);
+/* states[(offset..offset+len, col)] in amplitude-index order, qubit 0 = MSB */
+int    q1t_read_amplitudes(q1t_state *st, size_t col, size_t offset, size_t len, double *out_re_im);
+int    q1t_write_amplitudes(q1t_state *st, size_t col, size_t offset, size_t len, const double *in_re_im);
+/* canonical-order reductions: w0 of vectorstate.rs:252-261 and column norms */
+int    q1t_marginal0(q1t_state *st, size_t qbit, double *w0_out /* nr_columns */);
+int    q1t_column_totals(q1t_state *st, double *totals_out /* nr_columns */);
+/* run all queued (fused) gate work and wait for the device */
+int    q1t_flush(q1t_state *st);
+const char *q1t_last_error(const q1t_state *st);     /* st may be NULL: last constructor error */
+
+/* execution statistics since creation / last reset of the counters */
+typedef struct {
+    uint64_t gates_queued;        /* logical gates received */
+    uint64_t sweeps;              /* fused state sweeps (each amplitude of each column read+written once) */
+    uint64_t sweep_column_passes; /* sum over sweeps of columns touched */
+    uint64_t read_passes;         /* read-only reduction passes (marginals, scans), per column */
+    uint64_t kernel_launches;     /* kernels launched by this state */
+    uint64_t permute_sweeps;      /* sweeps spent only on qubit relabelling */
+    uint64_t fallback_sweeps;     /* gates executed by the unfused generic kernel */
+    double   sweep_ms;            /* device time of sweep kernels (CUDA events), if timing enabled */
+    double   read_ms;             /* device time of read passes */
+} q1t_stats;
+int q1t_get_stats(q1t_state *st, q1t_stats *out);
+int q1t_reset_stats(q1t_state *st);
+/* enable per-kernel CUDA-event timing (bench only; serialises the stream) */
+int q1t_set_timing(q1t_state *st, int enabled);
+/* engine knobs: "tile_bits" (8..13), "fuse" (0/1).  Returns Q1T_ERR_INVALID_ARGUMENT for unknown keys. */
+int q1t_set_option(q1t_state *st, const char *key, long value);
+
+/* ---- host-only helpers (no device needed) ---- */
+/* built-in generators usable as q1t_rng: SplitMix64(seed) and an injected array of raw words */
+typedef struct q1t_rng_state q1t_rng_state;
+q1t_rng_state *q1t_rng_splitmix64(uint64_t seed);
+q1t_rng_state *q1t_rng_from_words(const uint64_t *words, size_t n);   /* copies the words */
+q1t_rng_state *q1t_rng_entropy(void);                                /* like rand::thread_rng() */
+size_t         q1t_rng_consumed(const q1t_rng_state *r);
+void           q1t_rng_free(q1t_rng_state *r);
+q1t_rng        q1t_rng_handle(q1t_rng_state *r);
+/* rand_distr 0.2 Binomial restated (vectorstate.rs:271-272) */
+uint64_t q1t_binomial(q1t_rng rng, uint64_t n, double p);
+/* `matrix()` of a built-in gate by name (composite.rs:287-445 table); returns #qubits or <0 */
+int q1t_gate_matrix(const char *name, const double *params, size_t nr_params, double *out_re_im /* 2*64 */);
+/* fusion planner dry run (no device): how many sweeps / rounds a gate list takes on nr_bits qubits.
+ * gates: concatenated matrices, bits; returns Q1T_OK and fills out[0]=sweeps out[1]=rounds out[2]=ops
+ * out[3]=fallback gates out[4]=permute sweeps needed to restore canonical order */
+int q1t_plan_dry_run(size_t nr_bits, size_t nr_gates, const double *matrices, const size_t *matrix_dims,
+                     const size_t *bits, const size_t *nr_gate_bits, long tile_bits, uint64_t *out);
+int q1t_device_count(void);
+const char *q1t_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,93 @@
+/*
+ * q1tsim_ffi.h -- the OUTER C ABI: the symbols of the reference's src/ffi.rs
+ * (authoritative C declaration: python/q1tsimffi.py:35-82), re-implemented over
+ * the B200 engine so that python/q1tsim.py runs unchanged against
+ * q1tsim_b200/lib/libq1tsim.so.  Differences from the reference, all additive:
+ *   - the gate-name table is the superset parsed by Composite::from_string
+ *     (composite.rs:287-445: cs, ct, cu1, ccx, ... are reachable; ffi.rs:335-367
+ *     accepts only 25 names, so the README QFT cannot be expressed there);
+ *   - circuit_execute always runs the statevector backend on the GPU (the
+ *     reference switches to its stabilizer backend for all-Clifford circuits,
+ *     circuit.rs:576-583, which is out of scope here);
+ *   - circuit_latex / circuit_open_qasm / circuit_c_qasm return an error result
+ *     (text exporters are out of scope);
+ *   - extra entry points: circuit_add_matrix_gate, circuit_execute_with_rng,
+ *     circuit_reexecute_with_rng, circuit_histogram_u64, circuit_engine_stats,
+ *     circuit_set_device, circuit_state.
+ * Ownership (ffi.rs:139-169): every result_t is returned by value and owns
+ * `data`; the caller passes it to result_free exactly once.
+ */
+#ifndef Q1TSIM_FFI_H
+#define Q1TSIM_FFI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "q1t_engine.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct circuit circuit_t;
+typedef struct { const char *key; size_t count; } histelem_t;     /* ffi.rs:24-29 CHistElem */
+typedef struct { double value; double *value_ptr; } parameter_t;   /* ffi.rs:40-46 CParameter */
+typedef struct { void *data; size_t length; size_t size; uint32_t restype; } result_t;   /* ffi.rs:63-70 CResult */
+
+#define RESULT_ERROR 0u      /* ffi.rs:5-9 */
+#define RESULT_EMPTY 1u
+#define RESULT_STRING 2u
+#define RESULT_HISTOGRAM 3u
+#define RESULT_CSTATE 5u
+
+void       result_free(result_t res);                                        /* ffi.rs:165-169 */
+circuit_t *circuit_new(size_t nr_qbits, size_t nr_cbits);                    /* ffi.rs:172-176 */
+void       circuit_free(circuit_t *ptr);                                     /* ffi.rs:179-186 */
+size_t     circuit_nr_qbits(const circuit_t *ptr);                           /* ffi.rs:189-194 */
+size_t     circuit_nr_cbits(const circuit_t *ptr);                           /* ffi.rs:197-202 */
+result_t   circuit_cstate(const circuit_t *ptr);                             /* ffi.rs:205-214 */
+result_t   circuit_add_gate(circuit_t *ptr, const char *gate, const size_t *qbits, size_t nr_qbits,
+                            const parameter_t *param_ptr, size_t nr_params);  /* ffi.rs:307-384 */
+result_t   circuit_add_conditional_gate(circuit_t *ptr, const size_t *control_ptr, size_t nr_control,
+                                        uint64_t target, const char *gate, const size_t *qbits_ptr, size_t nr_qbits,
+                                        const parameter_t *param_ptr, size_t nr_params);   /* ffi.rs:387-464 */
+result_t   circuit_measure(circuit_t *ptr, size_t qbit, size_t cbit, char dir, uint8_t collapse);        /* ffi.rs:501-530 */
+result_t   circuit_measure_all(circuit_t *ptr, const size_t *cbits, size_t nr_cbits, char dir, uint8_t collapse); /* ffi.rs:533-567 */
+result_t   circuit_reset(circuit_t *ptr, size_t qbit);                       /* ffi.rs:467-483 */
+result_t   circuit_reset_all(circuit_t *ptr);                                /* ffi.rs:486-498 */
+result_t   circuit_execute(circuit_t *ptr, size_t nr_shots);                 /* ffi.rs:570-585 */
+result_t   circuit_reexecute(circuit_t *ptr);                                /* ffi.rs:588-603 */
+result_t   circuit_histogram(const circuit_t *ptr);                          /* ffi.rs:606-621 */
+result_t   circuit_latex(const circuit_t *ptr);                              /* ffi.rs:624-639 (out of scope: error) */
+result_t   circuit_open_qasm(const circuit_t *ptr);                          /* ffi.rs:643-658 (out of scope: error) */
+result_t   circuit_c_qasm(const circuit_t *ptr);                             /* ffi.rs:661-676 (out of scope: error) */
+
+/* ---- additive entry points ---- */
+/* arbitrary user gate given by its matrix() (gates.rs:174), row-major (re,im) */
+result_t   circuit_add_matrix_gate(circuit_t *ptr, const char *description, const double *matrix_re_im,
+                                   size_t matrix_dim, const size_t *qbits, size_t nr_qbits);
+result_t   circuit_add_conditional_matrix_gate(circuit_t *ptr, const size_t *control_ptr, size_t nr_control,
+                                               uint64_t target, const char *description, const double *matrix_re_im,
+                                               size_t matrix_dim, const size_t *qbits, size_t nr_qbits);
+result_t   circuit_barrier(circuit_t *ptr, const size_t *qbits, size_t nr_qbits);           /* circuit.rs:541-552 */
+/* execute_with_rng / reexecute_with_rng (circuit.rs:573-641) with a caller-owned generator */
+result_t   circuit_execute_with_rng(circuit_t *ptr, size_t nr_shots, q1t_rng rng);
+result_t   circuit_reexecute_with_rng(circuit_t *ptr, q1t_rng rng);
+/* execute_with (circuit.rs:594-600): start from a product state given by 2*nr_qbits complex coefficients */
+result_t   circuit_execute_with_qubit_coefs(circuit_t *ptr, size_t nr_shots, q1t_rng rng, const double *coefs_re_im);
+/* Circuit::histogram (circuit.rs:773-791): keys as u64; data = {uint64 key; size_t count}[length], restype 6 */
+#define RESULT_HISTOGRAM_U64 6u
+typedef struct { uint64_t key; size_t count; } histelem_u64_t;
+result_t   circuit_histogram_u64(const circuit_t *ptr);
+/* copy the classical register into a caller buffer (no allocation); returns number of words */
+size_t     circuit_cstate_into(const circuit_t *ptr, uint64_t *out, size_t out_len);
+/* preset the classical register (tests of circuit.rs:1628-1650 set c_state directly) */
+result_t   circuit_set_cstate(circuit_t *ptr, const uint64_t *words, size_t n);
+int        circuit_set_device(circuit_t *ptr, int device);
+q1t_state *circuit_state(circuit_t *ptr);          /* borrowed: the live q_state, NULL before execute */
+int        circuit_engine_stats(circuit_t *ptr, q1t_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,184 @@
+// capi.cpp -- extern "C" inner ABI (include/q1t_engine.h) over DeviceVectorState.
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "engine.h"
+
+using q1t::DeviceVectorState;
+
+struct q1t_state {
+    DeviceVectorState impl;
+    q1t_state(size_t n, size_t shots, int dev) : impl(n, shots, dev) {}
+};
+
+static thread_local std::string g_ctor_error;
+
+static int make_state(size_t nr_bits, size_t nr_shots, int device, const double *coefs, q1t_state **out)
+{
+    if (!out) { g_ctor_error = "NULL output pointer"; return Q1T_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    if (nr_bits < 1 || nr_bits > 34) { g_ctor_error = "nr_bits must be in 1..34 for one device"; return Q1T_ERR_INVALID_ARGUMENT; }
+    q1t_state *st = new (std::nothrow) q1t_state(nr_bits, nr_shots, device);
+    if (!st) { g_ctor_error = "out of host memory"; return Q1T_ERR_CUDA; }
+    const int rc = coefs ? st->impl.init_from_qubit_coefs(coefs) : st->impl.init_zero_state();
+    if (rc) {
+        g_ctor_error = st->impl.last_error();
+        delete st;
+        return rc;
+    }
+    *out = st;
+    return Q1T_OK;
+}
+
+extern "C" {
+
+int q1t_state_new(size_t nr_bits, size_t nr_shots, int device, q1t_state **out)
+{
+    return make_state(nr_bits, nr_shots, device, nullptr, out);
+}
+int q1t_state_from_qubit_coefs(const double *coefs, size_t nr_bits, size_t nr_shots, int device, q1t_state **out)
+{
+    if (!coefs) { g_ctor_error = "NULL coefficient array"; return Q1T_ERR_INVALID_ARGUMENT; }
+    return make_state(nr_bits, nr_shots, device, coefs, out);
+}
+void q1t_state_free(q1t_state *st) { delete st; }
+
+#define ST_OR_FAIL if (!st) return Q1T_ERR_INVALID_ARGUMENT
+
+int q1t_apply_gate(q1t_state *st, const double *m, size_t dim, const size_t *bits, size_t k, const char *desc)
+{
+    ST_OR_FAIL;
+    return st->impl.apply_gate(m, dim, bits, k, desc);
+}
+int q1t_apply_unary_gate_all(q1t_state *st, const double *m, size_t dim, const char *desc)
+{
+    ST_OR_FAIL;
+    if (dim != 2) return st->impl.apply_gate(m, dim, nullptr, 1, desc);   // produces the InvalidNrBits error
+    return st->impl.apply_unary_gate_all(m, dim, desc);
+}
+int q1t_apply_conditional_gate(q1t_state *st, const uint8_t *control, size_t nc, const double *m, size_t dim,
+                               const size_t *bits, size_t k, const char *desc)
+{
+    ST_OR_FAIL;
+    return st->impl.apply_conditional_gate(control, nc, m, dim, bits, k, desc);
+}
+int q1t_measure(q1t_state *st, size_t qbit, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    ST_OR_FAIL;
+    if (res && res_len >= st->impl.nr_shots()) std::memset(res, 0, sizeof(uint64_t) * st->impl.nr_shots());
+    return st->impl.measure_into(qbit, 0, res, res_len, rng, true);
+}
+int q1t_measure_into(q1t_state *st, size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    ST_OR_FAIL;
+    return st->impl.measure_into(qbit, cbit, res, res_len, rng, true);
+}
+int q1t_measure_all(q1t_state *st, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    ST_OR_FAIL;
+    size_t cb[64];
+    const size_t n = st->impl.nr_bits();
+    for (size_t i = 0; i < n && i < 64; ++i) cb[i] = i;
+    if (res && res_len >= st->impl.nr_shots()) std::memset(res, 0, sizeof(uint64_t) * st->impl.nr_shots());
+    return st->impl.measure_all_into(cb, n, res, res_len, rng, true);
+}
+int q1t_measure_all_into(q1t_state *st, const size_t *cbits, size_t ncb, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    ST_OR_FAIL;
+    return st->impl.measure_all_into(cbits, ncb, res, res_len, rng, true);
+}
+int q1t_peek_into(q1t_state *st, size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    ST_OR_FAIL;
+    return st->impl.measure_into(qbit, cbit, res, res_len, rng, false);
+}
+int q1t_peek_all_into(q1t_state *st, const size_t *cbits, size_t ncb, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    ST_OR_FAIL;
+    return st->impl.measure_all_into(cbits, ncb, res, res_len, rng, false);
+}
+int q1t_reset(q1t_state *st, size_t bit, q1t_rng rng) { ST_OR_FAIL; return st->impl.reset(bit, rng); }
+int q1t_reset_all(q1t_state *st) { ST_OR_FAIL; return st->impl.reset_all(); }
+
+size_t q1t_nr_bits(const q1t_state *st) { return st ? st->impl.nr_bits() : 0; }
+size_t q1t_nr_shots(const q1t_state *st) { return st ? st->impl.nr_shots() : 0; }
+size_t q1t_nr_columns(q1t_state *st) { return st ? st->impl.nr_columns() : 0; }
+int q1t_counts(q1t_state *st, size_t *out) { ST_OR_FAIL; return st->impl.counts(out); }
+int q1t_read_amplitudes(q1t_state *st, size_t col, size_t off, size_t len, double *out)
+{
+    ST_OR_FAIL;
+    return st->impl.read_amplitudes(col, off, len, out);
+}
+int q1t_write_amplitudes(q1t_state *st, size_t col, size_t off, size_t len, const double *in)
+{
+    ST_OR_FAIL;
+    return st->impl.write_amplitudes(col, off, len, in);
+}
+int q1t_marginal0(q1t_state *st, size_t qbit, double *out) { ST_OR_FAIL; return st->impl.marginal0(qbit, out); }
+int q1t_column_totals(q1t_state *st, double *out) { ST_OR_FAIL; return st->impl.column_totals(out); }
+int q1t_flush(q1t_state *st) { ST_OR_FAIL; return st->impl.flush(); }
+const char *q1t_last_error(const q1t_state *st) { return st ? st->impl.last_error() : g_ctor_error.c_str(); }
+int q1t_get_stats(q1t_state *st, q1t_stats *out) { ST_OR_FAIL; if (!out) return Q1T_ERR_INVALID_ARGUMENT; *out = st->impl.stats; return Q1T_OK; }
+int q1t_reset_stats(q1t_state *st) { ST_OR_FAIL; std::memset(&st->impl.stats, 0, sizeof(q1t_stats)); return Q1T_OK; }
+int q1t_set_timing(q1t_state *st, int enabled) { ST_OR_FAIL; st->impl.timing = enabled != 0; return Q1T_OK; }
+int q1t_set_option(q1t_state *st, const char *key, long value) { ST_OR_FAIL; return st->impl.set_option(key, value); }
+
+int q1t_gate_matrix(const char *name, const double *params, size_t nparams, double *out)
+{
+    if (!name || !out) return Q1T_ERR_INVALID_ARGUMENT;
+    return q1t::builtin_gate_matrix(name, params, nparams, reinterpret_cast<std::complex<double> *>(out));
+}
+
+int q1t_plan_dry_run(size_t nr_bits, size_t nr_gates, const double *matrices, const size_t *dims, const size_t *bits,
+                     const size_t *nbits, long tile_bits, uint64_t *out)
+{
+    if (!out || nr_bits < 5 || nr_bits > (size_t)q1t::kMaxBits) return Q1T_ERR_INVALID_ARGUMENT;
+    const int n = (int)nr_bits;
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    q1t::Planner pl(n, (int)tile_bits);
+    uint64_t fallback = 0;
+    size_t moff = 0, boff = 0;
+    for (size_t g = 0; g < nr_gates; ++g) {
+        const size_t k = nbits[g], dim = dims[g];
+        if (dim != ((size_t)1 << k) || k > 12) return Q1T_ERR_INVALID_NR_BITS;
+        int phys[16];
+        for (size_t j = 0; j < k; ++j) {
+            if (bits[boff + j] >= nr_bits) return Q1T_ERR_INVALID_QBIT;
+            phys[j] = perm[n - 1 - (int)bits[boff + j]];
+        }
+        q1t::LoweredGate lg;
+        std::string err;
+        if (!q1t::lower_gate(reinterpret_cast<const q1t::cplx *>(matrices + moff), (int)k, phys, lg, err)) return Q1T_ERR_UNSUPPORTED;
+        if (lg.kind == q1t::LoweredGate::SWAP) {
+            for (int l = 0; l < n; ++l) {
+                if (perm[l] == lg.b[0]) perm[l] = lg.b[1];
+                else if (perm[l] == lg.b[1]) perm[l] = lg.b[0];
+            }
+        } else if (lg.kind == q1t::LoweredGate::GENERIC) {
+            uint64_t m = 0;
+            for (int p : lg.pos) m |= 1ull << p;
+            pl.flush_diag_touching(m);
+            pl.cut();
+            ++fallback;
+        } else if (!(lg.kind == q1t::LoweredGate::POLY && lg.nb == 0)) pl.add(lg);
+        moff += 2 * dim * dim;
+        boff += k;
+    }
+    pl.finish();
+    bool ident = true;
+    for (int l = 0; l < n; ++l) if (perm[l] != l) ident = false;
+    out[0] = pl.stats.sweeps; out[1] = pl.stats.rounds; out[2] = pl.stats.ops; out[3] = fallback; out[4] = ident ? 0 : 1;
+    return Q1T_OK;
+}
+
+int q1t_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+const char *q1t_version(void) { return "q1tsim_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

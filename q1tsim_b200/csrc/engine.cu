@@ -1,0 +1,831 @@
+// engine.cu -- DeviceVectorState: HBM-resident multi-column run state.
+//
+// Mirrors `impl QuState for VectorState` (vectorstate.rs:164-416).  Storage is
+// one contiguous buffer of 2^n complex128 per branch column (cmatrix.rs moved
+// into HBM; the reference interleaves columns in an (N, C) row-major matrix,
+// which would re-stride every amplitude whenever a measurement splits a
+// column).  Gates are queued and executed by the fused sweep kernel at the next
+// point where the state is observed.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace q1t {
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+int DeviceVectorState::cuda_fail(cudaError_t e, const char *what)
+{
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "CUDA error: %s (%s)", cudaGetErrorString(e), what);
+    cudaGetLastError();
+    return fail(Q1T_ERR_CUDA, buf);
+}
+
+DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device)
+    : n_((int)nr_bits), shots_(nr_shots), device_(device)
+{
+    perm_.resize(n_);
+    for (int i = 0; i < n_; ++i) perm_[i] = i;
+}
+
+DeviceVectorState::~DeviceVectorState()
+{
+    if (stream_) {
+        cudaSetDevice(device_);
+        cudaStreamSynchronize(stream_);
+        for (Column &c : cols_)
+            if (c.buf) cudaFree(c.buf);
+        for (double2 *p : free_bufs_) cudaFree(p);
+        cudaFree(d_colptrs_); cudaFree(d_ptabs_); cudaFree(d_leaf_); cudaFree(d_block_); cudaFree(d_totals_);
+        cudaFree(d_chosen_); cudaFree(d_idx_); cudaFree(d_mat_);
+        if (ev0_) cudaEventDestroy(ev0_);
+        if (ev1_) cudaEventDestroy(ev1_);
+        cudaStreamDestroy(stream_);
+    }
+}
+
+int DeviceVectorState::ensure_device()
+{
+    if (stream_) { CK(cudaSetDevice(device_)); return Q1T_OK; }
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        return fail(Q1T_ERR_CUDA, "no CUDA device available: the q1tsim B200 engine has no CPU fallback");
+    }
+    if (device_ < 0 || device_ >= cnt) return fail(Q1T_ERR_CUDA, "invalid CUDA device ordinal");
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0_));
+    CK(cudaEventCreate(&ev1_));
+    CK(cudaMalloc(&d_ptabs_, sizeof(PhaseTab) * kMaxPhase));
+    CK(cudaMalloc(&d_mat_, sizeof(double2) << (2 * kMaxGenericBits)));
+    return Q1T_OK;
+}
+
+int DeviceVectorState::alloc_column(double2 **out)
+{
+    if (!free_bufs_.empty()) { *out = free_bufs_.back(); free_bufs_.pop_back(); return Q1T_OK; }
+    cudaError_t e = cudaMalloc(out, sizeof(double2) << n_);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char buf[256];
+        std::snprintf(buf, sizeof buf, "out of device memory allocating a branch column of %zu bytes (%zu columns live)",
+                      sizeof(double2) << n_, cols_.size());
+        return fail(Q1T_ERR_CUDA, buf);
+    }
+    return Q1T_OK;
+}
+
+void DeviceVectorState::release_column(double2 *p)
+{
+    if (!p) return;
+    // keep at most two spare buffers (relabel scratch + one split target)
+    if (free_bufs_.size() < 2 && n_ <= 31) free_bufs_.push_back(p);
+    else { cudaStreamSynchronize(stream_); cudaFree(p); }
+}
+
+int DeviceVectorState::init_zero_state()
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    Column c;
+    rc = alloc_column(&c.buf);
+    if (rc) return rc;
+    c.count = shots_;
+    CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
+    CK(launch_set_basis(c.buf, 0, stream_));
+    stats.kernel_launches++;
+    cols_.push_back(c);
+    return Q1T_OK;
+}
+
+// vectorstate.rs:62-83
+int DeviceVectorState::init_from_qubit_coefs(const double *coefs)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    std::vector<double2> nc(2 * (size_t)n_);
+    for (int q = 0; q < n_; ++q) {
+        const double *c = coefs + 4 * q;
+        const double norm = std::sqrt((c[0] * c[0] + c[1] * c[1]) + (c[2] * c[2] + c[3] * c[3]));
+        nc[2 * q] = make_double2(c[0] / norm, c[1] / norm);
+        nc[2 * q + 1] = make_double2(c[2] / norm, c[3] / norm);
+    }
+    Column c;
+    rc = alloc_column(&c.buf);
+    if (rc) return rc;
+    c.count = shots_;
+    double2 *d_coefs = nullptr;
+    CK(cudaMalloc(&d_coefs, sizeof(double2) * nc.size() + 16));
+    CK(cudaMemcpyAsync(d_coefs, nc.data(), sizeof(double2) * nc.size(), cudaMemcpyHostToDevice, stream_));
+    CK(launch_product_state(c.buf, n_, d_coefs, stream_));
+    stats.kernel_launches++;
+    CK(cudaStreamSynchronize(stream_));
+    cudaFree(d_coefs);
+    cols_.push_back(c);
+    return Q1T_OK;
+}
+
+int DeviceVectorState::materialize(Column &c)
+{
+    if (!c.basis) return Q1T_OK;
+    int rc = alloc_column(&c.buf);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
+    CK(launch_set_basis(c.buf, c.basis_idx, stream_));
+    stats.kernel_launches++;
+    c.basis = false;
+    return Q1T_OK;
+}
+
+int DeviceVectorState::upload_colptrs(const std::vector<int> &which)
+{
+    const size_t need = which.size();
+    if (need > colptrs_cap_) {
+        if (d_colptrs_) { CK(cudaStreamSynchronize(stream_)); cudaFree(d_colptrs_); }
+        colptrs_cap_ = std::max<size_t>(need * 2, 16);
+        CK(cudaMalloc(&d_colptrs_, sizeof(double2 *) * colptrs_cap_));
+    }
+    std::vector<double2 *> h(need);
+    for (size_t i = 0; i < need; ++i) h[i] = cols_[which[i]].buf;
+    CK(cudaMemcpyAsync(d_colptrs_, h.data(), sizeof(double2 *) * need, cudaMemcpyHostToDevice, stream_));
+    return Q1T_OK;
+}
+
+void DeviceVectorState::time_begin()
+{
+    if (timing) cudaEventRecord(ev0_, stream_);
+}
+void DeviceVectorState::time_end(double &acc)
+{
+    if (!timing) return;
+    cudaEventRecord(ev1_, stream_);
+    cudaEventSynchronize(ev1_);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0_, ev1_);
+    acc += ms;
+}
+
+// ---------------------------------------------------------------------------
+// gate queue
+// ---------------------------------------------------------------------------
+int DeviceVectorState::lower_and_queue(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc)
+{
+    if (!mat || (!bits && k)) return fail(Q1T_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    // vectorstate.rs:169-174: gate.nr_affected_bits() != bits.len()
+    size_t gate_bits = 0;
+    while (((size_t)1 << gate_bits) < dim) ++gate_bits;
+    if (((size_t)1 << gate_bits) != dim || gate_bits != k) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf, "Expected %zu bits for \"%s\", got %zu", gate_bits, desc ? desc : "gate", k);
+        return fail(Q1T_ERR_INVALID_NR_BITS, buf);
+    }
+    if (k == 0) return Q1T_OK;
+    if (k > 12) return fail(Q1T_ERR_UNSUPPORTED, "gates on more than 12 qubits are not supported");
+    int phys[16];
+    for (size_t j = 0; j < k; ++j) {
+        if (bits[j] >= (size_t)n_) {
+            char buf[128];
+            std::snprintf(buf, sizeof buf, "Invalid index %zu for a quantum bit", bits[j]);
+            return fail(Q1T_ERR_INVALID_QBIT, buf);
+        }
+        phys[j] = perm_[n_ - 1 - (int)bits[j]];
+    }
+    LoweredGate lg;
+    std::string e;
+    if (!lower_gate(reinterpret_cast<const cplx *>(mat), (int)k, phys, lg, e))
+        return fail(e.find("duplicate") != std::string::npos ? Q1T_ERR_INVALID_ARGUMENT : Q1T_ERR_UNSUPPORTED, e);
+    stats.gates_queued++;
+    if (lg.kind == LoweredGate::POLY && lg.nb == 0) return Q1T_OK;          // identity
+    if (lg.kind == LoweredGate::SWAP && n_ >= 5 && fuse_) {
+        // zero-byte relabel: exchange the physical homes of the two logical bits
+        for (int l = 0; l < n_; ++l) {
+            if (perm_[l] == lg.b[0]) perm_[l] = lg.b[1];
+            else if (perm_[l] == lg.b[1]) perm_[l] = lg.b[0];
+        }
+        return Q1T_OK;
+    }
+    queue_.push_back(lg);
+    return Q1T_OK;
+}
+
+static void to_generic(const LoweredGate &g, LoweredGate &out)
+{
+    out = g;
+    if (g.kind == LoweredGate::GENERIC) return;
+    out.kind = LoweredGate::GENERIC;
+    out.pos.clear();
+    out.mat.clear();
+    if (g.kind == LoweredGate::G1) {
+        out.pos.push_back(g.target);
+        for (int e = 0; e < 4; ++e) out.mat.push_back(cplx(g.m[2 * e], g.m[2 * e + 1]));
+    } else if (g.kind == LoweredGate::SWAP) {
+        out.pos.push_back(g.b[0]); out.pos.push_back(g.b[1]);
+        static const double sw[16] = { 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1 };
+        for (int e = 0; e < 16; ++e) out.mat.push_back(cplx(sw[e], 0));
+        out.cmask = 0;
+    } else {   // POLY -> diagonal matrix
+        const int k = g.nb, G = 1 << k;
+        out.cmask = 0;
+        for (int j = 0; j < k; ++j) out.pos.push_back(g.b[j]);
+        out.mat.assign((size_t)G * G, cplx(0, 0));
+        for (int x = 0; x < G; ++x) {
+            double a = g.c0;
+            if (k == 1) a += x ? g.lin[0] : 0.0;
+            else {
+                const int x0 = (x >> 1) & 1, x1 = x & 1;
+                a += x0 * g.lin[0] + x1 * g.lin[1] + (x0 & x1) * g.quad;
+            }
+            out.mat[(size_t)x * G + x] = cplx(std::cos(M_PI * a), std::sin(M_PI * a));
+        }
+    }
+}
+
+int DeviceVectorState::run_generic(const LoweredGate &g, const std::vector<int> &which)
+{
+    const int k = (int)g.pos.size();
+    GenericGateArgs a;
+    std::memset(&a, 0, sizeof a);
+    std::vector<int> sorted = g.pos;
+    std::sort(sorted.begin(), sorted.end());
+    for (int j = 0; j < k; ++j) a.sorted_pos[j] = sorted[j];
+    for (int h = 0; h < (1 << k); ++h) {
+        unsigned long long o = 0;
+        for (int j = 0; j < k; ++j)
+            if ((h >> (k - 1 - j)) & 1) o |= 1ull << g.pos[j];
+        a.offs[h] = o;
+    }
+    a.cmask = g.cmask;
+    CK(cudaMemcpyAsync(d_mat_, g.mat.data(), sizeof(double2) * g.mat.size(), cudaMemcpyHostToDevice, stream_));
+    time_begin();
+    CK(launch_generic_gate(d_colptrs_, (int)which.size(), n_, k, a, d_mat_, stream_));
+    time_end(stats.sweep_ms);
+    stats.kernel_launches++;
+    stats.sweeps++;
+    stats.fallback_sweeps++;
+    stats.sweep_column_passes += which.size();
+    return Q1T_OK;
+}
+
+int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which)
+{
+    for (PlannedSweep &ps : sweeps) {
+        if (!ps.ptabs.empty())
+            CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
+        time_begin();
+        CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, stream_));
+        time_end(stats.sweep_ms);
+        stats.kernel_launches++;
+        stats.sweeps++;
+        stats.sweep_column_passes += which.size();
+    }
+    sweeps.clear();
+    return Q1T_OK;
+}
+
+int DeviceVectorState::run_queue()
+{
+    if (queue_.empty()) return Q1T_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    std::vector<int> which = queue_cols_;
+    if (which.empty())
+        for (size_t c = 0; c < cols_.size(); ++c) which.push_back((int)c);
+    for (int c : which) {
+        rc = materialize(cols_[c]);
+        if (rc) return rc;
+    }
+    rc = upload_colptrs(which);
+    if (rc) return rc;
+    std::vector<LoweredGate> q;
+    q.swap(queue_);
+    queue_cols_.clear();
+    if (n_ < 5 || !fuse_) {
+        for (const LoweredGate &g : q) {
+            LoweredGate gg;
+            to_generic(g, gg);
+            rc = run_generic(gg, which);
+            if (rc) return rc;
+        }
+        return Q1T_OK;
+    }
+    Planner pl(n_, (int)tile_bits_);
+    for (const LoweredGate &g : q) {
+        if (g.kind == LoweredGate::POLY || g.kind == LoweredGate::G1) {
+            pl.add(g);
+            continue;
+        }
+        LoweredGate gg;
+        to_generic(g, gg);
+        uint64_t m = 0;
+        for (int p : gg.pos) m |= 1ull << p;
+        pl.flush_diag_touching(m);
+        pl.cut();
+        std::vector<PlannedSweep> sw = pl.take();
+        rc = run_sweeps(sw, which);
+        if (rc) return rc;
+        rc = run_generic(gg, which);
+        if (rc) return rc;
+    }
+    pl.finish();
+    std::vector<PlannedSweep> sw = pl.take();
+    return run_sweeps(sw, which);
+}
+
+// undo the zero-byte swap relabelling: one out-of-place relabel sweep per column
+int DeviceVectorState::canonicalize()
+{
+    bool ident = true;
+    for (int l = 0; l < n_; ++l)
+        if (perm_[l] != l) ident = false;
+    if (ident) return Q1T_OK;
+    std::vector<int> dstpos(n_);
+    for (int l = 0; l < n_; ++l) dstpos[perm_[l]] = l;
+    PlannedSweep ps = build_permute_sweep(n_, (int)tile_bits_, dstpos);
+    for (size_t c = 0; c < cols_.size(); ++c) {
+        Column &col = cols_[c];
+        if (col.basis) {
+            // lazy basis columns are stored by logical index; nothing to move
+            continue;
+        }
+        double2 *scratch = nullptr;
+        int rc = alloc_column(&scratch);
+        if (rc) return rc;
+        double2 *h[2] = { col.buf, scratch };
+        if (colptrs_cap_ < 2) {
+            std::vector<int> dummy;
+            colptrs_cap_ = 16;
+            if (d_colptrs_) cudaFree(d_colptrs_);
+            CK(cudaMalloc(&d_colptrs_, sizeof(double2 *) * colptrs_cap_));
+        }
+        CK(cudaMemcpyAsync(d_colptrs_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
+        time_begin();
+        CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_ + 1, 1, d_ptabs_, stream_));
+        time_end(stats.sweep_ms);
+        stats.kernel_launches++;
+        stats.sweeps++;
+        stats.permute_sweeps++;
+        stats.sweep_column_passes++;
+        double2 *old = col.buf;
+        col.buf = scratch;
+        release_column(old);
+    }
+    for (int l = 0; l < n_; ++l) perm_[l] = l;
+    return Q1T_OK;
+}
+
+int DeviceVectorState::flush()
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    rc = run_queue();
+    if (rc) return rc;
+    rc = canonicalize();
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// vectorstate.rs:166-178
+int DeviceVectorState::apply_gate(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc)
+{
+    if (!queue_cols_.empty()) { int rc = run_queue(); if (rc) return rc; }
+    int rc = lower_and_queue(mat, dim, bits, k, desc);
+    if (rc) return rc;
+    if (queue_.size() >= 8192) return run_queue();
+    return Q1T_OK;
+}
+
+// vectorstate.rs:180-189 -- the n one-qubit gates are queued and fused into a
+// handful of sweeps instead of n passes
+int DeviceVectorState::apply_unary_gate_all(const double *mat, size_t dim, const char *desc)
+{
+    for (size_t b = 0; b < (size_t)n_; ++b) {
+        int rc = apply_gate(mat, dim, &b, 1, desc);
+        if (rc) return rc;
+    }
+    return Q1T_OK;
+}
+
+// vectorstate.rs:193-227 + qustate.rs:100-127
+int DeviceVectorState::apply_conditional_gate(const uint8_t *control, size_t ncontrol, const double *mat, size_t dim,
+                                              const size_t *bits, size_t k, const char *desc)
+{
+    if (ncontrol != shots_) {
+        char buf[320];
+        std::snprintf(buf, sizeof buf, "The number of runs is %zu, but received %zu control bits for controlled %s operation",
+                      shots_, ncontrol, desc ? desc : "gate");
+        return fail(Q1T_ERR_INVALID_NR_CONTROL_BITS, buf);
+    }
+    size_t gate_bits = 0;
+    while (((size_t)1 << gate_bits) < dim) ++gate_bits;
+    if (((size_t)1 << gate_bits) != dim || gate_bits != k) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf, "Expected %zu bits for \"%s\", got %zu", gate_bits, desc ? desc : "gate", k);
+        return fail(Q1T_ERR_INVALID_NR_BITS, buf);
+    }
+    if (!control && ncontrol) return fail(Q1T_ERR_INVALID_ARGUMENT, "NULL control array");
+    int rc = ensure_device();
+    if (rc) return rc;
+    rc = run_queue();
+    if (rc) return rc;
+    // collect_conditional_ranges (qustate.rs:100-127)
+    struct Range { int icol; size_t len; bool apply; };
+    std::vector<Range> ranges;
+    size_t off = 0;
+    for (size_t icol = 0; icol < cols_.size(); ++icol) {
+        const size_t count = cols_[icol].count;
+        if (count == 0) continue;
+        size_t begin = off;
+        bool prev = control[off] != 0;
+        for (size_t ibit = off + 1; ibit < off + count; ++ibit) {
+            if ((control[ibit] != 0) != prev) {
+                ranges.push_back({ (int)icol, ibit - begin, prev });
+                begin = ibit;
+                prev = !prev;
+            }
+        }
+        if (begin < off + count) ranges.push_back({ (int)icol, off + count - begin, prev });
+        off += count;
+    }
+    // new column list: the last range of a column takes over its buffer, earlier ranges get copies
+    std::vector<Column> nc(ranges.size());
+    std::vector<int> last_of(cols_.size(), -1);
+    for (size_t r = 0; r < ranges.size(); ++r) last_of[ranges[r].icol] = (int)r;
+    std::vector<int> flagged;
+    for (size_t r = 0; r < ranges.size(); ++r) {
+        Column &src = cols_[ranges[r].icol];
+        Column &dst = nc[r];
+        dst.count = ranges[r].len;
+        if (last_of[ranges[r].icol] == (int)r) {
+            dst.buf = src.buf; dst.basis = src.basis; dst.basis_idx = src.basis_idx;
+            src.buf = nullptr;
+        } else if (src.basis) {
+            dst.basis = true; dst.basis_idx = src.basis_idx;
+        } else {
+            rc = alloc_column(&dst.buf);
+            if (rc) { cols_.swap(nc); return rc; }
+            CK(cudaMemcpyAsync(dst.buf, src.buf, sizeof(double2) << n_, cudaMemcpyDeviceToDevice, stream_));
+            stats.sweep_column_passes++;     // a column copy is one read + one write of the column
+        }
+        if (ranges[r].apply) flagged.push_back((int)r);
+    }
+    for (Column &c : cols_)
+        if (c.buf) release_column(c.buf);     // columns that had no shots
+    cols_.swap(nc);
+    if (flagged.empty()) return Q1T_OK;
+    rc = lower_and_queue(mat, dim, bits, k, desc);
+    if (rc) return rc;
+    if (queue_.empty()) return Q1T_OK;        // identity or relabel-only
+    queue_cols_ = flagged;
+    return run_queue();
+}
+
+// ---------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------
+int DeviceVectorState::ensure_scratch(size_t ncols)
+{
+    const int leaf_bits = n_ < kCanonLeafBits ? n_ : kCanonLeafBits;
+    const size_t nleaves = (size_t)1 << (n_ - leaf_bits);
+    const size_t nblocks = (nleaves + kCanonBlock - 1) / kCanonBlock;
+    if (ncols * nleaves > leaf_cap_) {
+        if (d_leaf_) cudaFree(d_leaf_);
+        leaf_cap_ = ncols * nleaves;
+        CK(cudaMalloc(&d_leaf_, sizeof(double) * leaf_cap_));
+    }
+    if (ncols * nblocks > block_cap_) {
+        if (d_block_) cudaFree(d_block_);
+        block_cap_ = ncols * nblocks;
+        CK(cudaMalloc(&d_block_, sizeof(double) * block_cap_));
+    }
+    if (ncols > totals_cap_) {
+        if (d_totals_) cudaFree(d_totals_);
+        totals_cap_ = ncols * 2;
+        CK(cudaMalloc(&d_totals_, sizeof(double) * totals_cap_));
+    }
+    return Q1T_OK;
+}
+
+// canonical totals of |amp|^2 over amplitudes with (index & mask) == want, for
+// every device-resident column; leaves d_leaf_/d_block_ holding the prefixes
+int DeviceVectorState::reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols)
+{
+    dev_cols.clear();
+    for (size_t c = 0; c < cols_.size(); ++c)
+        if (!cols_[c].basis) dev_cols.push_back((int)c);
+    totals.assign(dev_cols.size(), 0.0);
+    if (dev_cols.empty()) return Q1T_OK;
+    int rc = ensure_scratch(dev_cols.size());
+    if (rc) return rc;
+    rc = upload_colptrs(dev_cols);
+    if (rc) return rc;
+    time_begin();
+    CK(launch_leaf_totals(d_colptrs_, (int)dev_cols.size(), d_leaf_, n_, mask, want, stream_));
+    CK(launch_scan(d_leaf_, d_block_, d_totals_, (int)dev_cols.size(), n_, stream_));
+    time_end(stats.read_ms);
+    stats.kernel_launches += 3;
+    stats.read_passes += dev_cols.size();
+    CK(cudaMemcpyAsync(totals.data(), d_totals_, sizeof(double) * dev_cols.size(), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+int DeviceVectorState::marginal0(size_t qbit, double *w0_out)
+{
+    if (qbit >= (size_t)n_) {
+        char buf[128];
+        std::snprintf(buf, sizeof buf, "Invalid index %zu for a quantum bit", qbit);
+        return fail(Q1T_ERR_INVALID_QBIT, buf);
+    }
+    int rc = flush();
+    if (rc) return rc;
+    const uint64_t bit = 1ull << (n_ - 1 - (int)qbit);
+    std::vector<double> tot;
+    std::vector<int> dev;
+    rc = reduce_columns(bit, 0, tot, dev);
+    if (rc) return rc;
+    size_t k = 0;
+    for (size_t c = 0; c < cols_.size(); ++c) {
+        if (cols_[c].basis) w0_out[c] = (cols_[c].basis_idx & bit) ? 0.0 : 1.0;
+        else w0_out[c] = tot[k++];
+    }
+    return Q1T_OK;
+}
+
+int DeviceVectorState::column_totals(double *out)
+{
+    int rc = flush();
+    if (rc) return rc;
+    std::vector<double> tot;
+    std::vector<int> dev;
+    rc = reduce_columns(0, 0, tot, dev);
+    if (rc) return rc;
+    size_t k = 0;
+    for (size_t c = 0; c < cols_.size(); ++c) out[c] = cols_[c].basis ? 1.0 : tot[k++];
+    return Q1T_OK;
+}
+
+// ---------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------
+// measure_into (vectorstate.rs:237-329) / peek_into (vectorstate.rs:346-393)
+int DeviceVectorState::measure_into(size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng, bool collapse)
+{
+    if (qbit >= (size_t)n_) {
+        char buf[128];
+        std::snprintf(buf, sizeof buf, "Invalid index %zu for a quantum bit", qbit);
+        return fail(Q1T_ERR_INVALID_QBIT, buf);
+    }
+    if (res_len < shots_) {
+        char buf[192];
+        std::snprintf(buf, sizeof buf, "Not enough space to store %zu measurement results in array of length %zu", shots_, res_len);
+        return fail(Q1T_ERR_NOT_ENOUGH_SPACE, buf);
+    }
+    if (cbit >= 64) return fail(Q1T_ERR_INVALID_ARGUMENT, "classical bit index must be < 64");
+    if (!res || !rng.next_u64) return fail(Q1T_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    std::vector<double> w0s(cols_.size());
+    int rc = marginal0(qbit, w0s.data());
+    if (rc) return rc;
+    const int bitpos = n_ - 1 - (int)qbit;
+    const uint64_t bit = 1ull << bitpos;
+    const uint64_t one_mask = 1ull << cbit, zero_mask = ~one_mask;
+    // all Binomial draws first, in column order (vectorstate.rs:263-275)
+    std::vector<size_t> n0s(cols_.size());
+    for (size_t c = 0; c < cols_.size(); ++c) {
+        n0s[c] = (size_t)binomial_sample(rng, cols_[c].count, w0s[c] < 1.0 ? w0s[c] : 1.0);
+        if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
+    }
+    size_t start = 0;
+    std::vector<Column> nc;
+    for (size_t c = 0; c < cols_.size(); ++c) {
+        Column col = cols_[c];
+        const size_t n0 = n0s[c], cnt = col.count;
+        for (size_t j = start; j < start + n0; ++j) res[j] &= zero_mask;
+        for (size_t j = start + n0; j < start + cnt; ++j) res[j] |= one_mask;
+        start += cnt;
+        if (!collapse) continue;
+        const double w0 = w0s[c];
+        const double f0 = 1.0 / std::sqrt(w0), f1 = 1.0 / std::sqrt(1.0 - w0);
+        if (col.basis) {
+            // a basis state is an eigenstate: w0 is exactly 0 or 1, nothing changes
+            nc.push_back(col);
+            continue;
+        }
+        if (n0 == cnt) {
+            CK(launch_collapse(col.buf, col.buf, nullptr, n_, bitpos, f0, 0.0, stream_));
+            nc.push_back(col);
+        } else if (n0 == 0) {
+            CK(launch_collapse(col.buf, nullptr, col.buf, n_, bitpos, 0.0, f1, stream_));
+            nc.push_back(col);
+        } else {
+            Column one;
+            rc = alloc_column(&one.buf);
+            if (rc) { cols_[c] = col; return rc; }
+            CK(launch_collapse(col.buf, col.buf, one.buf, n_, bitpos, f0, f1, stream_));
+            col.count = n0;
+            one.count = cnt - n0;
+            nc.push_back(col);
+            nc.push_back(one);
+        }
+        stats.kernel_launches++;
+        stats.sweep_column_passes++;
+    }
+    (void)bit;
+    if (collapse) {
+        stats.sweeps++;
+        cols_.swap(nc);
+        CK(cudaStreamSynchronize(stream_));
+    }
+    return Q1T_OK;
+}
+
+// measure_all_into / peek_all_into (vectorstate.rs:106-161)
+int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint64_t *res, size_t res_len, q1t_rng rng,
+                                        bool collapse)
+{
+    if (res_len < shots_) {
+        char buf[192];
+        std::snprintf(buf, sizeof buf, "Not enough space to store %zu measurement results in array of length %zu", shots_, res_len);
+        return fail(Q1T_ERR_NOT_ENOUGH_SPACE, buf);
+    }
+    if (ncbits != (size_t)n_) {
+        char buf[128];
+        std::snprintf(buf, sizeof buf, "Expected %d measurement bits, but got %zu", n_, ncbits);
+        return fail(Q1T_ERR_INVALID_NR_MEASUREMENT_BITS, buf);
+    }
+    if (!res || !cbits || !rng.next_u64) return fail(Q1T_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+    for (size_t j = 0; j < ncbits; ++j)
+        if (cbits[j] >= 64) return fail(Q1T_ERR_INVALID_ARGUMENT, "classical bit index must be < 64");
+    int rc = flush();
+    if (rc) return rc;
+    std::vector<double> totals;
+    std::vector<int> dev;
+    rc = reduce_columns(0, 0, totals, dev);
+    if (rc) return rc;
+    const int leaf_bits = n_ < kCanonLeafBits ? n_ : kCanonLeafBits;
+    const size_t nleaves = (size_t)1 << (n_ - leaf_bits);
+    const size_t nblocks = (nleaves + kCanonBlock - 1) / kCanonBlock;
+
+    std::vector<std::pair<uint64_t, size_t>> state_counts;   // (basis index, multiplicity), grouped per column
+    std::vector<double> chosen;
+    std::vector<uint64_t> idx;
+    size_t k = 0;
+    for (size_t c = 0; c < cols_.size(); ++c) {
+        const size_t cnt = cols_[c].count;
+        if (cols_[c].basis) {
+            // WeightedIndex over a unit vector: every draw consumes one word and returns basis_idx
+            for (size_t j = 0; j < cnt; ++j) (void)rng.next_u64(rng.ctx);
+            if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
+            if (cnt) state_counts.push_back(std::make_pair(cols_[c].basis_idx, cnt));
+            continue;
+        }
+        const double total = totals[k];
+        if (!(total > 0.0)) return fail(Q1T_ERR_INVALID_ARGUMENT, "state column has zero norm");
+        const UniformF64 u = uniform_new(0.0, total);
+        chosen.resize(cnt);
+        for (size_t j = 0; j < cnt; ++j) chosen[j] = uniform_sample(u, rng);
+        if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
+        std::sort(chosen.begin(), chosen.end());
+        if (cnt > draws_cap_) {
+            if (d_chosen_) cudaFree(d_chosen_);
+            if (d_idx_) cudaFree(d_idx_);
+            draws_cap_ = cnt;
+            CK(cudaMalloc(&d_chosen_, sizeof(double) * draws_cap_));
+            CK(cudaMalloc(&d_idx_, sizeof(uint64_t) * draws_cap_));
+        }
+        idx.resize(cnt);
+        if (cnt) {
+            CK(cudaMemcpyAsync(d_chosen_, chosen.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice, stream_));
+            time_begin();
+            CK(launch_resolve_draws(cols_[c].buf, d_leaf_ + k * nleaves, d_block_ + k * nblocks, n_, d_chosen_, cnt,
+                                    reinterpret_cast<unsigned long long *>(d_idx_), stream_));
+            time_end(stats.read_ms);
+            stats.kernel_launches++;
+            CK(cudaMemcpyAsync(idx.data(), d_idx_, sizeof(uint64_t) * cnt, cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+        }
+        for (size_t j = 0; j < cnt; ++j) {
+            if (j > 0 && idx[j] == idx[j - 1]) state_counts.back().second++;
+            else state_counts.push_back(std::make_pair(idx[j], (size_t)1));
+        }
+        ++k;
+    }
+    // route bits: qubit j -> classical bit cbits[j] (support.rs:50-75, vectorstate.rs:135-148)
+    uint64_t m = 0;
+    for (size_t j = 0; j < ncbits; ++j) m |= 1ull << cbits[j];
+    const uint64_t mask = ~m;
+    size_t off = 0;
+    for (const auto &sc : state_counts) {
+        uint64_t word = 0;
+        for (int q = 0; q < n_; ++q)
+            if ((sc.first >> (n_ - 1 - q)) & 1ull) word |= 1ull << cbits[q];
+        for (size_t j = off; j < off + sc.second; ++j) res[j] = (res[j] & mask) | word;
+        off += sc.second;
+    }
+    if (collapse) {
+        // vectorstate.rs:150-158 allocates a dense (2^n, n_distinct) matrix of unit vectors;
+        // here the collapsed columns are kept as basis indices until a gate touches them
+        for (Column &c : cols_)
+            if (c.buf) release_column(c.buf);
+        cols_.clear();
+        for (const auto &sc : state_counts) {
+            Column c;
+            c.basis = true; c.basis_idx = sc.first; c.count = sc.second;
+            cols_.push_back(c);
+        }
+    }
+    return Q1T_OK;
+}
+
+// vectorstate.rs:402-408
+int DeviceVectorState::reset(size_t bit, q1t_rng rng)
+{
+    std::vector<uint64_t> m(shots_ ? shots_ : 1, 0);
+    int rc = measure_into(bit, 0, m.data(), shots_, rng, true);
+    if (rc) return rc;
+    std::vector<uint8_t> control(shots_ ? shots_ : 1);
+    for (size_t j = 0; j < shots_; ++j) control[j] = m[j] != 0;
+    static const double X[8] = { 0, 0, 1, 0, 1, 0, 0, 0 };
+    return apply_conditional_gate(control.data(), shots_, X, 2, &bit, 1, "X");
+}
+
+// vectorstate.rs:410-415
+int DeviceVectorState::reset_all()
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    queue_.clear();
+    queue_cols_.clear();
+    CK(cudaStreamSynchronize(stream_));
+    for (Column &c : cols_)
+        if (c.buf) release_column(c.buf);
+    cols_.clear();
+    for (int l = 0; l < n_; ++l) perm_[l] = l;
+    return init_zero_state();
+}
+
+int DeviceVectorState::counts(size_t *out)
+{
+    for (size_t c = 0; c < cols_.size(); ++c) out[c] = cols_[c].count;
+    return Q1T_OK;
+}
+
+int DeviceVectorState::read_amplitudes(size_t col, size_t offset, size_t len, double *out)
+{
+    if (col >= cols_.size() || offset + len > ((size_t)1 << n_)) return fail(Q1T_ERR_INVALID_ARGUMENT, "amplitude range out of bounds");
+    int rc = flush();
+    if (rc) return rc;
+    if (cols_[col].basis) {
+        std::memset(out, 0, sizeof(double) * 2 * len);
+        if (cols_[col].basis_idx >= offset && cols_[col].basis_idx < offset + len) out[2 * (cols_[col].basis_idx - offset)] = 1.0;
+        return Q1T_OK;
+    }
+    CK(cudaMemcpyAsync(out, cols_[col].buf + offset, sizeof(double2) * len, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+int DeviceVectorState::write_amplitudes(size_t col, size_t offset, size_t len, const double *in)
+{
+    if (col >= cols_.size() || offset + len > ((size_t)1 << n_)) return fail(Q1T_ERR_INVALID_ARGUMENT, "amplitude range out of bounds");
+    int rc = flush();
+    if (rc) return rc;
+    rc = materialize(cols_[col]);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(cols_[col].buf + offset, in, sizeof(double2) * len, cudaMemcpyHostToDevice, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+int DeviceVectorState::set_option(const char *key, long value)
+{
+    if (!key) return fail(Q1T_ERR_INVALID_ARGUMENT, "NULL option key");
+    if (!std::strcmp(key, "tile_bits")) {
+        if (value < 8 || value > kMaxTileBits) return fail(Q1T_ERR_INVALID_ARGUMENT, "tile_bits must be in 8..13");
+        int rc = run_queue();
+        if (rc) return rc;
+        tile_bits_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "fuse")) {
+        int rc = run_queue();
+        if (rc) return rc;
+        rc = canonicalize();
+        if (rc) return rc;
+        fuse_ = value != 0;
+        return Q1T_OK;
+    }
+    return fail(Q1T_ERR_INVALID_ARGUMENT, std::string("unknown option ") + key);
+}
+
+}  // namespace q1t

@@ -1,0 +1,109 @@
+// engine.h -- DeviceVectorState: the HBM-resident replacement of the reference's
+// `VectorState` (vectorstate.rs:25-415), one method per `QuState` trait method.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/q1t_engine.h"
+#include "kernels.h"
+#include "planner.h"
+
+namespace q1t {
+
+// one branch column (vectorstate.rs:31-34: `counts[c]` shots share `states[.., c]`)
+struct Column {
+    double2 *buf = nullptr;     // 2^n amplitudes in HBM, or null for a lazy basis state
+    bool basis = false;         // unit vector |basis_idx> kept as an index (measure_all collapse)
+    uint64_t basis_idx = 0;
+    size_t count = 0;
+};
+
+class DeviceVectorState {
+public:
+    DeviceVectorState(size_t nr_bits, size_t nr_shots, int device);
+    ~DeviceVectorState();
+    int init_zero_state();
+    int init_from_qubit_coefs(const double *coefs);
+
+    int apply_gate(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc);
+    int apply_unary_gate_all(const double *mat, size_t dim, const char *desc);
+    int apply_conditional_gate(const uint8_t *control, size_t ncontrol, const double *mat, size_t dim,
+                               const size_t *bits, size_t k, const char *desc);
+    int measure_into(size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng, bool collapse);
+    int measure_all_into(const size_t *cbits, size_t ncbits, uint64_t *res, size_t res_len, q1t_rng rng, bool collapse);
+    int reset(size_t bit, q1t_rng rng);
+    int reset_all();
+
+    int counts(size_t *out);
+    size_t nr_columns() { return cols_.size(); }
+    int read_amplitudes(size_t col, size_t offset, size_t len, double *out);
+    int write_amplitudes(size_t col, size_t offset, size_t len, const double *in);
+    int marginal0(size_t qbit, double *w0_out);
+    int column_totals(double *out);
+    int flush();                 // run queued gates, restore canonical layout, synchronise
+    int set_option(const char *key, long value);
+
+    size_t nr_bits() const { return n_; }
+    size_t nr_shots() const { return shots_; }
+    const char *last_error() const { return err_.c_str(); }
+    q1t_stats stats{};
+    bool timing = false;
+
+private:
+    int n_;
+    size_t shots_;
+    int device_;
+    cudaStream_t stream_ = nullptr;
+    std::vector<Column> cols_;
+    std::vector<int> perm_;                  // logical index bit -> physical position
+    std::vector<LoweredGate> queue_;         // gates waiting for the next fused flush
+    std::vector<int> queue_cols_;            // column subset of the queue (empty = all)
+    std::vector<double2 *> free_bufs_;
+    std::string err_;
+    long tile_bits_ = 12;
+    bool fuse_ = true;
+
+    // device scratch
+    double2 **d_colptrs_ = nullptr; size_t colptrs_cap_ = 0;
+    PhaseTab *d_ptabs_ = nullptr;
+    double *d_leaf_ = nullptr; size_t leaf_cap_ = 0;
+    double *d_block_ = nullptr; size_t block_cap_ = 0;
+    double *d_totals_ = nullptr; size_t totals_cap_ = 0;
+    double *d_chosen_ = nullptr; uint64_t *d_idx_ = nullptr; size_t draws_cap_ = 0;
+    double2 *d_mat_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+
+    int fail(int code, const std::string &msg) { err_ = msg; return code; }
+    int cuda_fail(cudaError_t e, const char *what);
+    int ensure_device();
+    int alloc_column(double2 **out);
+    void release_column(double2 *p);
+    int materialize(Column &c);
+    int upload_colptrs(const std::vector<int> &which);
+    int run_queue();                         // lower queue -> sweeps -> launches
+    int run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which);
+    int run_generic(const LoweredGate &g, const std::vector<int> &which);
+    int canonicalize();                      // undo swap relabelling (perm_ -> identity)
+    int reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols);
+    int ensure_scratch(size_t ncols);
+    int lower_and_queue(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc);
+    void time_begin();
+    void time_end(double &acc);
+};
+
+// host sampling helpers (sampling.cpp): rand 0.7 Uniform / rand_distr 0.2 Binomial restated
+struct UniformF64 { double low, scale; };
+UniformF64 uniform_new(double low, double high);
+double uniform_sample(const UniformF64 &u, q1t_rng rng);
+uint64_t binomial_sample(q1t_rng rng, uint64_t n, double p);
+bool rng_failed(q1t_rng rng);    // true if a built-in injected generator ran dry
+
+// gate table (gates.cpp)
+int builtin_gate_matrix(const char *name, const double *params, size_t nparams, std::complex<double> *out);
+
+}  // namespace q1t

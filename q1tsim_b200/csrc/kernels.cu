@@ -1,0 +1,579 @@
+// kernels.cu -- sm_100a kernels of the statevector engine.
+//
+//  sweep_kernel        fused gate application: one HBM read + one HBM write per
+//                      amplitude, gates applied in registers / shared memory
+//                      (replaces gates.rs:121-152 + Gate::apply_mat_slice
+//                      gates.rs:273-326, one sweep per *group* of gates).
+//  generic_gate_kernel unfused k-target dense gate with controls (fallback for
+//                      what the sweep kernel cannot express).
+//  leaf_totals / block_scan / top_chain / resolve_draws
+//                      canonical-order |amp|^2 reductions, prefix scan and
+//                      batched weighted sampling (vectorstate.rs:119-133,
+//                      249-261).
+//  collapse_kernel     zero one half + renormalise, 1 read -> 1 or 2 columns
+//                      (vectorstate.rs:91-104, 299-320).
+//
+// All data is complex128 = double2, HBM-resident, one contiguous buffer of
+// 2^n amplitudes per branch column.
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace q1t {
+
+__constant__ SweepProgram c_prog;
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ void st_global_cs(double2 *p, double2 v)
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// insert a zero bit at position J into p
+template <int J>
+__device__ __forceinline__ constexpr int ins0(int p)
+{
+    return ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
+}
+
+// ---------------------------------------------------------------------------
+// register-level ops on the 2^R amplitudes of one thread
+// ---------------------------------------------------------------------------
+template <int J>
+__device__ __forceinline__ void g1_generic(double2 (&a)[kSlots], const OpDesc &op)
+{
+    const double m00r = op.m[0], m00i = op.m[1], m01r = op.m[2], m01i = op.m[3];
+    const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6], m11i = op.m[7];
+    const unsigned cs = op.cslot;
+#pragma unroll
+    for (int p = 0; p < kSlots / 2; ++p) {
+        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
+        if ((s0 & cs) == cs) {
+            const double2 x = a[s0], y = a[s1];
+            double2 u, v;
+            u.x = fma(m00r, x.x, fma(-m00i, x.y, fma(m01r, y.x, -(m01i * y.y))));
+            u.y = fma(m00r, x.y, fma(m00i, x.x, fma(m01r, y.y, m01i * y.x)));
+            v.x = fma(m10r, x.x, fma(-m10i, x.y, fma(m11r, y.x, -(m11i * y.y))));
+            v.y = fma(m10r, x.y, fma(m10i, x.x, fma(m11r, y.y, m11i * y.x)));
+            a[s0] = u;
+            a[s1] = v;
+        }
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void g1_hadamard(double2 (&a)[kSlots], const OpDesc &op)
+{
+    const double c = op.m[0];
+    const unsigned cs = op.cslot;
+#pragma unroll
+    for (int p = 0; p < kSlots / 2; ++p) {
+        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
+        if ((s0 & cs) == cs) {
+            const double2 x = a[s0], y = a[s1];
+            a[s0] = make_double2((x.x + y.x) * c, (x.y + y.y) * c);
+            a[s1] = make_double2((x.x - y.x) * c, (x.y - y.y) * c);
+        }
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void g1_antidiag(double2 (&a)[kSlots], const OpDesc &op)
+{
+    const double2 m01 = make_double2(op.m[2], op.m[3]), m10 = make_double2(op.m[4], op.m[5]);
+    const unsigned cs = op.cslot;
+#pragma unroll
+    for (int p = 0; p < kSlots / 2; ++p) {
+        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
+        if ((s0 & cs) == cs) {
+            const double2 x = a[s0], y = a[s1];
+            a[s0] = cmul(m01, y);
+            a[s1] = cmul(m10, x);
+        }
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void g1_swapx(double2 (&a)[kSlots], const OpDesc &op)
+{
+    const unsigned cs = op.cslot;
+#pragma unroll
+    for (int p = 0; p < kSlots / 2; ++p) {
+        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
+        if ((s0 & cs) == cs) {
+            const double2 x = a[s0];
+            a[s0] = a[s1];
+            a[s1] = x;
+        }
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void g1_diag(double2 (&a)[kSlots], const OpDesc &op)
+{
+    const double2 m00 = make_double2(op.m[0], op.m[1]), m11 = make_double2(op.m[6], op.m[7]);
+    const unsigned cs = op.cslot;
+#pragma unroll
+    for (int p = 0; p < kSlots / 2; ++p) {
+        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
+        if ((s0 & cs) == cs) {
+            a[s0] = cmul(m00, a[s0]);
+            a[s1] = cmul(m11, a[s1]);
+        }
+    }
+}
+
+// PHASE: slots with bit J set are multiplied by F * prod_{other slot bits set} q[i];
+// optionally every slot is multiplied by the constant c0 (a global phase term).
+template <int J>
+__device__ __forceinline__ void phase_apply(double2 (&a)[kSlots], const OpDesc &op, double2 F)
+{
+    double2 f[kSlots / 2];
+    f[0] = F;
+    // other slot bits in ascending order; index u enumerates their subsets
+#pragma unroll
+    for (int i = 0; i < kRegBits - 1; ++i) {
+        if (op.flags & (1u << i)) {
+            const double2 q = make_double2(op.m[2 * i], op.m[2 * i + 1]);
+#pragma unroll
+            for (int u = 0; u < (1 << i); ++u) f[u | (1 << i)] = cmul(f[u], q);
+        } else {
+#pragma unroll
+            for (int u = 0; u < (1 << i); ++u) f[u | (1 << i)] = f[u];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kSlots / 2; ++u) {
+        const int s1 = ins0<J>(u) | (1 << J);
+        a[s1] = cmul(a[s1], f[u]);
+    }
+    if (op.flags & 8u) {
+        const double2 c0 = make_double2(op.m[6], op.m[7]);
+#pragma unroll
+        for (int u = 0; u < kSlots / 2; ++u) {
+            const int s0 = ins0<J>(u);
+            a[s0] = cmul(a[s0], c0);
+        }
+    }
+}
+
+#define Q1T_DISPATCH_J(fn, ...)          \
+    switch (op.j) {                      \
+    case 0: fn<0>(__VA_ARGS__); break;   \
+    case 1: fn<1>(__VA_ARGS__); break;   \
+    case 2: fn<2>(__VA_ARGS__); break;   \
+    default: fn<3>(__VA_ARGS__); break;  \
+    }
+
+// ---------------------------------------------------------------------------
+// the sweep kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
+             const PhaseTab *__restrict__ ptabs)
+{
+    extern __shared__ double2 tile[];
+    __shared__ double2 s_tileF[kMaxPhase];
+
+    const SweepProgram &P = c_prog;
+    const int T = P.T, TB = P.TB;
+    const unsigned tid = threadIdx.x;
+    const unsigned long long o = blockIdx.x;
+    const int col = blockIdx.y;
+
+    // tile base offsets in the source / destination layout
+    unsigned long long sbase = 0, dbase = 0;
+    for (int i = 0; i < P.n_outer; ++i) {
+        const unsigned long long b = (o >> i) & 1ull;
+        sbase |= b << P.osrc[i];
+        dbase |= b << P.odst[i];
+    }
+    unsigned long long soff_lo = 0;
+    for (int i = 0; i < TB; ++i) soff_lo |= (unsigned long long)((tid >> i) & 1u) << P.tsrc[i];
+
+    // ---- load the tile (coalesced: consecutive tid -> consecutive source addresses) ----
+    const double2 *__restrict__ src = src_cols[col] + sbase + soff_lo;
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i) {
+        const unsigned e = tid | ((unsigned)i << TB);
+        cp_async16(&tile[tile_swizzle(e)], src + P.ld_hi[i]);
+    }
+    // per-tile phase factors (depend on the outer index bits only)
+    for (int pid = tid; pid < P.nphase; pid += blockDim.x) {
+        const PhaseTab &pt = ptabs[pid];
+        double ang = pt.base;
+        for (int i = 0; i < P.n_outer; ++i)
+            if ((o >> i) & 1ull) ang += pt.outer_coef[i];
+        double s, c;
+        sincospi(ang, &s, &c);
+        s_tileF[pid] = make_double2(c, s);
+    }
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    const unsigned long long vhi = o << T;
+    for (int r = 0; r < P.nrounds; ++r) {
+        const RoundDesc &R = P.rounds[r];
+        unsigned thrL = 0;
+        for (int i = 0; i < TB; ++i) thrL |= ((tid >> i) & 1u) << R.thr_tb[i];
+        const unsigned swT = tile_swizzle(thrL);
+        double2 a[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) a[s] = tile[swT ^ R.sw_slot[s]];
+        const unsigned long long vbase = vhi | thrL;
+
+        for (int k = R.op_begin; k < R.op_end; ++k) {
+            const OpDesc &op = P.ops[k];
+            if (op.kind == OP_PHASE) {
+                const PhaseTab &pt = ptabs[op.phase_id];
+                const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
+                const double2 lo = make_double2(__ldg(&pt.lo[2 * il]), __ldg(&pt.lo[2 * il + 1]));
+                const double2 hi = make_double2(__ldg(&pt.hi[2 * ih]), __ldg(&pt.hi[2 * ih + 1]));
+                const double2 F = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
+                Q1T_DISPATCH_J(phase_apply, a, op, F)
+            } else {
+                if ((vbase & op.cmask) != op.cmask) continue;
+                switch (op.kind) {
+                case OP_G1_HADAMARD: Q1T_DISPATCH_J(g1_hadamard, a, op) break;
+                case OP_G1_ANTIDIAG: Q1T_DISPATCH_J(g1_antidiag, a, op) break;
+                case OP_G1_SWAPX: Q1T_DISPATCH_J(g1_swapx, a, op) break;
+                case OP_G1_DIAG: Q1T_DISPATCH_J(g1_diag, a, op) break;
+                default: Q1T_DISPATCH_J(g1_generic, a, op) break;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) tile[swT ^ R.sw_slot[s]] = a[s];
+        __syncthreads();
+    }
+
+    // ---- store the tile (coalesced in the destination layout) ----
+    unsigned long long doff_lo = 0;
+    unsigned l_lo = 0;
+    for (int i = 0; i < TB; ++i) {
+        const unsigned b = (tid >> i) & 1u;
+        const int tb = P.st_tb[i];
+        doff_lo |= (unsigned long long)b << P.tdst[tb];
+        l_lo |= b << tb;
+    }
+    double2 *__restrict__ dst = dst_cols[col] + dbase + doff_lo;
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i) {
+        const unsigned l = l_lo | P.st_l_hi[i];
+        st_global_cs(dst + P.st_off_hi[i], tile[tile_swizzle(l)]);
+    }
+}
+
+cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
+                         int ncols, const PhaseTab *d_ptabs, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    const size_t smem = sizeof(double2) << prog.T;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << kMaxTileBits));
+        if (e != cudaSuccess) return e;
+        smem_set = sizeof(double2) << kMaxTileBits;
+    }
+    dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
+    dim3 block(1u << prog.TB, 1, 1);
+    sweep_kernel<<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// generic (unfused) gate: one thread per group of 2^k amplitudes
+// ---------------------------------------------------------------------------
+__global__ void generic_gate_kernel(double2 *const *__restrict__ cols, int n, int k, GenericGateArgs g,
+                                    const double2 *__restrict__ mat)
+{
+    const unsigned long long ngroups = 1ull << (n - k);
+    double2 *__restrict__ st = cols[blockIdx.y];
+    const int G = 1 << k;
+    for (unsigned long long grp = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; grp < ngroups;
+         grp += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long base = grp;
+        for (int a = 0; a < k; ++a) {
+            const int p = g.sorted_pos[a];
+            base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
+        }
+        if ((base & g.cmask) != g.cmask) continue;
+        double2 in[1 << kMaxGenericBits];
+        for (int h = 0; h < G; ++h) in[h] = st[base | g.offs[h]];
+        for (int i = 0; i < G; ++i) {
+            double2 acc = make_double2(0.0, 0.0);
+            for (int h = 0; h < G; ++h) {
+                const double2 m = mat[i * G + h];
+                acc.x = fma(in[h].x, m.x, fma(-in[h].y, m.y, acc.x));
+                acc.y = fma(in[h].x, m.y, fma(in[h].y, m.x, acc.y));
+            }
+            st[base | g.offs[i]] = acc;
+        }
+    }
+}
+
+cudaError_t launch_generic_gate(double2 *const *d_cols, int ncols, int n, int k, const GenericGateArgs &g,
+                                const double2 *d_mat, cudaStream_t stream)
+{
+    const unsigned long long ngroups = 1ull << (n - k);
+    unsigned blocks = (unsigned)((ngroups + 127) / 128);
+    if (blocks > 148u * 32u) blocks = 148u * 32u;
+    if (blocks == 0) blocks = 1;
+    generic_gate_kernel<<<dim3(blocks, ncols), 128, 0, stream>>>(d_cols, n, k, g, d_mat);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// canonical-order reductions (DESIGN.md "canonical reduction order")
+//   leaf  = min(2^n, 1024) consecutive amplitudes, one warp per leaf:
+//           lane l accumulates elements l, l+32, ... sequentially, then a
+//           5-stage xor butterfly (16, 8, 4, 2, 1);  p = fl(fl(re*re)+fl(im*im))
+//   block = 1024 leaves chained sequentially; block totals chained sequentially
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double norm_sqr_rn(double2 v)
+{
+    return __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
+}
+
+__global__ void __launch_bounds__(256)
+leaf_totals_kernel(const double2 *const *__restrict__ cols, double *__restrict__ leaf_out, int n, int leaf_bits,
+                   unsigned long long mask, unsigned long long want)
+{
+    const unsigned long long nleaves = 1ull << (n - leaf_bits);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const double2 *__restrict__ st = cols[blockIdx.y];
+    double *__restrict__ out = leaf_out + (unsigned long long)blockIdx.y * nleaves;
+    const int leaf = 1 << leaf_bits;
+    for (unsigned long long L = warp; L < nleaves; L += nwarps) {
+        const unsigned long long first = L << leaf_bits;
+        double acc = 0.0;
+        // whole leaf masked out (mask bit above the leaf): total is exactly +0.0, skip the reads
+        const unsigned long long hi_mask = mask & ~((unsigned long long)leaf - 1ull);
+        if ((first & hi_mask) == (want & hi_mask)) {
+            if (leaf >= 32) {
+#pragma unroll 8
+                for (int t = 0; t < leaf; t += 32) {
+                    const unsigned long long idx = first + t + lane;
+                    if ((idx & mask) == want) acc = __dadd_rn(acc, norm_sqr_rn(__ldcs(&st[idx])));
+                }
+            } else if (lane < leaf) {
+                const unsigned long long idx = first + lane;
+                if ((idx & mask) == want) acc = __dadd_rn(acc, norm_sqr_rn(st[idx]));
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+        if (lane == 0) out[L] = acc;
+    }
+}
+
+// one warp per block of 1024 leaves: stage into shared memory, lane 0 chains sequentially
+__global__ void __launch_bounds__(128)
+block_scan_kernel(double *__restrict__ leaf_io, double *__restrict__ block_totals, unsigned long long nleaves,
+                  unsigned long long nblocks)
+{
+    __shared__ double s[4][kCanonBlock];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long b = blockIdx.x * 4ull + w;
+    double *__restrict__ leaf = leaf_io + (unsigned long long)blockIdx.y * nleaves;
+    if (b < nblocks) {
+        const unsigned long long first = b * kCanonBlock;
+        const unsigned long long cnt = (nleaves - first) < kCanonBlock ? (nleaves - first) : kCanonBlock;
+        for (unsigned i = lane; i < cnt; i += 32) s[w][i] = leaf[first + i];
+        __syncwarp();
+        if (lane == 0) {
+            double run = 0.0;
+            for (unsigned i = 0; i < cnt; ++i) {
+                run = __dadd_rn(run, s[w][i]);
+                s[w][i] = run;
+            }
+            block_totals[(unsigned long long)blockIdx.y * nblocks + b] = run;
+        }
+        __syncwarp();
+        for (unsigned i = lane; i < cnt; i += 32) leaf[first + i] = s[w][i];
+    }
+}
+
+// one thread per column: inclusive chain over block totals (in place)
+__global__ void top_chain_kernel(double *__restrict__ block_io, unsigned long long nblocks, int ncols,
+                                 double *__restrict__ totals_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double *__restrict__ bt = block_io + (unsigned long long)c * nblocks;
+    double run = 0.0;
+    for (unsigned long long b = 0; b < nblocks; ++b) {
+        run = __dadd_rn(run, bt[b]);
+        bt[b] = run;
+    }
+    totals_out[c] = run;
+}
+
+__device__ __forceinline__ double leaf_prefix(const double *__restrict__ inblock, const double *__restrict__ bpref,
+                                              unsigned long long L)
+{
+    const unsigned long long b = L / kCanonBlock;
+    return __dadd_rn(b ? bpref[b - 1] : 0.0, inblock[L]);
+}
+
+// one thread per draw (draws sorted ascending on the host): leaf by binary
+// search over the canonical leaf prefixes, then a sequential in-leaf scan.
+__global__ void resolve_draws_kernel(const double2 *__restrict__ st, const double *__restrict__ inblock,
+                                     const double *__restrict__ bpref, int n, int leaf_bits,
+                                     const double *__restrict__ chosen, unsigned long long ndraws,
+                                     unsigned long long *__restrict__ idx_out)
+{
+    const unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (j >= ndraws) return;
+    const double ch = chosen[j];
+    const unsigned long long nleaves = 1ull << (n - leaf_bits);
+    unsigned long long lo = 0, hi = nleaves - 1;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (leaf_prefix(inblock, bpref, mid) <= ch) lo = mid + 1; else hi = mid;
+    }
+    double run = lo == 0 ? 0.0 : leaf_prefix(inblock, bpref, lo - 1);
+    const unsigned leaf = 1u << leaf_bits;
+    const double2 *__restrict__ p = st + (lo << leaf_bits);
+    unsigned found = 0xffffffffu, last_nz = 0xffffffffu;
+    for (unsigned e0 = 0; e0 < leaf && found == 0xffffffffu; e0 += 8) {
+        double w[8];
+        const unsigned m = (leaf - e0) < 8u ? (leaf - e0) : 8u;
+#pragma unroll
+        for (unsigned q = 0; q < 8; ++q) w[q] = q < m ? norm_sqr_rn(p[e0 + q]) : 0.0;
+#pragma unroll
+        for (unsigned q = 0; q < 8; ++q) {
+            if (q < m && found == 0xffffffffu) {
+                if (w[q] > 0.0) last_nz = e0 + q;
+                run = __dadd_rn(run, w[q]);
+                if (ch < run) found = e0 + q;
+            }
+        }
+    }
+    if (found == 0xffffffffu) found = last_nz == 0xffffffffu ? leaf - 1 : last_nz;
+    idx_out[j] = (lo << leaf_bits) + found;
+}
+
+cudaError_t launch_leaf_totals(const double2 *const *d_cols, int ncols, double *d_leaf, int n,
+                               unsigned long long mask, unsigned long long want, cudaStream_t stream)
+{
+    const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
+    const unsigned long long nleaves = 1ull << (n - leaf_bits);
+    unsigned long long blocks = (nleaves + 7) / 8;      // 8 warps per CTA
+    if (blocks > 148ull * 64ull) blocks = 148ull * 64ull;
+    leaf_totals_kernel<<<dim3((unsigned)blocks, ncols), 256, 0, stream>>>(d_cols, d_leaf, n, leaf_bits, mask, want);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int ncols, int n, cudaStream_t stream)
+{
+    const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
+    const unsigned long long nleaves = 1ull << (n - leaf_bits);
+    const unsigned long long nblocks = (nleaves + kCanonBlock - 1) / kCanonBlock;
+    block_scan_kernel<<<dim3((unsigned)((nblocks + 3) / 4), ncols), 128, 0, stream>>>(d_leaf, d_block, nleaves, nblocks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    top_chain_kernel<<<(ncols + 63) / 64, 64, 0, stream>>>(d_block, nblocks, ncols, d_totals);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_draws(const double2 *d_col, const double *d_leaf, const double *d_block, int n,
+                                 const double *d_chosen, unsigned long long ndraws, unsigned long long *d_idx,
+                                 cudaStream_t stream)
+{
+    if (ndraws == 0) return cudaSuccess;
+    const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
+    resolve_draws_kernel<<<(unsigned)((ndraws + 63) / 64), 64, 0, stream>>>(d_col, d_leaf, d_block, n, leaf_bits, d_chosen,
+                                                                         ndraws, d_idx);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// collapse: out0 keeps the bit==0 half scaled by f0, out1 keeps the bit==1
+// half scaled by f1 (either may be null); everything else is zero.
+// vectorstate.rs:91-104 multiplies by Complex(1/sqrt(w), 0): both parts scaled.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+collapse_kernel(const double2 *in, double2 *out0, double2 *out1,   // in may alias out0 or out1
+                unsigned long long N, unsigned long long bit, double f0, double f1)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < N;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2 v = in[i];
+        const bool one = (i & bit) != 0;
+        // (re*f - im*0, re*0 + im*f) as num-complex does; +0.0 terms dropped
+        const double2 z = make_double2(0.0, 0.0);
+        if (out0) out0[i] = one ? z : make_double2(__dmul_rn(v.x, f0), __dmul_rn(v.y, f0));
+        if (out1) out1[i] = one ? make_double2(__dmul_rn(v.x, f1), __dmul_rn(v.y, f1)) : z;
+    }
+}
+
+cudaError_t launch_collapse(const double2 *d_in, double2 *d_out0, double2 *d_out1, int n, int bitpos, double f0,
+                            double f1, cudaStream_t stream)
+{
+    const unsigned long long N = 1ull << n;
+    unsigned long long blocks = (N + 255) / 256;
+    if (blocks > 148ull * 16ull) blocks = 148ull * 16ull;
+    collapse_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_in, d_out0, d_out1, N, 1ull << bitpos, f0, f1);
+    return cudaGetLastError();
+}
+
+// product state of per-qubit coefficient pairs, same multiplication chain as
+// vectorstate.rs:62-83 / cmatrix.rs:40-51 (kron_mat): cur = b_q[bit_q] * cur,
+// textbook complex product without FMA contraction.
+__global__ void product_state_kernel(double2 *__restrict__ st, int n, const double2 *__restrict__ coefs)
+{
+    const unsigned long long N = 1ull << n;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < N;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        double2 cur = make_double2(1.0, 0.0);
+        for (int q = 0; q < n; ++q) {
+            const int bit = (int)((i >> (n - 1 - q)) & 1ull);
+            const double2 b = coefs[2 * q + bit];
+            const double re = __dsub_rn(__dmul_rn(b.x, cur.x), __dmul_rn(b.y, cur.y));
+            const double im = __dadd_rn(__dmul_rn(b.x, cur.y), __dmul_rn(b.y, cur.x));
+            cur = make_double2(re, im);
+        }
+        st[i] = cur;
+    }
+}
+cudaError_t launch_product_state(double2 *d_col, int n, const double2 *d_coefs, cudaStream_t stream)
+{
+    const unsigned long long N = 1ull << n;
+    unsigned long long blocks = (N + 255) / 256;
+    if (blocks > 148ull * 16ull) blocks = 148ull * 16ull;
+    product_state_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_col, n, d_coefs);
+    return cudaGetLastError();
+}
+
+__global__ void set_basis_kernel(double2 *__restrict__ st, unsigned long long idx)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) st[idx] = make_double2(1.0, 0.0);
+}
+cudaError_t launch_set_basis(double2 *d_col, unsigned long long idx, cudaStream_t stream)
+{
+    set_basis_kernel<<<1, 32, 0, stream>>>(d_col, idx);
+    return cudaGetLastError();
+}
+
+}  // namespace q1t

@@ -1,0 +1,35 @@
+// kernels.h -- host-callable launchers of kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace q1t {
+
+constexpr int kMaxGenericBits = 6;       // dense fallback: up to 64x64 matrices
+constexpr int kCanonLeafBits = 10;       // canonical reduction: leaves of 1024 amplitudes
+constexpr unsigned kCanonBlock = 1024;   // leaves per chained block
+
+struct GenericGateArgs {
+    int sorted_pos[kMaxGenericBits];                  // target positions ascending
+    unsigned long long offs[1 << kMaxGenericBits];    // index offset of gate-matrix index g
+    unsigned long long cmask;                         // control positions that must be 1
+};
+
+cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
+                         int ncols, const PhaseTab *d_ptabs, cudaStream_t stream);
+cudaError_t launch_generic_gate(double2 *const *d_cols, int ncols, int n, int k, const GenericGateArgs &g,
+                                const double2 *d_mat, cudaStream_t stream);
+cudaError_t launch_leaf_totals(const double2 *const *d_cols, int ncols, double *d_leaf, int n,
+                               unsigned long long mask, unsigned long long want, cudaStream_t stream);
+cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int ncols, int n, cudaStream_t stream);
+cudaError_t launch_resolve_draws(const double2 *d_col, const double *d_leaf, const double *d_block, int n,
+                                 const double *d_chosen, unsigned long long ndraws, unsigned long long *d_idx,
+                                 cudaStream_t stream);
+cudaError_t launch_collapse(const double2 *d_in, double2 *d_out0, double2 *d_out1, int n, int bitpos, double f0,
+                            double f1, cudaStream_t stream);
+cudaError_t launch_product_state(double2 *d_col, int n, const double2 *d_coefs, cudaStream_t stream);
+cudaError_t launch_set_basis(double2 *d_col, unsigned long long idx, cudaStream_t stream);
+
+}  // namespace q1t

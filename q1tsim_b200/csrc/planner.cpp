@@ -1,0 +1,523 @@
+// planner.cpp -- gate lowering + fusion planner (host only).
+//
+// Lowering consumes only `Gate::matrix()` (gates.rs:174), as SURVEY 8(b)
+// prescribes: user gates define nothing else.  The unitary is classified into
+//   POLY    diagonal 1/2-qubit unitary  -> phase polynomial (Z,S,T,RZ,U1,CZ,CS,CT,CU1,CRZ..)
+//   G1      [controls] + one non-diagonal 2x2 target (H,X,Y,V,RX,RY,U2,U3,CX,CCX,CH,CU3..)
+//   SWAP    qubit relabel, zero bytes moved (swap.rs:78-88)
+//   GENERIC anything else (dense k-target block), unfused fallback kernel
+#include "planner.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace q1t {
+
+double wrap_half_turns(double a)
+{
+    if (a >= -1.0 && a < 1.0) return a;
+    double r = std::fmod(a, 2.0);      // exact
+    if (r >= 1.0) r -= 2.0;
+    if (r < -1.0) r += 2.0;
+    return r;
+}
+
+static void sincospi_host(double a, double &s, double &c)
+{
+    a = wrap_half_turns(a);
+    const double t = 2.0 * a;          // exact multiples of 1/2 turn-halves get exact values
+    if (t == std::floor(t)) {
+        const int q = ((int)t % 4 + 4) % 4;
+        static const double cs[4] = { 1, 0, -1, 0 }, sn[4] = { 0, 1, 0, -1 };
+        c = cs[q]; s = sn[q];
+        return;
+    }
+    s = std::sin(M_PI * a);
+    c = std::cos(M_PI * a);
+}
+
+static inline uint64_t deposit(uint64_t v, const int *positions, int nbits)
+{
+    uint64_t r = 0;
+    for (int i = 0; i < nbits; ++i) r |= ((v >> i) & 1ull) << positions[i];
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// lowering
+// ---------------------------------------------------------------------------
+bool lower_gate(const cplx *mat, int k, const int *phys, LoweredGate &out, std::string &err)
+{
+    out = LoweredGate();
+    const int G = 1 << k;
+    for (int a = 0; a < k; ++a)
+        for (int b = a + 1; b < k; ++b)
+            if (phys[a] == phys[b]) { err = "duplicate qubit index in gate bits"; return false; }
+
+    bool diagonal = true;
+    for (int r = 0; r < G && diagonal; ++r)
+        for (int c = 0; c < G; ++c)
+            if (r != c && (mat[r * G + c].real() != 0.0 || mat[r * G + c].imag() != 0.0)) { diagonal = false; break; }
+
+    if (diagonal && k <= 2) {
+        bool unit = true;
+        double a[4] = { 0, 0, 0, 0 };
+        for (int g = 0; g < G; ++g) {
+            const double mod = std::abs(mat[g * G + g]);
+            if (std::fabs(mod - 1.0) > 1e-9) unit = false;
+            a[g] = std::atan2(mat[g * G + g].imag(), mat[g * G + g].real()) / M_PI;
+        }
+        if (unit) {
+            out.kind = LoweredGate::POLY;
+            out.nb = k;
+            if (k == 1) {
+                out.b[0] = phys[0];
+                out.c0 = wrap_half_turns(a[0]);
+                out.lin[0] = wrap_half_turns(a[1] - a[0]);
+            } else {
+                out.b[0] = phys[0]; out.b[1] = phys[1];
+                out.c0 = wrap_half_turns(a[0]);
+                out.lin[0] = wrap_half_turns(a[2] - a[0]);
+                out.lin[1] = wrap_half_turns(a[1] - a[0]);
+                out.quad = wrap_half_turns(a[3] - a[2] - a[1] + a[0]);
+            }
+            return true;
+        }
+    }
+
+    // control extraction
+    std::vector<int> act(k);
+    for (int j = 0; j < k; ++j) act[j] = j;
+    std::vector<cplx> M(mat, mat + (size_t)G * G);
+    uint64_t cmask = 0;
+    int last_ctl = -1;
+    bool found = true;
+    while (found && !act.empty()) {
+        found = false;
+        const int na = (int)act.size(), D = 1 << na;
+        for (int a = 0; a < na && !found; ++a) {
+            const int bit = 1 << (na - 1 - a);
+            bool ctl = true;
+            for (int r = 0; r < D && ctl; ++r)
+                for (int c = 0; c < D; ++c) {
+                    if ((r & bit) && (c & bit)) continue;
+                    const cplx e = M[(size_t)r * D + c];
+                    const double want = r == c ? 1.0 : 0.0;
+                    if (e.real() != want || e.imag() != 0.0) { ctl = false; break; }
+                }
+            if (!ctl) continue;
+            // reduce to the bit==1 block
+            std::vector<cplx> M2((size_t)(D / 2) * (D / 2));
+            int rr = 0;
+            for (int r = 0; r < D; ++r) {
+                if (!(r & bit)) continue;
+                int cc = 0;
+                for (int c = 0; c < D; ++c) {
+                    if (!(c & bit)) continue;
+                    M2[(size_t)rr * (D / 2) + cc] = M[(size_t)r * D + c];
+                    ++cc;
+                }
+                ++rr;
+            }
+            M.swap(M2);
+            cmask |= 1ull << phys[act[a]];
+            last_ctl = act[a];
+            act.erase(act.begin() + a);
+            found = true;
+        }
+    }
+    if (act.empty()) {
+        const cplx s = M[0];
+        if (s.real() == 1.0 && s.imag() == 0.0) {   // identity gate
+            out.kind = LoweredGate::POLY;
+            out.nb = 0;
+            return true;
+        }
+        // all bits were controls of a scalar phase: make the last one the target of diag(1, s)
+        out.kind = LoweredGate::G1;
+        out.target = phys[last_ctl];
+        out.cmask = cmask & ~(1ull << phys[last_ctl]);
+        const double mm[8] = { 1, 0, 0, 0, 0, 0, s.real(), s.imag() };
+        std::memcpy(out.m, mm, sizeof mm);
+        return true;
+    }
+    if (act.size() == 1) {
+        out.kind = LoweredGate::G1;
+        out.target = phys[act[0]];
+        out.cmask = cmask;
+        for (int e = 0; e < 4; ++e) { out.m[2 * e] = M[e].real(); out.m[2 * e + 1] = M[e].imag(); }
+        return true;
+    }
+    if (act.size() == 2 && cmask == 0) {
+        static const double sw[16] = { 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1 };
+        bool is_swap = true;
+        for (int e = 0; e < 16; ++e)
+            if (M[e].real() != sw[e] || M[e].imag() != 0.0) is_swap = false;
+        if (is_swap) {
+            out.kind = LoweredGate::SWAP;
+            out.b[0] = phys[act[0]]; out.b[1] = phys[act[1]];
+            return true;
+        }
+    }
+    if ((int)act.size() > 6) { err = "dense gate blocks on more than 6 target qubits are not supported"; return false; }
+    out.kind = LoweredGate::GENERIC;
+    out.cmask = cmask;
+    for (int a : act) out.pos.push_back(phys[a]);
+    out.mat = M;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// pending diagonal terms
+// ---------------------------------------------------------------------------
+bool PendingDiag::touches(int t) const
+{
+    if (lin[t] != 0.0) return true;
+    for (int p = 0; p < n; ++p)
+        if (quad[(size_t)t * n + p] != 0.0) return true;
+    return false;
+}
+bool PendingDiag::empty() const
+{
+    if (c0 != 0.0) return false;
+    for (int t = 0; t < n; ++t)
+        if (touches(t)) return false;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// planner
+// ---------------------------------------------------------------------------
+Planner::Planner(int n, int tile_bits) : n_(n), T_(std::min(tile_bits, n))
+{
+    pd_.init(n);
+    open_sweep();
+}
+
+void Planner::open_sweep()
+{
+    tile_.clear();
+    rounds_.clear();
+    nops_ = nphase_ = 0;
+    for (int p = 0; p < 3 && p < n_; ++p) tile_.push_back(p);   // coalescing bits: 8 amplitudes = 128 B
+}
+
+bool Planner::in_tile(int p) const { return std::find(tile_.begin(), tile_.end(), p) != tile_.end(); }
+
+bool Planner::has_pending() const { return !rounds_.empty() || !pd_.empty(); }
+
+bool Planner::place_target(int t)
+{
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!rounds_.empty()) {
+            RoundB &r = rounds_.back();
+            if (std::find(r.regs.begin(), r.regs.end(), t) != r.regs.end()) return true;
+            if ((int)r.regs.size() < kRegBits && (in_tile(t) || (int)tile_.size() < T_)) {
+                if (!in_tile(t)) tile_.push_back(t);
+                r.regs.push_back(t);
+                return true;
+            }
+        }
+        if ((int)rounds_.size() < kMaxRounds && (in_tile(t) || (int)tile_.size() < T_)) {
+            if (!in_tile(t)) tile_.push_back(t);
+            RoundB r;
+            r.regs.push_back(t);
+            rounds_.push_back(r);
+            return true;
+        }
+        close_sweep();
+        open_sweep();
+    }
+    return false;
+}
+
+void Planner::emit_op(const OpB &op)
+{
+    rounds_.back().ops.push_back(op);
+    ++nops_;
+    if (op.is_phase) ++nphase_;
+}
+
+void Planner::emit_phase_for(int t)
+{
+    OpB op;
+    op.is_phase = true;
+    op.target = t;
+    op.base = pd_.lin[t];
+    for (int p = 0; p < n_; ++p) {
+        if (p == t) continue;
+        const double v = pd_.q(t, p);
+        if (v != 0.0) op.partners.push_back(std::make_pair(p, v));
+        pd_.q(t, p) = 0.0;
+        pd_.q(p, t) = 0.0;
+    }
+    pd_.lin[t] = 0.0;
+    if (pd_.c0 != 0.0) { op.has_c0 = true; op.c0 = pd_.c0; pd_.c0 = 0.0; }
+    if (op.base == 0.0 && op.partners.empty() && !op.has_c0) return;
+    emit_op(op);
+}
+
+void Planner::add(const LoweredGate &g)
+{
+    if (g.kind == LoweredGate::POLY) {
+        pd_.c0 = wrap_half_turns(pd_.c0 + g.c0);
+        for (int i = 0; i < g.nb; ++i) pd_.lin[g.b[i]] = wrap_half_turns(pd_.lin[g.b[i]] + g.lin[i]);
+        if (g.nb == 2 && g.quad != 0.0) {
+            const double v = wrap_half_turns(pd_.q(g.b[0], g.b[1]) + g.quad);
+            pd_.q(g.b[0], g.b[1]) = v;
+            pd_.q(g.b[1], g.b[0]) = v;
+        }
+        return;
+    }
+    // G1
+    const int t = g.target;
+    const size_t need_ops = 2;
+    if (nops_ + need_ops > (size_t)kMaxOps || nphase_ + 1 > (size_t)kMaxPhase) {
+        close_sweep();
+        open_sweep();
+    }
+    place_target(t);
+    if (pd_.touches(t)) emit_phase_for(t);
+    OpB op;
+    op.target = t;
+    op.cmask = g.cmask;
+    std::memcpy(op.m, g.m, sizeof op.m);
+    const double *m = g.m;
+    const bool real = m[1] == 0 && m[3] == 0 && m[5] == 0 && m[7] == 0;
+    if (real && m[0] == m[2] && m[0] == m[4] && m[0] == -m[6]) op.kind = OP_G1_HADAMARD;
+    else if (m[0] == 0 && m[1] == 0 && m[6] == 0 && m[7] == 0) {
+        op.kind = (m[2] == 1 && m[3] == 0 && m[4] == 1 && m[5] == 0) ? OP_G1_SWAPX : OP_G1_ANTIDIAG;
+    } else if (m[2] == 0 && m[3] == 0 && m[4] == 0 && m[5] == 0) op.kind = OP_G1_DIAG;
+    else op.kind = OP_G1_GENERIC;
+    emit_op(op);
+}
+
+void Planner::flush_diag_touching(uint64_t bits_mask)
+{
+    for (int t = 0; t < n_; ++t) {
+        if (!((bits_mask >> t) & 1ull)) continue;
+        if (!pd_.touches(t)) continue;
+        if (nops_ + 1 > (size_t)kMaxOps || nphase_ + 1 > (size_t)kMaxPhase) { close_sweep(); open_sweep(); }
+        place_target(t);
+        emit_phase_for(t);
+    }
+}
+
+void Planner::finish()
+{
+    for (;;) {
+        // pick the bit with the most pending partners; prefer one already in registers / the tile
+        int best = -1, best_score = -1;
+        for (int t = 0; t < n_; ++t) {
+            if (!pd_.touches(t)) continue;
+            int deg = 0;
+            for (int p = 0; p < n_; ++p)
+                if (p != t && pd_.q(t, p) != 0.0) ++deg;
+            int score = deg * 4;
+            if (!rounds_.empty() && std::find(rounds_.back().regs.begin(), rounds_.back().regs.end(), t) != rounds_.back().regs.end()) score += 3;
+            else if (in_tile(t)) score += 1;
+            if (score > best_score) { best_score = score; best = t; }
+        }
+        if (best < 0) break;
+        if (nops_ + 1 > (size_t)kMaxOps || nphase_ + 1 > (size_t)kMaxPhase) { close_sweep(); open_sweep(); }
+        place_target(best);
+        emit_phase_for(best);
+    }
+    if (pd_.c0 != 0.0) {
+        place_target(0);
+        emit_phase_for(0);
+    }
+    close_sweep();
+    open_sweep();
+}
+
+std::vector<PlannedSweep> Planner::take()
+{
+    std::vector<PlannedSweep> out;
+    out.swap(done_);
+    return out;
+}
+
+void Planner::close_sweep()
+{
+    if (rounds_.empty()) return;
+    PlannedSweep ps;
+    SweepProgram &P = ps.prog;
+    std::memset(&P, 0, sizeof P);
+    const int T = T_;
+    // pad the tile with the lowest unused positions
+    std::vector<int> tile = tile_;
+    for (int p = 0; p < n_ && (int)tile.size() < T; ++p)
+        if (std::find(tile.begin(), tile.end(), p) == tile.end()) tile.push_back(p);
+    std::sort(tile.begin(), tile.end());
+    std::vector<int> outer;
+    for (int p = 0; p < n_; ++p)
+        if (!std::binary_search(tile.begin(), tile.end(), p)) outer.push_back(p);
+    P.n = n_; P.T = T; P.TB = T - kRegBits; P.n_outer = n_ - T;
+    P.relabel = 0;
+    int tile_index[kMaxBits], outer_index[kMaxBits];
+    for (int p = 0; p < kMaxBits; ++p) { tile_index[p] = -1; outer_index[p] = -1; }
+    for (int i = 0; i < T; ++i) { P.tsrc[i] = P.tdst[i] = (uint8_t)tile[i]; tile_index[tile[i]] = i; P.st_tb[i] = (uint8_t)i; }
+    for (int i = 0; i < P.n_outer; ++i) { P.osrc[i] = P.odst[i] = (uint8_t)outer[i]; outer_index[outer[i]] = i; }
+    for (int i = 0; i < kSlots; ++i) {
+        uint64_t off = 0;
+        for (int b = 0; b < kRegBits; ++b)
+            if ((i >> b) & 1) off |= 1ull << tile[P.TB + b];
+        P.ld_hi[i] = off;
+        P.st_off_hi[i] = off;
+        P.st_l_hi[i] = (uint16_t)(i << P.TB);
+    }
+    P.nrounds = (int)rounds_.size();
+    int nops = 0, nphase = 0;
+    for (int r = 0; r < P.nrounds; ++r) {
+        RoundB &rb = rounds_[r];
+        RoundDesc &R = P.rounds[r];
+        // register bits as tile-bit indices, padded with the highest free tile bits
+        std::vector<int> regs;
+        for (int p : rb.regs) regs.push_back(tile_index[p]);
+        for (int tb = T - 1; tb >= 0 && (int)regs.size() < kRegBits; --tb)
+            if (std::find(regs.begin(), regs.end(), tb) == regs.end()) regs.push_back(tb);
+        std::sort(regs.begin(), regs.end());
+        int slot_of_tb[kMaxTileBits + 3];
+        for (int tb = 0; tb < T; ++tb) slot_of_tb[tb] = -1;
+        for (int j = 0; j < kRegBits; ++j) { R.reg_tb[j] = (uint8_t)regs[j]; slot_of_tb[regs[j]] = j; }
+        // thread bits: the first three should land in distinct shared-memory bank groups (tile bit mod 3)
+        std::vector<int> thr;
+        for (int tb = 0; tb < T; ++tb)
+            if (slot_of_tb[tb] < 0) thr.push_back(tb);
+        std::vector<int> ordered;
+        bool used_res[3] = { false, false, false };
+        std::vector<bool> taken(thr.size(), false);
+        for (size_t i = 0; i < thr.size() && ordered.size() < 3; ++i)
+            if (!used_res[thr[i] % 3]) { used_res[thr[i] % 3] = true; ordered.push_back(thr[i]); taken[i] = true; }
+        for (size_t i = 0; i < thr.size(); ++i)
+            if (!taken[i]) ordered.push_back(thr[i]);
+        int thr_index_of_tb[kMaxTileBits + 3];
+        for (int tb = 0; tb < T; ++tb) thr_index_of_tb[tb] = -1;
+        for (int i = 0; i < P.TB; ++i) { R.thr_tb[i] = (uint8_t)ordered[i]; thr_index_of_tb[ordered[i]] = i; }
+        for (int s = 0; s < kSlots; ++s) {
+            uint32_t l = 0;
+            for (int j = 0; j < kRegBits; ++j)
+                if ((s >> j) & 1) l |= 1u << regs[j];
+            R.sw_slot[s] = (uint16_t)tile_swizzle(l);
+        }
+        R.op_begin = (uint16_t)nops;
+        for (const OpB &ob : rb.ops) {
+            OpDesc &op = P.ops[nops];
+            std::memset(&op, 0, sizeof op);
+            const int j = slot_of_tb[tile_index[ob.target]];
+            op.j = (uint8_t)j;
+            if (!ob.is_phase) {
+                op.kind = (uint8_t)ob.kind;
+                std::memcpy(op.m, ob.m, sizeof op.m);
+                for (int p = 0; p < n_; ++p) {
+                    if (!((ob.cmask >> p) & 1ull)) continue;
+                    if (tile_index[p] >= 0) {
+                        const int tb = tile_index[p];
+                        if (slot_of_tb[tb] >= 0) op.cslot |= 1u << slot_of_tb[tb];
+                        else op.cmask |= 1ull << tb;
+                    } else op.cmask |= 1ull << (T + outer_index[p]);
+                }
+            } else {
+                op.kind = OP_PHASE;
+                op.phase_id = (uint32_t)nphase;
+                PhaseTab pt;
+                std::memset(&pt, 0, sizeof pt);
+                double lo_ang[1 << kThrLoBits] = { 0 }, hi_ang[1 << (kMaxThrBits - kThrLoBits)] = { 0 };
+                pt.base = wrap_half_turns(ob.base + (ob.has_c0 ? ob.c0 : 0.0));
+                if (ob.has_c0) {
+                    op.flags |= 8u;
+                    sincospi_host(ob.c0, op.m[7], op.m[6]);
+                }
+                for (const auto &pr : ob.partners) {
+                    const int p = pr.first;
+                    const double v = pr.second;
+                    if (tile_index[p] >= 0) {
+                        const int tb = tile_index[p];
+                        if (slot_of_tb[tb] >= 0) {
+                            int js = slot_of_tb[tb];
+                            const int qi = js < j ? js : js - 1;      // index among the other slot bits
+                            op.flags |= 1u << qi;
+                            sincospi_host(v, op.m[2 * qi + 1], op.m[2 * qi]);
+                        } else {
+                            const int ti = thr_index_of_tb[tb];
+                            if (ti < kThrLoBits) {
+                                for (int x = 0; x < (1 << kThrLoBits); ++x)
+                                    if ((x >> ti) & 1) lo_ang[x] += v;
+                            } else {
+                                for (int x = 0; x < (1 << (kMaxThrBits - kThrLoBits)); ++x)
+                                    if ((x >> (ti - kThrLoBits)) & 1) hi_ang[x] += v;
+                            }
+                        }
+                    } else pt.outer_coef[outer_index[p]] = v;
+                }
+                for (int x = 0; x < (1 << kThrLoBits); ++x) sincospi_host(lo_ang[x], pt.lo[2 * x + 1], pt.lo[2 * x]);
+                for (int x = 0; x < (1 << (kMaxThrBits - kThrLoBits)); ++x) sincospi_host(hi_ang[x], pt.hi[2 * x + 1], pt.hi[2 * x]);
+                ps.ptabs.push_back(pt);
+                ++nphase;
+            }
+            ++nops;
+        }
+        R.op_end = (uint16_t)nops;
+    }
+    P.nops = nops;
+    P.nphase = nphase;
+    stats.sweeps += 1;
+    stats.rounds += P.nrounds;
+    stats.ops += nops;
+    done_.push_back(ps);
+    rounds_.clear();
+}
+
+// ---------------------------------------------------------------------------
+// relabelling sweep (no ops): source bit p goes to destination position dstpos[p]
+// ---------------------------------------------------------------------------
+PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos)
+{
+    PlannedSweep ps;
+    ps.is_permute = true;
+    SweepProgram &P = ps.prog;
+    std::memset(&P, 0, sizeof P);
+    const int T = std::min(tile_bits, n);
+    std::vector<int> srcpos_of_dst(n);
+    for (int p = 0; p < n; ++p) srcpos_of_dst[dstpos[p]] = p;
+    // tile = low source bits + sources of the low destination bits, alternating until full
+    std::vector<int> tile;
+    for (int i = 0; i < n && (int)tile.size() < T; ++i) {
+        if (std::find(tile.begin(), tile.end(), i) == tile.end()) tile.push_back(i);
+        if ((int)tile.size() >= T) break;
+        const int s = srcpos_of_dst[i];
+        if (std::find(tile.begin(), tile.end(), s) == tile.end()) tile.push_back(s);
+    }
+    std::sort(tile.begin(), tile.end());
+    std::vector<int> outer;
+    for (int p = 0; p < n; ++p)
+        if (!std::binary_search(tile.begin(), tile.end(), p)) outer.push_back(p);
+    P.n = n; P.T = T; P.TB = T - kRegBits; P.n_outer = n - T;
+    P.relabel = 1;
+    for (int i = 0; i < T; ++i) { P.tsrc[i] = (uint8_t)tile[i]; P.tdst[i] = (uint8_t)dstpos[tile[i]]; }
+    for (int i = 0; i < P.n_outer; ++i) { P.osrc[i] = (uint8_t)outer[i]; P.odst[i] = (uint8_t)dstpos[outer[i]]; }
+    std::vector<int> order(T);
+    for (int i = 0; i < T; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return P.tdst[a] < P.tdst[b]; });
+    for (int i = 0; i < T; ++i) P.st_tb[i] = (uint8_t)order[i];
+    for (int i = 0; i < kSlots; ++i) {
+        uint64_t so = 0, dof = 0;
+        uint32_t l = 0;
+        for (int b = 0; b < kRegBits; ++b) {
+            if (!((i >> b) & 1)) continue;
+            so |= 1ull << tile[P.TB + b];
+            const int tb = order[P.TB + b];
+            dof |= 1ull << P.tdst[tb];
+            l |= 1u << tb;
+        }
+        P.ld_hi[i] = so;
+        P.st_off_hi[i] = dof;
+        P.st_l_hi[i] = (uint16_t)l;
+    }
+    P.nrounds = 0; P.nops = 0; P.nphase = 0;
+    return ps;
+}
+
+}  // namespace q1t

@@ -1,0 +1,118 @@
+// planner.h -- host-side lowering of (matrix, bits) gates and the fusion planner
+// that packs them into sweep programs.  Pure host C++ (no CUDA calls) so that it
+// is unit-testable without a device (q1t_plan_dry_run).
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "program.h"
+
+namespace q1t {
+
+typedef std::complex<double> cplx;
+
+// A gate after lowering, expressed on PHYSICAL index-bit positions.
+struct LoweredGate {
+    enum Kind { POLY, G1, SWAP, GENERIC } kind = GENERIC;
+    // POLY: diagonal unitary on <= 2 bits as a phase polynomial in half-turns:
+    //   angle(x)/pi = c0 + lin0*x_b0 + lin1*x_b1 + quad*x_b0*x_b1
+    int nb = 0;
+    int b[2] = { 0, 0 };
+    double c0 = 0, lin[2] = { 0, 0 }, quad = 0;
+    // G1: 2x2 matrix on `target`, applied where all bits of cmask are 1
+    int target = 0;
+    uint64_t cmask = 0;
+    double m[8] = { 0 };
+    // SWAP: exchange positions b[0], b[1] (handled as a relabel by the engine)
+    // GENERIC: dense matrix on pos[] (gate-index MSB first) with controls cmask
+    std::vector<int> pos;
+    std::vector<cplx> mat;
+};
+
+// (matrix, logical index bits MSB-first-of-gate-index) -> lowered form.
+// `phys[j]` is the physical position of gate bit j.  Returns false if the gate
+// cannot be represented (too many dense targets).
+bool lower_gate(const cplx *mat, int k, const int *phys, LoweredGate &out, std::string &err);
+
+struct PlannedSweep {
+    SweepProgram prog;
+    std::vector<PhaseTab> ptabs;
+    bool is_permute = false;
+};
+
+struct PlanStats {
+    uint64_t sweeps = 0, rounds = 0, ops = 0;
+};
+
+// Accumulates diagonal (phase-polynomial) terms that have not been applied yet.
+struct PendingDiag {
+    int n = 0;
+    double c0 = 0;
+    std::vector<double> lin;     // n
+    std::vector<double> quad;    // n*n symmetric
+    void init(int nbits) { n = nbits; c0 = 0; lin.assign(n, 0.0); quad.assign((size_t)n * n, 0.0); }
+    double &q(int a, int b) { return quad[(size_t)a * n + b]; }
+    void add_quad(int a, int b, double v) { q(a, b) += v; q(b, a) += v; }
+    bool touches(int t) const;
+    bool empty() const;
+};
+
+class Planner {
+public:
+    Planner(int n, int tile_bits);
+    // feed gates in program order
+    void add(const LoweredGate &g);           // POLY or G1 only
+    // flush everything that is pending (diagonal terms included) into sweeps
+    void finish();
+    // close the open sweep without touching pending diagonal terms
+    void cut() { close_sweep(); open_sweep(); }
+    // move the planned sweeps out (call after finish(), or at any time to drain
+    // completed sweeps; the current partial sweep stays open unless finished)
+    std::vector<PlannedSweep> take();
+    bool has_pending() const;
+    // make sure no pending diagonal term touches these physical bits (used
+    // before a GENERIC gate); emits PHASE ops into the current sweep
+    void flush_diag_touching(uint64_t bits_mask);
+    PlanStats stats;
+
+private:
+    struct OpB {
+        bool is_phase = false;
+        int target = 0;                 // physical
+        uint64_t cmask = 0;             // physical (G1)
+        double m[8] = { 0 };
+        int kind = OP_G1_GENERIC;
+        // phase
+        double base = 0;
+        bool has_c0 = false;
+        double c0 = 0;
+        std::vector<std::pair<int, double>> partners;   // (physical bit, half-turns)
+    };
+    struct RoundB {
+        std::vector<int> regs;          // physical
+        std::vector<OpB> ops;
+    };
+    int n_, T_;
+    std::vector<int> tile_;             // physical bits in the open sweep's tile
+    std::vector<RoundB> rounds_;
+    size_t nops_ = 0, nphase_ = 0;
+    PendingDiag pd_;
+    std::vector<PlannedSweep> done_;
+
+    bool in_tile(int p) const;
+    bool place_target(int t);           // make t a register bit of the current round (may open round/sweep)
+    void emit_phase_for(int t);
+    void emit_op(const OpB &op);
+    void close_sweep();
+    void open_sweep();
+};
+
+// relabelling sweep: dstpos[p] = destination position of source bit p
+PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos);
+
+// reduce an angle in half-turns to [-1, 1)
+double wrap_half_turns(double a);
+
+}  // namespace q1t

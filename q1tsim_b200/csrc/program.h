@@ -1,0 +1,91 @@
+// program.h -- the "sweep program": what one fused pass over the state does.
+//
+// A sweep reads every amplitude of the selected columns once and writes it
+// once.  A CTA owns a tile of 2^T amplitudes (T tile bits = the low
+// coalescing bits + up to T-3 arbitrary index bits) staged in shared memory;
+// inside the tile, work proceeds in rounds: in a round each thread holds the
+// 2^R amplitudes spanned by R "register bits" and applies a list of ops to
+// them without touching memory.  Shared by the host planner and the kernels.
+#pragma once
+#include <stdint.h>
+
+namespace q1t {
+
+constexpr int kMaxBits = 40;        // index bits of one column (one GPU's shard)
+constexpr int kMaxTileBits = 13;    // 2^13 * 16 B = 128 KiB of shared memory
+constexpr int kRegBits = 4;         // amplitudes per thread = 16
+constexpr int kSlots = 1 << kRegBits;
+constexpr int kMaxThrBits = kMaxTileBits - kRegBits;   // 9 -> 512 threads
+constexpr int kMaxRounds = 24;
+constexpr int kMaxOps = 112;
+constexpr int kMaxPhase = 64;
+constexpr int kThrLoBits = 4;       // per-thread phase factor = lo[tid & 15] * hi[tid >> 4]
+
+enum OpKind : uint8_t {
+    OP_G1_GENERIC = 0,   // dense complex 2x2 on slot bit j
+    OP_G1_HADAMARD = 1,  // c * [[1,1],[1,-1]], c real
+    OP_G1_ANTIDIAG = 2,  // [[0,m01],[m10,0]]
+    OP_G1_SWAPX = 3,     // [[0,1],[1,0]]
+    OP_PHASE = 4,        // multiply slots with bit j set by a per-thread phase
+    OP_G1_DIAG = 5,      // [[m00,0],[0,m11]] (controlled-diagonal fallback)
+};
+
+struct OpDesc {          // 96 bytes
+    uint8_t kind;
+    uint8_t j;           // slot bit
+    uint8_t flags;       // PHASE: bit0..2 = partner q[i] is non-unit, bit3 = has c0 factor
+    uint8_t pad0;
+    uint32_t cslot;      // G1: slot bits that must be 1 (controls that are register bits)
+    uint64_t cmask;      // G1: virtual-index bits (outer<<T | tile-local) that must be 1, register bits excluded
+    double m[8];         // G1: m00,m01,m10,m11 (re,im).  PHASE: q[0..2] partner factors (other slot bits ascending), m[6..7] = c0 factor
+    uint32_t phase_id;   // PHASE: row of the phase tables
+    uint32_t pad1;
+    uint64_t pad2;
+};
+
+struct RoundDesc {
+    uint8_t reg_tb[kRegBits];       // tile bit of slot bit j
+    uint8_t thr_tb[kMaxThrBits];    // tile bit of thread-index bit i
+    uint8_t pad[3];
+    uint16_t sw_slot[kSlots];       // swizzled shared-memory index contributed by slot s
+    uint16_t op_begin, op_end;
+};
+
+struct SweepProgram {
+    int32_t n;            // index bits per column
+    int32_t T;            // tile bits
+    int32_t TB;           // thread bits = T - kRegBits (threads per CTA = 2^TB)
+    int32_t n_outer;      // n - T
+    int32_t nrounds, nops, nphase;
+    int32_t relabel;      // 1 if dst positions differ from src positions (out-of-place only)
+    // tile bits are numbered by ascending source position; outer bits likewise
+    uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];
+    uint8_t osrc[kMaxBits], odst[kMaxBits];
+    // load: element e = tid | i<<TB lives at source offset dep(tid, tsrc[0..TB)) | ld_hi[i], tile index e
+    uint64_t ld_hi[kSlots];
+    // store: element f = tid | i<<TB (ascending destination position)
+    uint8_t st_tb[kMaxTileBits + 3];   // tile bit whose destination position is the f-th smallest
+    uint64_t st_off_hi[kSlots];        // destination offset of the high part of f
+    uint16_t st_l_hi[kSlots];          // tile index of the high part of f
+    RoundDesc rounds[kMaxRounds];
+    OpDesc ops[kMaxOps];
+};
+
+// per PHASE op, in global memory
+struct PhaseTab {
+    double base;                      // half-turns: constant part of the angle for slots with bit j set
+    double outer_coef[kMaxBits];      // half-turns per outer-index bit
+    double lo[2 * (1 << kThrLoBits)];                 // complex factors indexed by tid & 15
+    double hi[2 * (1 << (kMaxThrBits - kThrLoBits))]; // complex factors indexed by tid >> 4
+};
+
+#ifdef __CUDACC__
+#define Q1T_HD __host__ __device__
+#else
+#define Q1T_HD
+#endif
+Q1T_HD inline constexpr uint32_t tile_swizzle(uint32_t l) {
+    return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9) ^ (l >> 12)) & 7u);
+}
+
+}  // namespace q1t
