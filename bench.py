@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the statevector hot path (BASELINE.json: QFT-30 f64 + measure_all,
+8192 shots on 1 B200; gate-amplitude updates/s, HBM fraction of the sweep kernel,
+CPU oracle timed beside it).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--qubits n]
+
+One "step" = one full execution of the circuit: |0..0> state, every gate,
+measure_all of all shots.  `value` times the steps with the state buffer already
+resident in HBM (reset + gates + measurement); `e2e` times the public call a user
+makes (state allocation and initialisation, gate lowering/planning on the host,
+all host<->device copies, results returned in host memory).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--qubits", type=int, default=30)
+    ap.add_argument("--shots", type=int, default=8192)
+    ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's own algorithm (the reference is
+# Rust and cannot be built in this image), single thread like the reference.
+# ---------------------------------------------------------------------------
+def cpu_oracle_run(n, shots, faithful=True):
+    from oracle import oracle as O
+    from q1tsim_b200 import workloads as W
+    ops = W.qft_ops(n, measure=True)
+    c = O.OracleCircuit(n, n, mode=0 if faithful else 1, order=0 if faithful else 1)
+    W.load_ops(c, ops)
+    t0 = time.perf_counter()
+    c.execute(shots, O.Rng(seed=2))
+    dt = time.perf_counter() - t0
+    return W.gate_count(ops) * float(1 << n) / dt, dt
+
+
+def cpu_baseline(budget_s, shots):
+    """bounded sample: the same circuit family (QFT-n + measure_all) at the largest n
+    whose faithful single-thread run fits the budget; throughput is per amplitude,
+    so the unit (gate-amplitude updates/s) carries over."""
+    n = 14
+    _, dt = cpu_oracle_run(n, min(shots, 1024))
+    while n < 24:
+        gates_ratio = ((n + 1) * (n + 2) / 2 + (n + 1) // 2) / (n * (n + 1) / 2 + n // 2)
+        est = dt * 2.0 * gates_ratio
+        if est > budget_s:
+            break
+        n += 1
+        _, dt = cpu_oracle_run(n, min(shots, 1024)) if est < 1.0 else (None, est)
+    val, dt = cpu_oracle_run(n, shots)
+    return {"value": val, "unit": "gate_amp_updates/s", "cores": 1, "kind": "port",
+            "sample": "QFT-%d + measure_all, %d shots, oracle faithful mode (reference loop structure: per-block temporaries, "
+                      "materialised bit_permutation gather/scatter, sequential prefix sum), 1 thread, %.1f s" % (n, shots, dt)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base = cpu_baseline(args.cpu_seconds, args.shots)
+    times = []
+    n = int(base["sample"].split("QFT-")[1].split(" ")[0])
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_oracle_run(n, args.shots)
+        if i >= args.warmup:
+            times.append(dt)
+        if sum(times) > 150:
+            break
+    from q1tsim_b200 import workloads as W
+    gates = W.gate_count(W.qft_ops(n))
+    val = gates * float(1 << n) * len(times) / sum(times)
+    base["value"] = val
+    line = {"impl": "reference", "metric": "qft_f64_gate_amp_updates_per_s", "value": val, "unit": "gate_amp_updates/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "QFT-%d f64 + measure_all, %d shots (bounded CPU sample of the QFT-%d workload)" % (n, args.shots, args.qubits)},
+            "cpu_baseline": base,
+            "e2e": {"value": val, "unit": "gate_amp_updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local):
+    import torch
+    from q1tsim_b200 import engine as E
+    from q1tsim_b200 import workloads as W
+    if not torch.cuda.is_available() or E.lib().q1t_device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
+    dev = local % E.lib().q1t_device_count()
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    n, shots = args.qubits, args.shots
+    ops = W.qft_ops(n, measure=True)
+    gates = [(E.gate_matrix(o[1], o[2]), o[3], o[1]) for o in ops if o[0] == "gate"]
+    ngates = len(gates)
+    cbits = list(range(n))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: state buffer resident in HBM ----
+    st = E.VectorState(n, shots, dev)
+    if args.tile_bits:
+        st.set_option("tile_bits", args.tile_bits)
+    res = np.zeros(shots, dtype=np.uint64)
+    rng = E.Rng(seed=2)
+
+    def step():
+        st.reset_all()
+        for m, b, name in gates:
+            st.apply_gate(m, b, name)
+        st.measure_all_into(cbits, res, rng)
+
+    for _ in range(args.warmup):
+        step()
+    st.reset_stats()
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    stats = st.stats()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+
+    # ---- roofline of the dominant kernel: CUDA events on the engine's stream around every sweep launch ----
+    st.set_timing(True)
+    st.reset_stats()
+    for _ in range(2):
+        step()
+    ts = st.stats()
+    st.set_timing(False)
+    sweep_ms = ts["sweep_ms"] / max(ts["sweeps"], 1)
+    sweep_bytes = 32.0 * (1 << n)
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    read_ms = ts["read_ms"] / 2.0
+    roofline = {"bound": "hbm", "kernel": "sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_ms, "sweeps_per_step": ts["sweeps"] / 2.0,
+                "read_pass_ms_per_step": read_ms}
+    st.close()
+
+    # ---- e2e: the call a user makes, host buffers in, host buffers out ----
+    e2e_steps = max(3, min(args.steps, 5))
+
+    def e2e_step():
+        s2 = E.VectorState(n, shots, dev)
+        if args.tile_bits:
+            s2.set_option("tile_bits", args.tile_bits)
+        out = np.zeros(shots, dtype=np.uint64)
+        for o in ops:
+            if o[0] == "gate":
+                s2.apply_gate(E.gate_matrix(o[1], o[2]), o[3], o[1])
+            else:
+                s2.measure_all_into(o[1], out, rng)
+        s2.close()
+        return out
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dte = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dte], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dte = float(t.item())
+
+    updates_per_step = ngates * float(1 << n) * world        # independent replicas until the sharded path lands
+    value = updates_per_step * args.steps / dt
+    e2e_val = updates_per_step * e2e_steps / dte
+    if rank != 0:
+        return
+    line = {
+        "metric": "qft_f64_gate_amp_updates_per_s", "value": value, "unit": "gate_amp_updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "QFT-%d f64 + measure_all, %d shots, input |0..0>" % (n, shots), "gates": ngates,
+                   "state_bytes": 16 << n, "l2": "state (16 GiB at n=30) is far larger than the 126 MB L2; no explicit flush",
+                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
+        "circuit_ms": 1e3 * dt / args.steps,
+        "e2e": {"value": e2e_val, "unit": "gate_amp_updates/s", "ms_per_step": 1e3 * dte / e2e_steps,
+                "h2d_bytes_per_step": int(stats["sweeps"] / args.steps * 16384 + shots * 8),
+                "d2h_bytes_per_step": int(shots * 8 + 8), "steps": e2e_steps},
+        "gpu_launches": int(stats["kernel_launches"]),
+        "engine_stats": stats,
+        "roofline": roofline,
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, shots)
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,10 @@ typedef struct {
 #define Q1T_ERR_CUDA (-7)                         /* no device / CUDA failure / out of device memory */
 #define Q1T_ERR_INVALID_ARGUMENT (-8)             /* NULL pointer, duplicate qubit in `bits`, ... */
 #define Q1T_ERR_UNSUPPORTED (-9)
+/* circuit-level variants (used by the outer ABI, include/q1tsim_ffi.h) */
+#define Q1T_ERR_INVALID_CBIT (-10)                /* Error::InvalidCBit */
+#define Q1T_ERR_NOT_EXECUTED (-11)                /* Error::NotExecuted */
+#define Q1T_ERR_PARSE (-12)                       /* Error::ParseError(UnknownGate | InvalidNrArguments) */
 
 /* ---- construction: VectorState::new / from_qubit_coefs (vectorstate.rs:41-83) ---- */
 int  q1t_state_new(size_t nr_bits, size_t nr_shots, int device, q1t_state **out);

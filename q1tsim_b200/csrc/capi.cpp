@@ -7,10 +7,7 @@
 
 using q1t::DeviceVectorState;
 
-struct q1t_state {
-    DeviceVectorState impl;
-    q1t_state(size_t n, size_t shots, int dev) : impl(n, shots, dev) {}
-};
+#include "capi_internal.h"
 
 static thread_local std::string g_ctor_error;
 
@@ -19,11 +16,14 @@ static int make_state(size_t nr_bits, size_t nr_shots, int device, const double 
     if (!out) { g_ctor_error = "NULL output pointer"; return Q1T_ERR_INVALID_ARGUMENT; }
     *out = nullptr;
     if (nr_bits < 1 || nr_bits > 34) { g_ctor_error = "nr_bits must be in 1..34 for one device"; return Q1T_ERR_INVALID_ARGUMENT; }
-    q1t_state *st = new (std::nothrow) q1t_state(nr_bits, nr_shots, device);
+    q1t_state *st = new (std::nothrow) q1t_state();
     if (!st) { g_ctor_error = "out of host memory"; return Q1T_ERR_CUDA; }
-    const int rc = coefs ? st->impl.init_from_qubit_coefs(coefs) : st->impl.init_zero_state();
+    st->impl = new DeviceVectorState(nr_bits, nr_shots, device);
+    st->owns = true;
+    const int rc = coefs ? st->impl->init_from_qubit_coefs(coefs) : st->impl->init_zero_state();
     if (rc) {
-        g_ctor_error = st->impl.last_error();
+        g_ctor_error = st->impl->last_error();
+        delete st->impl;
         delete st;
         return rc;
     }
@@ -42,87 +42,92 @@ int q1t_state_from_qubit_coefs(const double *coefs, size_t nr_bits, size_t nr_sh
     if (!coefs) { g_ctor_error = "NULL coefficient array"; return Q1T_ERR_INVALID_ARGUMENT; }
     return make_state(nr_bits, nr_shots, device, coefs, out);
 }
-void q1t_state_free(q1t_state *st) { delete st; }
+void q1t_state_free(q1t_state *st)
+{
+    if (!st) return;
+    if (st->owns) delete st->impl;
+    delete st;
+}
 
 #define ST_OR_FAIL if (!st) return Q1T_ERR_INVALID_ARGUMENT
 
 int q1t_apply_gate(q1t_state *st, const double *m, size_t dim, const size_t *bits, size_t k, const char *desc)
 {
     ST_OR_FAIL;
-    return st->impl.apply_gate(m, dim, bits, k, desc);
+    return st->impl->apply_gate(m, dim, bits, k, desc);
 }
 int q1t_apply_unary_gate_all(q1t_state *st, const double *m, size_t dim, const char *desc)
 {
     ST_OR_FAIL;
-    if (dim != 2) return st->impl.apply_gate(m, dim, nullptr, 1, desc);   // produces the InvalidNrBits error
-    return st->impl.apply_unary_gate_all(m, dim, desc);
+    if (dim != 2) return st->impl->apply_gate(m, dim, nullptr, 1, desc);   // produces the InvalidNrBits error
+    return st->impl->apply_unary_gate_all(m, dim, desc);
 }
 int q1t_apply_conditional_gate(q1t_state *st, const uint8_t *control, size_t nc, const double *m, size_t dim,
                                const size_t *bits, size_t k, const char *desc)
 {
     ST_OR_FAIL;
-    return st->impl.apply_conditional_gate(control, nc, m, dim, bits, k, desc);
+    return st->impl->apply_conditional_gate(control, nc, m, dim, bits, k, desc);
 }
 int q1t_measure(q1t_state *st, size_t qbit, uint64_t *res, size_t res_len, q1t_rng rng)
 {
     ST_OR_FAIL;
-    if (res && res_len >= st->impl.nr_shots()) std::memset(res, 0, sizeof(uint64_t) * st->impl.nr_shots());
-    return st->impl.measure_into(qbit, 0, res, res_len, rng, true);
+    if (res && res_len >= st->impl->nr_shots()) std::memset(res, 0, sizeof(uint64_t) * st->impl->nr_shots());
+    return st->impl->measure_into(qbit, 0, res, res_len, rng, true);
 }
 int q1t_measure_into(q1t_state *st, size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng)
 {
     ST_OR_FAIL;
-    return st->impl.measure_into(qbit, cbit, res, res_len, rng, true);
+    return st->impl->measure_into(qbit, cbit, res, res_len, rng, true);
 }
 int q1t_measure_all(q1t_state *st, uint64_t *res, size_t res_len, q1t_rng rng)
 {
     ST_OR_FAIL;
     size_t cb[64];
-    const size_t n = st->impl.nr_bits();
+    const size_t n = st->impl->nr_bits();
     for (size_t i = 0; i < n && i < 64; ++i) cb[i] = i;
-    if (res && res_len >= st->impl.nr_shots()) std::memset(res, 0, sizeof(uint64_t) * st->impl.nr_shots());
-    return st->impl.measure_all_into(cb, n, res, res_len, rng, true);
+    if (res && res_len >= st->impl->nr_shots()) std::memset(res, 0, sizeof(uint64_t) * st->impl->nr_shots());
+    return st->impl->measure_all_into(cb, n, res, res_len, rng, true);
 }
 int q1t_measure_all_into(q1t_state *st, const size_t *cbits, size_t ncb, uint64_t *res, size_t res_len, q1t_rng rng)
 {
     ST_OR_FAIL;
-    return st->impl.measure_all_into(cbits, ncb, res, res_len, rng, true);
+    return st->impl->measure_all_into(cbits, ncb, res, res_len, rng, true);
 }
 int q1t_peek_into(q1t_state *st, size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng)
 {
     ST_OR_FAIL;
-    return st->impl.measure_into(qbit, cbit, res, res_len, rng, false);
+    return st->impl->measure_into(qbit, cbit, res, res_len, rng, false);
 }
 int q1t_peek_all_into(q1t_state *st, const size_t *cbits, size_t ncb, uint64_t *res, size_t res_len, q1t_rng rng)
 {
     ST_OR_FAIL;
-    return st->impl.measure_all_into(cbits, ncb, res, res_len, rng, false);
+    return st->impl->measure_all_into(cbits, ncb, res, res_len, rng, false);
 }
-int q1t_reset(q1t_state *st, size_t bit, q1t_rng rng) { ST_OR_FAIL; return st->impl.reset(bit, rng); }
-int q1t_reset_all(q1t_state *st) { ST_OR_FAIL; return st->impl.reset_all(); }
+int q1t_reset(q1t_state *st, size_t bit, q1t_rng rng) { ST_OR_FAIL; return st->impl->reset(bit, rng); }
+int q1t_reset_all(q1t_state *st) { ST_OR_FAIL; return st->impl->reset_all(); }
 
-size_t q1t_nr_bits(const q1t_state *st) { return st ? st->impl.nr_bits() : 0; }
-size_t q1t_nr_shots(const q1t_state *st) { return st ? st->impl.nr_shots() : 0; }
-size_t q1t_nr_columns(q1t_state *st) { return st ? st->impl.nr_columns() : 0; }
-int q1t_counts(q1t_state *st, size_t *out) { ST_OR_FAIL; return st->impl.counts(out); }
+size_t q1t_nr_bits(const q1t_state *st) { return st ? st->impl->nr_bits() : 0; }
+size_t q1t_nr_shots(const q1t_state *st) { return st ? st->impl->nr_shots() : 0; }
+size_t q1t_nr_columns(q1t_state *st) { return st ? st->impl->nr_columns() : 0; }
+int q1t_counts(q1t_state *st, size_t *out) { ST_OR_FAIL; return st->impl->counts(out); }
 int q1t_read_amplitudes(q1t_state *st, size_t col, size_t off, size_t len, double *out)
 {
     ST_OR_FAIL;
-    return st->impl.read_amplitudes(col, off, len, out);
+    return st->impl->read_amplitudes(col, off, len, out);
 }
 int q1t_write_amplitudes(q1t_state *st, size_t col, size_t off, size_t len, const double *in)
 {
     ST_OR_FAIL;
-    return st->impl.write_amplitudes(col, off, len, in);
+    return st->impl->write_amplitudes(col, off, len, in);
 }
-int q1t_marginal0(q1t_state *st, size_t qbit, double *out) { ST_OR_FAIL; return st->impl.marginal0(qbit, out); }
-int q1t_column_totals(q1t_state *st, double *out) { ST_OR_FAIL; return st->impl.column_totals(out); }
-int q1t_flush(q1t_state *st) { ST_OR_FAIL; return st->impl.flush(); }
-const char *q1t_last_error(const q1t_state *st) { return st ? st->impl.last_error() : g_ctor_error.c_str(); }
-int q1t_get_stats(q1t_state *st, q1t_stats *out) { ST_OR_FAIL; if (!out) return Q1T_ERR_INVALID_ARGUMENT; *out = st->impl.stats; return Q1T_OK; }
-int q1t_reset_stats(q1t_state *st) { ST_OR_FAIL; std::memset(&st->impl.stats, 0, sizeof(q1t_stats)); return Q1T_OK; }
-int q1t_set_timing(q1t_state *st, int enabled) { ST_OR_FAIL; st->impl.timing = enabled != 0; return Q1T_OK; }
-int q1t_set_option(q1t_state *st, const char *key, long value) { ST_OR_FAIL; return st->impl.set_option(key, value); }
+int q1t_marginal0(q1t_state *st, size_t qbit, double *out) { ST_OR_FAIL; return st->impl->marginal0(qbit, out); }
+int q1t_column_totals(q1t_state *st, double *out) { ST_OR_FAIL; return st->impl->column_totals(out); }
+int q1t_flush(q1t_state *st) { ST_OR_FAIL; return st->impl->flush(); }
+const char *q1t_last_error(const q1t_state *st) { return st ? st->impl->last_error() : g_ctor_error.c_str(); }
+int q1t_get_stats(q1t_state *st, q1t_stats *out) { ST_OR_FAIL; if (!out) return Q1T_ERR_INVALID_ARGUMENT; *out = st->impl->stats; return Q1T_OK; }
+int q1t_reset_stats(q1t_state *st) { ST_OR_FAIL; std::memset(&st->impl->stats, 0, sizeof(q1t_stats)); return Q1T_OK; }
+int q1t_set_timing(q1t_state *st, int enabled) { ST_OR_FAIL; st->impl->timing = enabled != 0; return Q1T_OK; }
+int q1t_set_option(q1t_state *st, const char *key, long value) { ST_OR_FAIL; return st->impl->set_option(key, value); }
 
 int q1t_gate_matrix(const char *name, const double *params, size_t nparams, double *out)
 {

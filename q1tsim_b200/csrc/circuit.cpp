@@ -1,0 +1,340 @@
+// circuit.cpp -- `Circuit` of the reference on the device engine.
+//   builder          circuit.rs:161-554
+//   execute family   circuit.rs:562-641
+//   interpreter      circuit.rs:643-762 (do_execute_with)
+//   histograms       circuit.rs:773-841
+#include "circuit.h"
+
+#include <cstdio>
+#include <cstring>
+
+namespace q1t {
+
+static CircuitError ok() { return CircuitError(); }
+static CircuitError mkerr(int code, const std::string &m)
+{
+    CircuitError e;
+    e.code = code;
+    e.msg = m;
+    return e;
+}
+static CircuitError invalid_qbit(size_t b)
+{
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "Invalid index %zu for a quantum bit", b);
+    return mkerr(Q1T_ERR_INVALID_QBIT, buf);
+}
+static CircuitError invalid_cbit(size_t b)
+{
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "Invalid index %zu for a classical bit", b);
+    return mkerr(Q1T_ERR_INVALID_CBIT, buf);
+}
+
+// description(): "H", "CX", "RX(1.2300)", "S†" ... (src/gates/*.rs `description`)
+std::string GateSpec::description(bool with_values) const
+{
+    if (name.empty()) return "matrix gate";
+    // every table name that starts with 'c' is C<..> of a base gate (controlled.rs:402-552)
+    std::string inner = name, prefix;
+    while (inner.size() > 1 && inner[0] == 'c') { prefix += "C"; inner = inner.substr(1); }
+    std::string d;
+    if (inner == "sdg") d = "S\xE2\x80\xA0";
+    else if (inner == "tdg") d = "T\xE2\x80\xA0";
+    else if (inner == "vdg") d = "V\xE2\x80\xA0";
+    else if (inner == "swap") d = "Swap";
+    else { d = inner; for (char &ch : d) if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32); }
+    if (!params.empty() && with_values) {
+        d += "(";
+        for (size_t i = 0; i < params.size(); ++i) {
+            char buf[48];
+            std::snprintf(buf, sizeof buf, "%s%.4f", i ? ", " : "", params[i].get());
+            d += buf;
+        }
+        d += ")";
+    }
+    return prefix + d;
+}
+
+int GateSpec::evaluate(std::vector<std::complex<double>> &out) const
+{
+    if (name.empty()) { out = matrix; return (int)nr_bits; }
+    double p[4] = { 0, 0, 0, 0 };
+    for (size_t i = 0; i < params.size() && i < 4; ++i) p[i] = params[i].get();
+    out.assign(64, std::complex<double>(0, 0));
+    const int nb = builtin_gate_matrix(name.c_str(), p, params.size(), out.data());
+    if (nb > 0) out.resize((size_t)1 << (2 * nb));
+    return nb;
+}
+
+int gate_spec_from_name(const char *name, const Param *params, size_t nparams, GateSpec &out, std::string &err)
+{
+    out = GateSpec();
+    std::string nm(name ? name : "");
+    const std::string original = nm;
+    for (char &ch : nm) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32);
+    out.name = nm;
+    // arity check the way the reference reports it (ffi.rs:216-305, error.rs ParseError)
+    static const struct { const char *n; int np; } arity[] = {
+        { "rx", 1 }, { "ry", 1 }, { "rz", 1 }, { "u1", 1 }, { "u2", 2 }, { "u3", 3 }, { "crx", 1 }, { "cry", 1 }, { "crz", 1 },
+        { "cu1", 1 }, { "cu2", 2 }, { "cu3", 3 }, { "ccrx", 1 }, { "ccry", 1 }, { "ccrz", 1 }, { nullptr, 0 } };
+    int want = 0;
+    for (int a = 0; arity[a].n; ++a) if (nm == arity[a].n) want = arity[a].np;
+    double probe[4] = { 0.1, 0.2, 0.3, 0.4 };
+    std::complex<double> tmp[64];
+    const int nb = builtin_gate_matrix(nm.c_str(), probe, (size_t)want, tmp);
+    if (nb == -1) { err = "Unknown gate \"" + original + "\""; return Q1T_ERR_PARSE; }
+    if ((int)nparams != want && want > 0) {
+        std::string up = nm;
+        for (char &ch : up) if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "Expected %d arguments to \"%s\" gate, got %zu", want, up.c_str(), nparams);
+        err = buf;
+        return Q1T_ERR_PARSE;
+    }
+    out.nr_bits = (size_t)nb;
+    for (int i = 0; i < want; ++i) out.params.push_back(params[i]);
+    return Q1T_OK;
+}
+
+// ---- builder -------------------------------------------------------------
+CircuitError Circuit::add_gate(const GateSpec &g, const std::vector<size_t> &bits)
+{
+    for (size_t b : bits)
+        if (b >= nr_qbits_) return invalid_qbit(b);          // circuit.rs:164-167
+    CircuitOp op;
+    op.kind = CircuitOp::Gate;
+    op.gate = g;
+    op.bits = bits;
+    ops_.push_back(op);
+    return ok();
+}
+
+CircuitError Circuit::add_conditional_gate(const std::vector<size_t> &control, uint64_t target, const GateSpec &g,
+                                           const std::vector<size_t> &bits)
+{
+    for (size_t b : control)
+        if (b >= nr_cbits_) return invalid_cbit(b);          // circuit.rs:187-190
+    for (size_t b : bits)
+        if (b >= nr_qbits_) return invalid_qbit(b);
+    CircuitOp op;
+    op.kind = CircuitOp::ConditionalGate;
+    op.gate = g;
+    op.bits = bits;
+    op.control = control;
+    op.target = target;
+    ops_.push_back(op);
+    return ok();
+}
+
+CircuitError Circuit::measure_basis(size_t qbit, size_t cbit, Basis b)
+{
+    if (qbit >= nr_qbits_) return invalid_qbit(qbit);        // circuit.rs:209-216
+    if (cbit >= nr_cbits_) return invalid_cbit(cbit);
+    CircuitOp op;
+    op.kind = CircuitOp::Measure;
+    op.qbit = qbit; op.cbit = cbit; op.basis = b;
+    ops_.push_back(op);
+    return ok();
+}
+
+CircuitError Circuit::measure_all_basis(const std::vector<size_t> &cbits, Basis b)
+{
+    for (size_t c : cbits)
+        if (c >= nr_cbits_) return invalid_cbit(c);          // circuit.rs:271-274
+    CircuitOp op;
+    op.kind = CircuitOp::MeasureAll;
+    op.bits = cbits; op.basis = b;
+    ops_.push_back(op);
+    return ok();
+}
+
+CircuitError Circuit::peek_basis(size_t qbit, size_t cbit, Basis b)
+{
+    if (qbit >= nr_qbits_) return invalid_qbit(qbit);
+    if (cbit >= nr_cbits_) return invalid_cbit(cbit);
+    CircuitOp op;
+    op.kind = CircuitOp::Peek;
+    op.qbit = qbit; op.cbit = cbit; op.basis = b;
+    ops_.push_back(op);
+    return ok();
+}
+
+CircuitError Circuit::peek_all_basis(const std::vector<size_t> &cbits, Basis b)
+{
+    for (size_t c : cbits)
+        if (c >= nr_cbits_) return invalid_cbit(c);
+    CircuitOp op;
+    op.kind = CircuitOp::PeekAll;
+    op.bits = cbits; op.basis = b;
+    ops_.push_back(op);
+    return ok();
+}
+
+CircuitError Circuit::reset(size_t qbit)
+{
+    if (qbit >= nr_qbits_) return invalid_qbit(qbit);
+    CircuitOp op;
+    op.kind = CircuitOp::Reset;
+    op.qbit = qbit;
+    ops_.push_back(op);
+    return ok();
+}
+
+void Circuit::reset_all()
+{
+    CircuitOp op;
+    op.kind = CircuitOp::ResetAll;
+    ops_.push_back(op);
+}
+
+CircuitError Circuit::barrier(const std::vector<size_t> &qbits)
+{
+    for (size_t b : qbits)
+        if (b >= nr_qbits_) return invalid_qbit(b);
+    CircuitOp op;
+    op.kind = CircuitOp::Barrier;
+    op.bits = qbits;
+    ops_.push_back(op);
+    return ok();
+}
+
+// ---- execution -------------------------------------------------------------
+CircuitError Circuit::state_err(int rc)
+{
+    return mkerr(rc, q_state_ ? q_state_->last_error() : "no state");
+}
+
+// circuit.rs:562-600: fresh quantum state (always the statevector backend here),
+// classical register cleared
+CircuitError Circuit::execute(size_t nr_shots, q1t_rng rng, const double *qubit_coefs)
+{
+    q_state_.reset(new DeviceVectorState(nr_qbits_, nr_shots, device));
+    const int rc = qubit_coefs ? q_state_->init_from_qubit_coefs(qubit_coefs) : q_state_->init_zero_state();
+    if (rc) {
+        CircuitError e = state_err(rc);
+        q_state_.reset();
+        has_cstate_ = false;
+        return e;
+    }
+    c_state_.assign(nr_shots, 0);
+    has_cstate_ = true;
+    return do_execute(rng);
+}
+
+// circuit.rs:618-641
+CircuitError Circuit::reexecute(q1t_rng rng)
+{
+    if (!has_cstate_ || !q_state_) return mkerr(Q1T_ERR_NOT_EXECUTED, "The circuit has not been executed yet");
+    return do_execute(rng);
+}
+
+CircuitError Circuit::set_cstate(const uint64_t *w, size_t n)
+{
+    if (!q_state_) {
+        q_state_.reset(new DeviceVectorState(nr_qbits_, n, device));
+        const int rc = q_state_->init_zero_state();
+        if (rc) { CircuitError e = state_err(rc); q_state_.reset(); return e; }
+    }
+    if (n != q_state_->nr_shots()) return mkerr(Q1T_ERR_INVALID_ARGUMENT, "classical register length must equal the number of shots");
+    c_state_.assign(w, w + n);
+    has_cstate_ = true;
+    return ok();
+}
+
+// circuit.rs:643-762
+CircuitError Circuit::do_execute(q1t_rng rng)
+{
+    DeviceVectorState &q = *q_state_;
+    static const double H[8] = { 0.70710678118654752440, 0, 0.70710678118654752440, 0, 0.70710678118654752440, 0, -0.70710678118654752440, -0.0 };
+    static const double S[8] = { 1, 0, 0, 0, 0, 0, 0, 1 };
+    static const double SDG[8] = { 1, 0, 0, 0, 0, 0, -0.0, -1 };
+    std::vector<std::complex<double>> mat;
+    std::vector<uint8_t> apply;
+#define TRY(expr) do { const int rc__ = (expr); if (rc__) return state_err(rc__); } while (0)
+    for (const CircuitOp &op : ops_) {
+        switch (op.kind) {
+        case CircuitOp::Gate: {
+            const int nb = op.gate.evaluate(mat);
+            if (nb < 0) return mkerr(Q1T_ERR_PARSE, "invalid gate");
+            TRY(q.apply_gate(reinterpret_cast<const double *>(mat.data()), (size_t)1 << nb, op.bits.data(), op.bits.size(),
+                             op.gate.description().c_str()));
+            break;
+        }
+        case CircuitOp::ConditionalGate: {
+            // control word bit k = classical bit control[k] (first listed = LSB), circuit.rs:655-665
+            apply.assign(c_state_.size(), 0);
+            for (size_t s = 0; s < c_state_.size(); ++s) {
+                uint64_t w = 0;
+                for (size_t idst = 0; idst < op.control.size(); ++idst) w |= ((c_state_[s] >> op.control[idst]) & 1ull) << idst;
+                apply[s] = w == op.target;
+            }
+            const int nb = op.gate.evaluate(mat);
+            if (nb < 0) return mkerr(Q1T_ERR_PARSE, "invalid gate");
+            TRY(q.apply_conditional_gate(apply.data(), apply.size(), reinterpret_cast<const double *>(mat.data()), (size_t)1 << nb,
+                                         op.bits.data(), op.bits.size(), op.gate.description().c_str()));
+            break;
+        }
+        case CircuitOp::Measure:
+        case CircuitOp::Peek: {
+            const bool collapse = op.kind == CircuitOp::Measure;
+            const size_t qb = op.qbit;
+            if (op.basis == Basis::X) TRY(q.apply_gate(H, 2, &qb, 1, "H"));
+            if (op.basis == Basis::Y) { TRY(q.apply_gate(SDG, 2, &qb, 1, "S\xE2\x80\xA0")); TRY(q.apply_gate(H, 2, &qb, 1, "H")); }
+            TRY(q.measure_into(op.qbit, op.cbit, c_state_.data(), c_state_.size(), rng, collapse));
+            if (op.basis == Basis::X) TRY(q.apply_gate(H, 2, &qb, 1, "H"));
+            if (op.basis == Basis::Y) { TRY(q.apply_gate(H, 2, &qb, 1, "H")); TRY(q.apply_gate(S, 2, &qb, 1, "S")); }
+            break;
+        }
+        case CircuitOp::MeasureAll:
+        case CircuitOp::PeekAll: {
+            const bool collapse = op.kind == CircuitOp::MeasureAll;
+            if (op.basis == Basis::X) TRY(q.apply_unary_gate_all(H, 2, "H"));
+            if (op.basis == Basis::Y) { TRY(q.apply_unary_gate_all(SDG, 2, "S\xE2\x80\xA0")); TRY(q.apply_unary_gate_all(H, 2, "H")); }
+            TRY(q.measure_all_into(op.bits.data(), op.bits.size(), c_state_.data(), c_state_.size(), rng, collapse));
+            if (op.basis == Basis::X) TRY(q.apply_unary_gate_all(H, 2, "H"));
+            if (op.basis == Basis::Y) { TRY(q.apply_unary_gate_all(H, 2, "H")); TRY(q.apply_unary_gate_all(S, 2, "S")); }
+            break;
+        }
+        case CircuitOp::Reset:
+            TRY(q.reset(op.qbit, rng));
+            break;
+        case CircuitOp::ResetAll:
+            TRY(q.reset_all());
+            break;
+        case CircuitOp::Barrier:
+            break;
+        }
+    }
+#undef TRY
+    // the reference's execute() returns with the state fully evolved; queued gates after the
+    // last measurement are run here so that errors surface now
+    const int rc = q.flush();
+    if (rc) return state_err(rc);
+    return ok();
+}
+
+// ---- histograms (circuit.rs:773-841) ----------------------------------------
+std::map<uint64_t, size_t> Circuit::histogram() const
+{
+    std::map<uint64_t, size_t> h;
+    for (uint64_t k : c_state_) h[k] += 1;
+    return h;
+}
+
+std::map<std::string, size_t> Circuit::histogram_string() const
+{
+    std::map<std::string, size_t> h;
+    for (const auto &kv : histogram()) {
+        // format!("{:0width$b}", key, width = nr_cbits): last character = classical bit 0
+        std::string s;
+        uint64_t k = kv.first;
+        while (k) { s.insert(s.begin(), (char)('0' + (k & 1))); k >>= 1; }
+        while (s.size() < nr_cbits_) s.insert(s.begin(), '0');
+        if (s.empty()) s = "0";
+        h[s] += kv.second;
+    }
+    return h;
+}
+
+}  // namespace q1t

@@ -1,0 +1,91 @@
+// circuit.h -- host-side mirror of the reference's `Circuit` (src/circuit.rs):
+// builder methods, the op interpreter `do_execute_with` and histograms, on top
+// of DeviceVectorState.  Same names, argument meaning and error behaviour.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace q1t {
+
+enum class Basis { X, Y, Z };
+
+// gates/parameter.rs:21-50: a value, or a pointer read at *execute* time
+struct Param {
+    double value = 0;
+    const double *ptr = nullptr;
+    double get() const { return ptr ? *ptr : value; }
+};
+
+struct GateSpec {
+    std::string name;                  // lower-case table name, or empty for a matrix gate
+    std::vector<Param> params;
+    std::vector<std::complex<double>> matrix;   // user gate: matrix() given directly
+    size_t nr_bits = 0;
+    std::string description(bool with_values = true) const;
+    // evaluate matrix() now (gates read their parameters at execution time)
+    int evaluate(std::vector<std::complex<double>> &out) const;
+};
+
+struct CircuitOp {       // circuit.rs:27-51
+    enum Kind { Gate, ConditionalGate, Reset, ResetAll, Measure, MeasureAll, Peek, PeekAll, Barrier } kind;
+    GateSpec gate;
+    std::vector<size_t> bits;          // qubits (Gate, ConditionalGate, Barrier) or cbits (MeasureAll, PeekAll)
+    std::vector<size_t> control;
+    uint64_t target = 0;
+    size_t qbit = 0, cbit = 0;
+    Basis basis = Basis::Z;
+};
+
+struct CircuitError {
+    int code = 0;
+    std::string msg;
+    explicit operator bool() const { return code != 0; }
+};
+
+class Circuit {
+public:
+    Circuit(size_t nr_qbits, size_t nr_cbits) : nr_qbits_(nr_qbits), nr_cbits_(nr_cbits) {}
+    size_t nr_qbits() const { return nr_qbits_; }
+    size_t nr_cbits() const { return nr_cbits_; }
+
+    CircuitError add_gate(const GateSpec &g, const std::vector<size_t> &bits);
+    CircuitError add_conditional_gate(const std::vector<size_t> &control, uint64_t target, const GateSpec &g,
+                                      const std::vector<size_t> &bits);
+    CircuitError measure_basis(size_t qbit, size_t cbit, Basis b);
+    CircuitError measure_all_basis(const std::vector<size_t> &cbits, Basis b);
+    CircuitError peek_basis(size_t qbit, size_t cbit, Basis b);
+    CircuitError peek_all_basis(const std::vector<size_t> &cbits, Basis b);
+    CircuitError reset(size_t qbit);
+    void reset_all();
+    CircuitError barrier(const std::vector<size_t> &qbits);
+
+    CircuitError execute(size_t nr_shots, q1t_rng rng, const double *qubit_coefs = nullptr);
+    CircuitError reexecute(q1t_rng rng);
+
+    bool executed() const { return has_cstate_; }
+    const std::vector<uint64_t> &cstate() const { return c_state_; }
+    CircuitError set_cstate(const uint64_t *w, size_t n);
+    std::map<uint64_t, size_t> histogram() const;
+    std::map<std::string, size_t> histogram_string() const;
+    DeviceVectorState *state() { return q_state_.get(); }
+    int device = 0;
+
+private:
+    size_t nr_qbits_, nr_cbits_;
+    std::unique_ptr<DeviceVectorState> q_state_;
+    bool has_cstate_ = false;
+    std::vector<uint64_t> c_state_;
+    std::vector<CircuitOp> ops_;
+    CircuitError state_err(int rc);
+    CircuitError do_execute(q1t_rng rng);
+};
+
+int gate_spec_from_name(const char *name, const Param *params, size_t nparams, GateSpec &out, std::string &err);
+
+}  // namespace q1t

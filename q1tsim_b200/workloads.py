@@ -1,7 +1,7 @@
 """Synthetic workloads of BASELINE.json, as backend-neutral op lists.
 
-An op list is a sequence of tuples understood both by the product `Circuit`
-(q1tsim_b200.circuit) and by the test oracle's `OracleCircuit`:
+An op list is a sequence of tuples that `load_ops` feeds to any object exposing
+the reference's `Circuit` builder methods (q1tsim_b200.circuit.Circuit does):
   ("gate", name, params, bits) | ("measure_all", cbits, basis) | ("measure", q, c, basis)
   | ("cond", control, target, name, params, bits) | ...
 Generators follow SURVEY.md 8(d); the PRNG is SplitMix64 so C++/Python agree.
