@@ -214,7 +214,7 @@ def run_ours(args, rank, world, local):
     ts = st.stats()
     st.set_timing(False)
     sweep_ms = ts["sweep_ms"] / max(ts["sweeps"], 1)
-    sweep_bytes = 32.0 * (1 << n)
+    sweep_bytes = ts["sweep_bytes"] / max(ts["sweeps"], 1)     # 32 B/amplitude, 16 B when the |0..0> input is generated
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -232,17 +232,16 @@ def run_ours(args, rank, world, local):
     # ---- e2e: the call a user makes, host buffers in, host buffers out ----
     e2e_steps = max(3, min(args.steps, 5))
 
+    from q1tsim_b200 import circuit as QC
+
     def e2e_step():
-        s2 = E.VectorState(n, shots, dev)
-        if args.tile_bits:
-            s2.set_option("tile_bits", args.tile_bits)
-        out = np.zeros(shots, dtype=np.uint64)
-        for o in ops:
-            if o[0] == "gate":
-                s2.apply_gate(E.gate_matrix(o[1], o[2]), o[3], o[1])
-            else:
-                s2.measure_all_into(o[1], out, rng)
-        s2.close()
+        # the reference-facing call: build the circuit through the ffi.rs-compatible C ABI,
+        # execute(nr_shots) (fresh state, gate lowering + planning, every H2D/D2H copy), read c_state
+        c = QC.Circuit(n, n, dev)
+        W.load_ops(c, ops)
+        c.execute(shots, rng)
+        out = c.cstate()
+        c.close()
         return out
 
     e2e_step()

@@ -120,6 +120,8 @@ typedef struct {
     uint64_t kernel_launches;     /* kernels launched by this state */
     uint64_t permute_sweeps;      /* sweeps spent only on qubit relabelling */
     uint64_t fallback_sweeps;     /* gates executed by the unfused generic kernel */
+    uint64_t fused_relabels;      /* relabellings absorbed into the last gate sweep (no extra pass) */
+    uint64_t sweep_bytes;         /* algorithmic bytes of the sweep launches: 32 B per amplitude, 16 B when the input is generated */
     double   sweep_ms;            /* device time of sweep kernels (CUDA events), if timing enabled */
     double   read_ms;             /* device time of read passes */
 } q1t_stats;

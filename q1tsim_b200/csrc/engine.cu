@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 namespace q1t {
 
@@ -20,6 +21,50 @@ namespace q1t {
         cudaError_t e__ = (call);                             \
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
+
+// ---------------------------------------------------------------------------
+// process-wide cache of column buffers: execute() builds a fresh state every
+// call (circuit.rs:594-600), so without a cache every call would pay
+// cudaMalloc + cudaFree of 16 B * 2^n
+// ---------------------------------------------------------------------------
+namespace {
+struct PoolEntry { int device; size_t bytes; void *ptr; };
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+const size_t kPoolMaxPerClass = 3;
+
+void *pool_take(int device, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); ++i)
+        if (g_pool[i].device == device && g_pool[i].bytes == bytes) {
+            void *p = g_pool[i].ptr;
+            g_pool.erase(g_pool.begin() + i);
+            return p;
+        }
+    return nullptr;
+}
+// returns false if the caller must cudaFree the buffer itself
+bool pool_give(int device, size_t bytes, void *ptr)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t same = 0;
+    for (const PoolEntry &e : g_pool)
+        if (e.device == device && e.bytes == bytes) ++same;
+    if (same >= kPoolMaxPerClass) return false;
+    g_pool.push_back({ device, bytes, ptr });
+    return true;
+}
+// free every cached buffer of a device (called before reporting out-of-memory)
+void pool_flush(int device)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size();) {
+        if (g_pool[i].device == device) { cudaFree(g_pool[i].ptr); g_pool.erase(g_pool.begin() + i); }
+        else ++i;
+    }
+}
+}  // namespace
 
 int DeviceVectorState::cuda_fail(cudaError_t e, const char *what)
 {
@@ -41,11 +86,13 @@ DeviceVectorState::~DeviceVectorState()
     if (stream_) {
         cudaSetDevice(device_);
         cudaStreamSynchronize(stream_);
+        const size_t bytes = sizeof(double2) << n_;
         for (Column &c : cols_)
-            if (c.buf) cudaFree(c.buf);
-        for (double2 *p : free_bufs_) cudaFree(p);
+            if (c.buf && !pool_give(device_, bytes, c.buf)) cudaFree(c.buf);
+        for (double2 *p : free_bufs_)
+            if (!pool_give(device_, bytes, p)) cudaFree(p);
         cudaFree(d_colptrs_); cudaFree(d_ptabs_); cudaFree(d_leaf_); cudaFree(d_block_); cudaFree(d_totals_);
-        cudaFree(d_chosen_); cudaFree(d_idx_); cudaFree(d_mat_);
+        cudaFree(d_chosen_); cudaFree(d_idx_); cudaFree(d_mat_); cudaFree(d_pair_); cudaFree(d_gen_);
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
         cudaStreamDestroy(stream_);
@@ -68,13 +115,22 @@ int DeviceVectorState::ensure_device()
     CK(cudaEventCreate(&ev1_));
     CK(cudaMalloc(&d_ptabs_, sizeof(PhaseTab) * kMaxPhase));
     CK(cudaMalloc(&d_mat_, sizeof(double2) << (2 * kMaxGenericBits)));
+    CK(cudaMalloc(&d_pair_, sizeof(double2 *) * 2));
     return Q1T_OK;
 }
 
 int DeviceVectorState::alloc_column(double2 **out)
 {
     if (!free_bufs_.empty()) { *out = free_bufs_.back(); free_bufs_.pop_back(); return Q1T_OK; }
-    cudaError_t e = cudaMalloc(out, sizeof(double2) << n_);
+    const size_t bytes = sizeof(double2) << n_;
+    if (void *p = pool_take(device_, bytes)) { *out = static_cast<double2 *>(p); return Q1T_OK; }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(stream_);
+        pool_flush(device_);
+        e = cudaMalloc(out, bytes);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         char buf[256];
@@ -97,13 +153,12 @@ int DeviceVectorState::init_zero_state()
 {
     int rc = ensure_device();
     if (rc) return rc;
+    // |0..0> is kept as a lazy basis column: the first fused sweep synthesises it on the fly
+    // instead of paying a memset (one full write) plus a read of 2^n zeros
     Column c;
-    rc = alloc_column(&c.buf);
-    if (rc) return rc;
     c.count = shots_;
-    CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
-    CK(launch_set_basis(c.buf, 0, stream_));
-    stats.kernel_launches++;
+    c.basis = true;
+    c.basis_idx = 0;
     cols_.push_back(c);
     return Q1T_OK;
 }
@@ -273,26 +328,108 @@ int DeviceVectorState::run_generic(const LoweredGate &g, const std::vector<int> 
     stats.sweeps++;
     stats.fallback_sweeps++;
     stats.sweep_column_passes += which.size();
+    stats.sweep_bytes += (uint64_t)which.size() * (32ull << n_);
     return Q1T_OK;
 }
 
-int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which)
+// physical (current layout) index of a logical basis index
+static unsigned long long physical_index(uint64_t logical, const std::vector<int> &perm)
 {
-    for (PlannedSweep &ps : sweeps) {
+    unsigned long long p = 0;
+    for (size_t l = 0; l < perm.size(); ++l)
+        if ((logical >> l) & 1ull) p |= 1ull << perm[l];
+    return p;
+}
+
+// Launch the planned sweeps on the columns `which`.
+//  - if every column is still a lazy basis state, the first sweep generates its input;
+//  - if `final_relabel` is set and the qubit relabelling is not the identity, the last
+//    sweep also restores the canonical layout on its way out (out-of-place), when its
+//    tile allows coalesced stores; otherwise canonicalize() runs a separate sweep later.
+int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel)
+{
+    if (sweeps.empty()) return Q1T_OK;
+    bool all_basis = true;
+    for (int c : which) all_basis = all_basis && cols_[c].basis;
+    std::vector<unsigned long long> gen(which.size());
+    bool generate = all_basis;
+    if (generate) {
+        for (size_t i = 0; i < which.size(); ++i) {
+            Column &c = cols_[which[i]];
+            gen[i] = physical_index(c.basis_idx, perm_);
+            int rc = alloc_column(&c.buf);
+            if (rc) return rc;
+            c.basis = false;
+        }
+        if (which.size() > gen_cap_) {
+            if (d_gen_) cudaFree(d_gen_);
+            gen_cap_ = std::max<size_t>(which.size() * 2, 16);
+            CK(cudaMalloc(&d_gen_, sizeof(unsigned long long) * gen_cap_));
+        }
+        CK(cudaMemcpyAsync(d_gen_, gen.data(), sizeof(unsigned long long) * gen.size(), cudaMemcpyHostToDevice, stream_));
+    } else {
+        for (int c : which) {
+            int rc = materialize(cols_[c]);
+            if (rc) return rc;
+        }
+    }
+    int rc = upload_colptrs(which);
+    if (rc) return rc;
+    bool ident = true;
+    for (int l = 0; l < n_; ++l)
+        if (perm_[l] != l) ident = false;
+    for (size_t si = 0; si < sweeps.size(); ++si) {
+        PlannedSweep &ps = sweeps[si];
         if (!ps.ptabs.empty())
             CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
-        time_begin();
-        CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, stream_));
-        time_end(stats.sweep_ms);
-        stats.kernel_launches++;
+        ps.prog.generate = (generate && si == 0) ? 1 : 0;
+        const bool last = si + 1 == sweeps.size();
+        bool relabel = false;
+        if (last && final_relabel && !ident && which.size() == cols_.size()) {
+            std::vector<int> dstpos(n_);
+            for (int l = 0; l < n_; ++l) dstpos[perm_[l]] = l;
+            if (can_fuse_relabel(ps.prog, dstpos)) {
+                set_relabel(ps.prog, dstpos);
+                relabel = true;
+            }
+        }
+        if (!relabel) {
+            time_begin();
+            CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_));
+            time_end(stats.sweep_ms);
+            stats.kernel_launches++;
+            stats.sweeps++;
+            stats.sweep_column_passes += which.size();
+            stats.sweep_bytes += (uint64_t)which.size() * ((ps.prog.generate ? 16ull : 32ull) << n_);
+            continue;
+        }
+        // out-of-place: one column at a time through a scratch buffer
+        for (size_t i = 0; i < which.size(); ++i) {
+            Column &col = cols_[which[i]];
+            double2 *scratch = nullptr;
+            rc = alloc_column(&scratch);
+            if (rc) return rc;
+            double2 *h[2] = { col.buf, scratch };
+            CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
+            time_begin();
+            CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, d_gen_ ? d_gen_ + i : nullptr, stream_));
+            time_end(stats.sweep_ms);
+            stats.kernel_launches++;
+            double2 *old = col.buf;
+            col.buf = scratch;
+            release_column(old);
+        }
         stats.sweeps++;
+        stats.fused_relabels++;
         stats.sweep_column_passes += which.size();
+        stats.sweep_bytes += (uint64_t)which.size() * ((ps.prog.generate ? 16ull : 32ull) << n_);
+        for (int l = 0; l < n_; ++l) perm_[l] = l;
     }
     sweeps.clear();
     return Q1T_OK;
 }
 
-int DeviceVectorState::run_queue()
+int DeviceVectorState::run_queue(bool final_relabel)
 {
     if (queue_.empty()) return Q1T_OK;
     int rc = ensure_device();
@@ -300,16 +437,19 @@ int DeviceVectorState::run_queue()
     std::vector<int> which = queue_cols_;
     if (which.empty())
         for (size_t c = 0; c < cols_.size(); ++c) which.push_back((int)c);
-    for (int c : which) {
-        rc = materialize(cols_[c]);
-        if (rc) return rc;
-    }
-    rc = upload_colptrs(which);
-    if (rc) return rc;
     std::vector<LoweredGate> q;
     q.swap(queue_);
     queue_cols_.clear();
+    auto materialize_all = [&]() -> int {
+        for (int c : which) {
+            int r = materialize(cols_[c]);
+            if (r) return r;
+        }
+        return upload_colptrs(which);
+    };
     if (n_ < 5 || !fuse_) {
+        rc = materialize_all();
+        if (rc) return rc;
         for (const LoweredGate &g : q) {
             LoweredGate gg;
             to_generic(g, gg);
@@ -331,14 +471,16 @@ int DeviceVectorState::run_queue()
         pl.flush_diag_touching(m);
         pl.cut();
         std::vector<PlannedSweep> sw = pl.take();
-        rc = run_sweeps(sw, which);
+        rc = run_sweeps(sw, which, false);
+        if (rc) return rc;
+        rc = materialize_all();
         if (rc) return rc;
         rc = run_generic(gg, which);
         if (rc) return rc;
     }
     pl.finish();
     std::vector<PlannedSweep> sw = pl.take();
-    return run_sweeps(sw, which);
+    return run_sweeps(sw, which, final_relabel);
 }
 
 // undo the zero-byte swap relabelling: one out-of-place relabel sweep per column
@@ -361,20 +503,15 @@ int DeviceVectorState::canonicalize()
         int rc = alloc_column(&scratch);
         if (rc) return rc;
         double2 *h[2] = { col.buf, scratch };
-        if (colptrs_cap_ < 2) {
-            std::vector<int> dummy;
-            colptrs_cap_ = 16;
-            if (d_colptrs_) cudaFree(d_colptrs_);
-            CK(cudaMalloc(&d_colptrs_, sizeof(double2 *) * colptrs_cap_));
-        }
-        CK(cudaMemcpyAsync(d_colptrs_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
+        CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
         time_begin();
-        CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_ + 1, 1, d_ptabs_, stream_));
+        CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, nullptr, stream_));
         time_end(stats.sweep_ms);
         stats.kernel_launches++;
         stats.sweeps++;
         stats.permute_sweeps++;
         stats.sweep_column_passes++;
+        stats.sweep_bytes += 32ull << n_;
         double2 *old = col.buf;
         col.buf = scratch;
         release_column(old);
@@ -387,7 +524,7 @@ int DeviceVectorState::flush()
 {
     int rc = ensure_device();
     if (rc) return rc;
-    rc = run_queue();
+    rc = run_queue(true);
     if (rc) return rc;
     rc = canonicalize();
     if (rc) return rc;

@@ -76,6 +76,8 @@ private:
     double *d_totals_ = nullptr; size_t totals_cap_ = 0;
     double *d_chosen_ = nullptr; uint64_t *d_idx_ = nullptr; size_t draws_cap_ = 0;
     double2 *d_mat_ = nullptr;
+    double2 **d_pair_ = nullptr;
+    unsigned long long *d_gen_ = nullptr; size_t gen_cap_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 
     int fail(int code, const std::string &msg) { err_ = msg; return code; }
@@ -85,8 +87,8 @@ private:
     void release_column(double2 *p);
     int materialize(Column &c);
     int upload_colptrs(const std::vector<int> &which);
-    int run_queue();                         // lower queue -> sweeps -> launches
-    int run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which);
+    int run_queue(bool final_relabel = false);   // queue -> planner -> sweep launches
+    int run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel);
     int run_generic(const LoweredGate &g, const std::vector<int> &which);
     int canonicalize();                      // undo swap relabelling (perm_ -> identity)
     int reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols);

@@ -54,28 +54,37 @@ __device__ __forceinline__ constexpr int ins0(int p)
 }
 
 // ---------------------------------------------------------------------------
-// register-level ops on the 2^R amplitudes of one thread
+// register-level ops on the 2^R amplitudes of one thread.
+// Every body exists twice: a branch-free one for cslot == 0 (no control among
+// the register bits, the common case) and one with a per-pair test.
 // ---------------------------------------------------------------------------
+#define Q1T_FOR_PAIRS(BODY)                                              \
+    if (cs == 0u) {                                                      \
+        _Pragma("unroll") for (int p = 0; p < kSlots / 2; ++p) {         \
+            const int s0 = ins0<J>(p), s1 = s0 | (1 << J);               \
+            BODY                                                         \
+        }                                                                \
+    } else {                                                             \
+        _Pragma("unroll") for (int p = 0; p < kSlots / 2; ++p) {         \
+            const int s0 = ins0<J>(p), s1 = s0 | (1 << J);               \
+            if ((s0 & cs) == cs) { BODY }                                \
+        }                                                                \
+    }
+
 template <int J>
 __device__ __forceinline__ void g1_generic(double2 (&a)[kSlots], const OpDesc &op)
 {
     const double m00r = op.m[0], m00i = op.m[1], m01r = op.m[2], m01i = op.m[3];
     const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6], m11i = op.m[7];
     const unsigned cs = op.cslot;
-#pragma unroll
-    for (int p = 0; p < kSlots / 2; ++p) {
-        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
-        if ((s0 & cs) == cs) {
-            const double2 x = a[s0], y = a[s1];
-            double2 u, v;
-            u.x = fma(m00r, x.x, fma(-m00i, x.y, fma(m01r, y.x, -(m01i * y.y))));
-            u.y = fma(m00r, x.y, fma(m00i, x.x, fma(m01r, y.y, m01i * y.x)));
-            v.x = fma(m10r, x.x, fma(-m10i, x.y, fma(m11r, y.x, -(m11i * y.y))));
-            v.y = fma(m10r, x.y, fma(m10i, x.x, fma(m11r, y.y, m11i * y.x)));
-            a[s0] = u;
-            a[s1] = v;
-        }
-    }
+    Q1T_FOR_PAIRS(
+        const double2 x = a[s0]; const double2 y = a[s1];
+        double2 u; double2 v;
+        u.x = fma(m00r, x.x, fma(-m00i, x.y, fma(m01r, y.x, -(m01i * y.y))));
+        u.y = fma(m00r, x.y, fma(m00i, x.x, fma(m01r, y.y, m01i * y.x)));
+        v.x = fma(m10r, x.x, fma(-m10i, x.y, fma(m11r, y.x, -(m11i * y.y))));
+        v.y = fma(m10r, x.y, fma(m10i, x.x, fma(m11r, y.y, m11i * y.x)));
+        a[s0] = u; a[s1] = v;)
 }
 
 template <int J>
@@ -83,14 +92,23 @@ __device__ __forceinline__ void g1_hadamard(double2 (&a)[kSlots], const OpDesc &
 {
     const double c = op.m[0];
     const unsigned cs = op.cslot;
+    Q1T_FOR_PAIRS(
+        const double2 x = a[s0]; const double2 y = a[s1];
+        a[s0] = make_double2((x.x + y.x) * c, (x.y + y.y) * c);
+        a[s1] = make_double2((x.x - y.x) * c, (x.y - y.y) * c);)
+}
+
+// uncontrolled Hadamard without its 1/sqrt(2): the factor is applied once per
+// sweep at the store (SweepProgram::scale)
+template <int J>
+__device__ __forceinline__ void h_unnorm(double2 (&a)[kSlots])
+{
 #pragma unroll
     for (int p = 0; p < kSlots / 2; ++p) {
         const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
-        if ((s0 & cs) == cs) {
-            const double2 x = a[s0], y = a[s1];
-            a[s0] = make_double2((x.x + y.x) * c, (x.y + y.y) * c);
-            a[s1] = make_double2((x.x - y.x) * c, (x.y - y.y) * c);
-        }
+        const double2 x = a[s0], y = a[s1];
+        a[s0] = make_double2(x.x + y.x, x.y + y.y);
+        a[s1] = make_double2(x.x - y.x, x.y - y.y);
     }
 }
 
@@ -99,30 +117,20 @@ __device__ __forceinline__ void g1_antidiag(double2 (&a)[kSlots], const OpDesc &
 {
     const double2 m01 = make_double2(op.m[2], op.m[3]), m10 = make_double2(op.m[4], op.m[5]);
     const unsigned cs = op.cslot;
-#pragma unroll
-    for (int p = 0; p < kSlots / 2; ++p) {
-        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
-        if ((s0 & cs) == cs) {
-            const double2 x = a[s0], y = a[s1];
-            a[s0] = cmul(m01, y);
-            a[s1] = cmul(m10, x);
-        }
-    }
+    Q1T_FOR_PAIRS(
+        const double2 x = a[s0]; const double2 y = a[s1];
+        a[s0] = cmul(m01, y);
+        a[s1] = cmul(m10, x);)
 }
 
 template <int J>
 __device__ __forceinline__ void g1_swapx(double2 (&a)[kSlots], const OpDesc &op)
 {
     const unsigned cs = op.cslot;
-#pragma unroll
-    for (int p = 0; p < kSlots / 2; ++p) {
-        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
-        if ((s0 & cs) == cs) {
-            const double2 x = a[s0];
-            a[s0] = a[s1];
-            a[s1] = x;
-        }
-    }
+    Q1T_FOR_PAIRS(
+        const double2 x = a[s0];
+        a[s0] = a[s1];
+        a[s1] = x;)
 }
 
 template <int J>
@@ -130,24 +138,15 @@ __device__ __forceinline__ void g1_diag(double2 (&a)[kSlots], const OpDesc &op)
 {
     const double2 m00 = make_double2(op.m[0], op.m[1]), m11 = make_double2(op.m[6], op.m[7]);
     const unsigned cs = op.cslot;
-#pragma unroll
-    for (int p = 0; p < kSlots / 2; ++p) {
-        const int s0 = ins0<J>(p), s1 = s0 | (1 << J);
-        if ((s0 & cs) == cs) {
-            a[s0] = cmul(m00, a[s0]);
-            a[s1] = cmul(m11, a[s1]);
-        }
-    }
+    Q1T_FOR_PAIRS(
+        a[s0] = cmul(m00, a[s0]);
+        a[s1] = cmul(m11, a[s1]);)
 }
 
-// PHASE: slots with bit J set are multiplied by F * prod_{other slot bits set} q[i];
-// optionally every slot is multiplied by the constant c0 (a global phase term).
-template <int J>
-__device__ __forceinline__ void phase_apply(double2 (&a)[kSlots], const OpDesc &op, double2 F)
+// per-slot phase factors of a PHASE op: f[u] = F * prod_{other slot bits set in u} q[i]
+__device__ __forceinline__ void phase_factors(double2 (&f)[kSlots / 2], const OpDesc &op, double2 F)
 {
-    double2 f[kSlots / 2];
     f[0] = F;
-    // other slot bits in ascending order; index u enumerates their subsets
 #pragma unroll
     for (int i = 0; i < kRegBits - 1; ++i) {
         if (op.flags & (1u << i)) {
@@ -159,6 +158,15 @@ __device__ __forceinline__ void phase_apply(double2 (&a)[kSlots], const OpDesc &
             for (int u = 0; u < (1 << i); ++u) f[u | (1 << i)] = f[u];
         }
     }
+}
+
+// PHASE: slots with bit J set are multiplied by f[u]; optionally every slot is
+// multiplied by the constant c0 (a global phase term).
+template <int J>
+__device__ __forceinline__ void phase_apply(double2 (&a)[kSlots], const OpDesc &op, double2 F)
+{
+    double2 f[kSlots / 2];
+    phase_factors(f, op, F);
 #pragma unroll
     for (int u = 0; u < kSlots / 2; ++u) {
         const int s1 = ins0<J>(u) | (1 << J);
@@ -174,6 +182,68 @@ __device__ __forceinline__ void phase_apply(double2 (&a)[kSlots], const OpDesc &
     }
 }
 
+// PHASE followed by the unnormalised Hadamard on the same slot bit:
+//   (x, y) -> (x + f*y, x - f*y), 8 FP64 instructions per pair
+template <int J>
+__device__ __forceinline__ void phase_h_apply(double2 (&a)[kSlots], const OpDesc &op, double2 F)
+{
+    double2 f[kSlots / 2];
+    phase_factors(f, op, F);
+#pragma unroll
+    for (int u = 0; u < kSlots / 2; ++u) {
+        const int s0 = ins0<J>(u), s1 = s0 | (1 << J);
+        const double2 x = a[s0], y = a[s1];
+        const double tr = fma(y.x, f[u].x, -(y.y * f[u].y));
+        const double ti = fma(y.x, f[u].y, y.y * f[u].x);
+        a[s0] = make_double2(x.x + tr, x.y + ti);
+        a[s1] = make_double2(x.x - tr, x.y - ti);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ROUND_PH: NS fused (phase, Hadamard-butterfly) steps on slot bits 0..NS-1,
+// straight-line code.  Step j multiplies the bit-j=1 half by
+//   F_j(thread, tile) * prod_{i<j, slot bit i set} q_{j,i}
+// and then applies the unnormalised butterfly -- a radix-2^NS decimation stage
+// of the QFT/FFT with per-thread twiddles, but for arbitrary phase coefficients.
+// ---------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void round_ph(char *tile_b, unsigned swT, const RoundDesc &R, const SweepProgram &P,
+                                         const PhaseTab *__restrict__ ptabs, const double2 *s_tileF, unsigned tid)
+{
+    double2 a[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
+    const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const OpDesc &op = P.ops[R.op_begin + j];
+        const PhaseTab &pt = ptabs[op.phase_id];
+        const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
+        const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
+        double2 f[1 << (NS - 1)];
+        f[0] = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+            const double2 q = make_double2(op.m[2 * i], op.m[2 * i + 1]);
+#pragma unroll
+            for (int u = 0; u < (1 << i); ++u) f[u | (1 << i)] = cmul(f[u], q);
+        }
+#pragma unroll
+        for (int p = 0; p < kSlots / 2; ++p) {
+            const int s0 = ((p >> j) << (j + 1)) | (p & ((1 << j) - 1)), s1 = s0 | (1 << j);
+            const double2 ff = f[p & ((1 << j) - 1)];
+            const double2 x = a[s0], y = a[s1];
+            const double tr = fma(y.x, ff.x, -(y.y * ff.y));
+            const double ti = fma(y.x, ff.y, y.y * ff.x);
+            a[s0] = make_double2(x.x + tr, x.y + ti);
+            a[s1] = make_double2(x.x - tr, x.y - ti);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
+}
+
 #define Q1T_DISPATCH_J(fn, ...)          \
     switch (op.j) {                      \
     case 0: fn<0>(__VA_ARGS__); break;   \
@@ -182,12 +252,23 @@ __device__ __forceinline__ void phase_apply(double2 (&a)[kSlots], const OpDesc &
     default: fn<3>(__VA_ARGS__); break;  \
     }
 
+__device__ __forceinline__ unsigned long long outer_base(const uint64_t (&tab)[kOuterChunks][1 << kOuterChunkBits],
+                                                         unsigned long long o, int n_outer)
+{
+    unsigned long long r = tab[0][o & 63ull];
+    if (n_outer > 6) r |= tab[1][(o >> 6) & 63ull];
+    if (n_outer > 12) r |= tab[2][(o >> 12) & 63ull];
+    if (n_outer > 18) r |= tab[3][(o >> 18) & 63ull];
+    if (n_outer > 24) r |= tab[4][(o >> 24) & 63ull];
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // the sweep kernel
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1)
 sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
-             const PhaseTab *__restrict__ ptabs)
+             const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx)
 {
     extern __shared__ double2 tile[];
     __shared__ double2 s_tileF[kMaxPhase];
@@ -197,23 +278,21 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
     const unsigned tid = threadIdx.x;
     const unsigned long long o = blockIdx.x;
     const int col = blockIdx.y;
+    char *const tile_b = reinterpret_cast<char *>(tile);
 
-    // tile base offsets in the source / destination layout
-    unsigned long long sbase = 0, dbase = 0;
-    for (int i = 0; i < P.n_outer; ++i) {
-        const unsigned long long b = (o >> i) & 1ull;
-        sbase |= b << P.osrc[i];
-        dbase |= b << P.odst[i];
-    }
-    unsigned long long soff_lo = 0;
-    for (int i = 0; i < TB; ++i) soff_lo |= (unsigned long long)((tid >> i) & 1u) << P.tsrc[i];
-
-    // ---- load the tile (coalesced: consecutive tid -> consecutive source addresses) ----
-    const double2 *__restrict__ src = src_cols[col] + sbase + soff_lo;
+    // ---- stage the tile in shared memory ----
+    const unsigned sw_tid = tile_swizzle(tid) * 16u;      // tid < 2^TB <= 512: swizzle of the low part
+    if (!P.generate) {
+        // coalesced: consecutive tid -> consecutive source addresses
+        unsigned long long soff = outer_base(P.o_src, o, P.n_outer);
+        for (int k = 0; k < P.ld_nruns; ++k) soff |= (unsigned long long)(tid & P.ld_runs[k].mask) << P.ld_runs[k].shift;
+        const double2 *__restrict__ src = src_cols[col] + soff;
 #pragma unroll
-    for (int i = 0; i < kSlots; ++i) {
-        const unsigned e = tid | ((unsigned)i << TB);
-        cp_async16(&tile[tile_swizzle(e)], src + P.ld_hi[i]);
+        for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw_tid ^ P.ld_sw_hi[i]), src + P.ld_hi[i]);
+    } else {
+        // the source is the basis state |gen_idx>: synthesise the tile instead of reading it
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) *reinterpret_cast<double2 *>(tile_b + (sw_tid ^ P.ld_sw_hi[i])) = make_double2(0.0, 0.0);
     }
     // per-tile phase factors (depend on the outer index bits only)
     for (int pid = tid; pid < P.nphase; pid += blockDim.x) {
@@ -225,32 +304,60 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         sincospi(ang, &s, &c);
         s_tileF[pid] = make_double2(c, s);
     }
-    cp_async_commit_wait_all();
+    if (!P.generate) {
+        cp_async_commit_wait_all();
+    } else {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long g = gen_idx[col];
+            unsigned long long tmask = 0;
+            unsigned l = 0;
+            for (int i = 0; i < T; ++i) {
+                tmask |= 1ull << P.tsrc[i];
+                l |= (unsigned)((g >> P.tsrc[i]) & 1ull) << i;
+            }
+            if ((g & ~tmask) == outer_base(P.o_src, o, P.n_outer)) tile[tile_swizzle(l)] = make_double2(1.0, 0.0);
+        }
+    }
     __syncthreads();
 
     const unsigned long long vhi = o << T;
     for (int r = 0; r < P.nrounds; ++r) {
         const RoundDesc &R = P.rounds[r];
         unsigned thrL = 0;
-        for (int i = 0; i < TB; ++i) thrL |= ((tid >> i) & 1u) << R.thr_tb[i];
-        const unsigned swT = tile_swizzle(thrL);
+        for (int k = 0; k < R.nruns; ++k) thrL |= (tid & R.runs[k].mask) << R.runs[k].shift;
+        const unsigned swT = tile_swizzle(thrL) * 16u;
+        if (R.kind == ROUND_PH) {
+            switch (R.nsteps) {
+            case 1: round_ph<1>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
+            case 2: round_ph<2>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
+            case 3: round_ph<3>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
+            default: round_ph<4>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
+            }
+            __syncthreads();
+            continue;
+        }
         double2 a[kSlots];
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) a[s] = tile[swT ^ R.sw_slot[s]];
+        for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
         const unsigned long long vbase = vhi | thrL;
 
         for (int k = R.op_begin; k < R.op_end; ++k) {
             const OpDesc &op = P.ops[k];
-            if (op.kind == OP_PHASE) {
+            const unsigned kind = op.kind;
+            if (kind == OP_PHASE_H || kind == OP_PHASE) {
                 const PhaseTab &pt = ptabs[op.phase_id];
                 const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
-                const double2 lo = make_double2(__ldg(&pt.lo[2 * il]), __ldg(&pt.lo[2 * il + 1]));
-                const double2 hi = make_double2(__ldg(&pt.hi[2 * ih]), __ldg(&pt.hi[2 * ih + 1]));
+                const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
+                const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
                 const double2 F = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
-                Q1T_DISPATCH_J(phase_apply, a, op, F)
+                if (kind == OP_PHASE_H) { Q1T_DISPATCH_J(phase_h_apply, a, op, F) }
+                else { Q1T_DISPATCH_J(phase_apply, a, op, F) }
+            } else if (kind == OP_H_UNNORM) {
+                Q1T_DISPATCH_J(h_unnorm, a)
             } else {
                 if ((vbase & op.cmask) != op.cmask) continue;
-                switch (op.kind) {
+                switch (kind) {
                 case OP_G1_HADAMARD: Q1T_DISPATCH_J(g1_hadamard, a, op) break;
                 case OP_G1_ANTIDIAG: Q1T_DISPATCH_J(g1_antidiag, a, op) break;
                 case OP_G1_SWAPX: Q1T_DISPATCH_J(g1_swapx, a, op) break;
@@ -260,42 +367,50 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
             }
         }
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) tile[swT ^ R.sw_slot[s]] = a[s];
+        for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
         __syncthreads();
     }
 
     // ---- store the tile (coalesced in the destination layout) ----
-    unsigned long long doff_lo = 0;
+    unsigned long long doff = outer_base(P.o_dst, o, P.n_outer);
     unsigned l_lo = 0;
-    for (int i = 0; i < TB; ++i) {
-        const unsigned b = (tid >> i) & 1u;
-        const int tb = P.st_tb[i];
-        doff_lo |= (unsigned long long)b << P.tdst[tb];
-        l_lo |= b << tb;
+    for (int k = 0; k < P.st_nruns; ++k) {
+        doff |= (unsigned long long)(tid & P.st_runs[k].mask) << P.st_runs[k].shift;
+        const int sh = P.st_lruns[k].shift;
+        const unsigned v = tid & P.st_lruns[k].mask;
+        l_lo |= sh >= 0 ? v << sh : v >> -sh;
     }
-    double2 *__restrict__ dst = dst_cols[col] + dbase + doff_lo;
+    double2 *__restrict__ dst = dst_cols[col] + doff;
+    const double scale = P.scale;
+    const unsigned sw_lo = tile_swizzle(l_lo) * 16u;
+    if (scale == 1.0) {
 #pragma unroll
-    for (int i = 0; i < kSlots; ++i) {
-        const unsigned l = l_lo | P.st_l_hi[i];
-        st_global_cs(dst + P.st_off_hi[i], tile[tile_swizzle(l)]);
+        for (int i = 0; i < kSlots; ++i)
+            st_global_cs(dst + P.st_off_hi[i], *reinterpret_cast<const double2 *>(tile_b + (sw_lo ^ P.st_l_hi[i])));
+    } else {
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            const double2 v = *reinterpret_cast<const double2 *>(tile_b + (sw_lo ^ P.st_l_hi[i]));
+            st_global_cs(dst + P.st_off_hi[i], make_double2(v.x * scale, v.y * scale));
+        }
     }
 }
 
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
-                         int ncols, const PhaseTab *d_ptabs, cudaStream_t stream)
+                         int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream)
 {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     const size_t smem = sizeof(double2) << prog.T;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static bool smem_set = false;
+    if (!smem_set) {
         e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << kMaxTileBits));
         if (e != cudaSuccess) return e;
-        smem_set = sizeof(double2) << kMaxTileBits;
+        smem_set = true;
     }
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
-    sweep_kernel<<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs);
+    sweep_kernel<<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
     return cudaGetLastError();
 }
 

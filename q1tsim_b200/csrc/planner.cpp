@@ -44,6 +44,39 @@ static inline uint64_t deposit(uint64_t v, const int *positions, int nbits)
     return r;
 }
 
+// tid bit i -> target bit pos[i] (strictly ascending): group into (mask, shift) runs
+static int make_runs(const int *pos, int nbits, BitRun *runs)
+{
+    int nr = 0;
+    int i = 0;
+    while (i < nbits) {
+        int j = i;
+        uint32_t mask = 0;
+        while (j < nbits && pos[j] - j == pos[i] - i) { mask |= 1u << j; ++j; }
+        runs[nr].mask = mask;
+        runs[nr].shift = pos[i] - i;
+        ++nr;
+        i = j;
+    }
+    return nr;
+}
+
+static void fill_outer_tables(SweepProgram &P)
+{
+    for (int c = 0; c < kOuterChunks; ++c)
+        for (int v = 0; v < (1 << kOuterChunkBits); ++v) {
+            uint64_t so = 0, dof = 0;
+            for (int b = 0; b < kOuterChunkBits; ++b) {
+                const int i = c * kOuterChunkBits + b;
+                if (i >= P.n_outer || !((v >> b) & 1)) continue;
+                so |= 1ull << P.osrc[i];
+                dof |= 1ull << P.odst[i];
+            }
+            P.o_src[c][v] = so;
+            P.o_dst[c][v] = dof;
+        }
+}
+
 // ---------------------------------------------------------------------------
 // lowering
 // ---------------------------------------------------------------------------
@@ -360,14 +393,26 @@ void Planner::close_sweep()
     for (int p = 0; p < kMaxBits; ++p) { tile_index[p] = -1; outer_index[p] = -1; }
     for (int i = 0; i < T; ++i) { P.tsrc[i] = P.tdst[i] = (uint8_t)tile[i]; tile_index[tile[i]] = i; P.st_tb[i] = (uint8_t)i; }
     for (int i = 0; i < P.n_outer; ++i) { P.osrc[i] = P.odst[i] = (uint8_t)outer[i]; outer_index[outer[i]] = i; }
+    fill_outer_tables(P);
+    {
+        int pos[kMaxThrBits + 1];
+        for (int i = 0; i < P.TB; ++i) pos[i] = tile[i];
+        P.ld_nruns = make_runs(pos, P.TB, P.ld_runs);
+        P.st_nruns = make_runs(pos, P.TB, P.st_runs);
+        for (int i = 0; i < P.TB; ++i) pos[i] = i;
+        const int nl = make_runs(pos, P.TB, P.st_lruns);     // identity: one run
+        for (int k = nl; k < P.st_nruns; ++k) { P.st_lruns[k].mask = 0; P.st_lruns[k].shift = 0; }
+    }
     for (int i = 0; i < kSlots; ++i) {
         uint64_t off = 0;
         for (int b = 0; b < kRegBits; ++b)
             if ((i >> b) & 1) off |= 1ull << tile[P.TB + b];
         P.ld_hi[i] = off;
+        P.ld_sw_hi[i] = tile_swizzle((uint32_t)i << P.TB) * 16u;
         P.st_off_hi[i] = off;
-        P.st_l_hi[i] = (uint16_t)(i << P.TB);
+        P.st_l_hi[i] = tile_swizzle((uint32_t)i << P.TB) * 16u;
     }
+    P.scale = 1.0;
     P.nrounds = (int)rounds_.size();
     int nops = 0, nphase = 0;
     for (int r = 0; r < P.nrounds; ++r) {
@@ -382,33 +427,33 @@ void Planner::close_sweep()
         int slot_of_tb[kMaxTileBits + 3];
         for (int tb = 0; tb < T; ++tb) slot_of_tb[tb] = -1;
         for (int j = 0; j < kRegBits; ++j) { R.reg_tb[j] = (uint8_t)regs[j]; slot_of_tb[regs[j]] = j; }
-        // thread bits: the first three should land in distinct shared-memory bank groups (tile bit mod 3)
-        std::vector<int> thr;
-        for (int tb = 0; tb < T; ++tb)
-            if (slot_of_tb[tb] < 0) thr.push_back(tb);
+        // thread bits: the remaining tile bits in ascending order (tid bit i -> tile bit thr[i])
         std::vector<int> ordered;
-        bool used_res[3] = { false, false, false };
-        std::vector<bool> taken(thr.size(), false);
-        for (size_t i = 0; i < thr.size() && ordered.size() < 3; ++i)
-            if (!used_res[thr[i] % 3]) { used_res[thr[i] % 3] = true; ordered.push_back(thr[i]); taken[i] = true; }
-        for (size_t i = 0; i < thr.size(); ++i)
-            if (!taken[i]) ordered.push_back(thr[i]);
+        for (int tb = 0; tb < T; ++tb)
+            if (slot_of_tb[tb] < 0) ordered.push_back(tb);
         int thr_index_of_tb[kMaxTileBits + 3];
         for (int tb = 0; tb < T; ++tb) thr_index_of_tb[tb] = -1;
         for (int i = 0; i < P.TB; ++i) { R.thr_tb[i] = (uint8_t)ordered[i]; thr_index_of_tb[ordered[i]] = i; }
+        R.nruns = (uint8_t)make_runs(ordered.data(), P.TB, R.runs);
         for (int s = 0; s < kSlots; ++s) {
             uint32_t l = 0;
             for (int j = 0; j < kRegBits; ++j)
                 if ((s >> j) & 1) l |= 1u << regs[j];
-            R.sw_slot[s] = (uint16_t)tile_swizzle(l);
+            R.sw_slot[s] = tile_swizzle(l) * 16u;
         }
         R.op_begin = (uint16_t)nops;
-        for (const OpB &ob : rb.ops) {
+        for (size_t oi = 0; oi < rb.ops.size(); ++oi) {
+            const OpB &ob = rb.ops[oi];
             OpDesc &op = P.ops[nops];
             std::memset(&op, 0, sizeof op);
             const int j = slot_of_tb[tile_index[ob.target]];
             op.j = (uint8_t)j;
-            if (!ob.is_phase) {
+            const bool plain_h = !ob.is_phase && ob.kind == OP_G1_HADAMARD && ob.cmask == 0;
+            if (plain_h) {
+                // uncontrolled Hadamard: butterfly only, c = 1/sqrt(2) deferred to the store
+                op.kind = OP_H_UNNORM;
+                P.scale *= ob.m[0];
+            } else if (!ob.is_phase) {
                 op.kind = (uint8_t)ob.kind;
                 std::memcpy(op.m, ob.m, sizeof op.m);
                 for (int p = 0; p < n_; ++p) {
@@ -421,6 +466,14 @@ void Planner::close_sweep()
                 }
             } else {
                 op.kind = OP_PHASE;
+                if (!ob.has_c0 && oi + 1 < rb.ops.size()) {
+                    const OpB &nx = rb.ops[oi + 1];
+                    if (!nx.is_phase && nx.kind == OP_G1_HADAMARD && nx.cmask == 0 && nx.target == ob.target) {
+                        op.kind = OP_PHASE_H;       // phase then butterfly on the same bit, fused
+                        P.scale *= nx.m[0];
+                        ++oi;
+                    }
+                }
                 op.phase_id = (uint32_t)nphase;
                 PhaseTab pt;
                 std::memset(&pt, 0, sizeof pt);
@@ -460,6 +513,39 @@ void Planner::close_sweep()
             ++nops;
         }
         R.op_end = (uint16_t)nops;
+        // ROUND_PH: the round is a ladder of fused (phase, butterfly) steps on slot bits 0,1,2,.. in
+        // order, each phase only coupling to slot bits already processed -> straight-line kernel path
+        R.kind = ROUND_GENERIC;
+        R.nsteps = 0;
+        const int cnt = nops - R.op_begin;
+        bool ladder = cnt >= 1 && cnt <= kRegBits;
+        for (int i = 0; ladder && i < cnt; ++i) {
+            const OpDesc &op = P.ops[R.op_begin + i];
+            if (op.j != i) ladder = false;
+            else if (op.kind == OP_H_UNNORM) continue;
+            else if (op.kind != OP_PHASE_H) ladder = false;
+            else if (op.flags >> i) ladder = false;          // partner among later slot bits, or a c0 term
+        }
+        if (ladder && nphase + cnt <= kMaxPhase) {
+            for (int i = 0; i < cnt; ++i) {
+                OpDesc &op = P.ops[R.op_begin + i];
+                if (op.kind == OP_H_UNNORM) {                // bare butterfly = phase step with unit factors
+                    PhaseTab pt;
+                    std::memset(&pt, 0, sizeof pt);
+                    for (int x = 0; x < (1 << kThrLoBits); ++x) pt.lo[2 * x] = 1.0;
+                    for (int x = 0; x < (1 << (kMaxThrBits - kThrLoBits)); ++x) pt.hi[2 * x] = 1.0;
+                    op.kind = OP_PHASE_H;
+                    op.phase_id = (uint32_t)nphase;
+                    op.flags = 0;
+                    ps.ptabs.push_back(pt);
+                    ++nphase;
+                }
+                for (int q = 0; q < i; ++q)
+                    if (!(op.flags & (1u << q))) { op.m[2 * q] = 1.0; op.m[2 * q + 1] = 0.0; }
+            }
+            R.kind = ROUND_PH;
+            R.nsteps = (uint8_t)cnt;
+        }
     }
     P.nops = nops;
     P.nphase = nphase;
@@ -471,8 +557,68 @@ void Planner::close_sweep()
 }
 
 // ---------------------------------------------------------------------------
-// relabelling sweep (no ops): source bit p goes to destination position dstpos[p]
+// relabelling: source bit p goes to destination position dstpos[p]
 // ---------------------------------------------------------------------------
+// Fill the destination side of a program whose source side (tsrc, osrc, T, TB)
+// is set.  The store is coalesced when the tile contains the sources of the low
+// destination bits.
+void set_relabel(SweepProgram &P, const std::vector<int> &dstpos)
+{
+    const int T = P.T;
+    bool ident = true;
+    for (int i = 0; i < T; ++i) { P.tdst[i] = (uint8_t)dstpos[P.tsrc[i]]; ident = ident && P.tdst[i] == P.tsrc[i]; }
+    for (int i = 0; i < P.n_outer; ++i) { P.odst[i] = (uint8_t)dstpos[P.osrc[i]]; ident = ident && P.odst[i] == P.osrc[i]; }
+    P.relabel = ident ? 0 : 1;
+    std::vector<int> order(T);
+    for (int i = 0; i < T; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return P.tdst[a] < P.tdst[b]; });
+    for (int i = 0; i < T; ++i) P.st_tb[i] = (uint8_t)order[i];
+    int pos[kMaxThrBits + 1];
+    for (int i = 0; i < P.TB; ++i) pos[i] = P.tdst[order[i]];
+    P.st_nruns = make_runs(pos, P.TB, P.st_runs);
+    // tile index of the low part of f: tid bit m -> tile bit order[m]; split at the same places as st_runs
+    // (each run is re-split until both mappings are affine inside it)
+    {
+        BitRun a[kMaxRuns * 2], b[kMaxRuns * 2];
+        int n2 = 0;
+        int i = 0;
+        while (i < P.TB) {
+            int j = i;
+            uint32_t mask = 0;
+            while (j < P.TB && pos[j] - j == pos[i] - i && order[j] - j == order[i] - i) { mask |= 1u << j; ++j; }
+            a[n2].mask = mask; a[n2].shift = pos[i] - i;
+            b[n2].mask = mask; b[n2].shift = order[i] - i;
+            ++n2;
+            i = j;
+        }
+        P.st_nruns = n2;
+        for (int k = 0; k < n2 && k < kMaxRuns; ++k) { P.st_runs[k] = a[k]; P.st_lruns[k] = b[k]; }
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        uint64_t dof = 0;
+        uint32_t l = 0;
+        for (int b = 0; b < kRegBits; ++b) {
+            if (!((i >> b) & 1)) continue;
+            const int tb = order[P.TB + b];
+            dof |= 1ull << P.tdst[tb];
+            l |= 1u << tb;
+        }
+        P.st_off_hi[i] = dof;
+        P.st_l_hi[i] = tile_swizzle(l) * 16u;
+    }
+    fill_outer_tables(P);
+}
+
+// can a relabel be fused into this (gate) sweep?  the sources of the three lowest
+// destination bits must be tile bits so that stores stay 128-byte coalesced
+bool can_fuse_relabel(const SweepProgram &P, const std::vector<int> &dstpos)
+{
+    int found = 0;
+    for (int i = 0; i < P.T; ++i)
+        if (dstpos[P.tsrc[i]] < 3) ++found;
+    return found >= (P.n < 3 ? P.n : 3);
+}
+
 PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos)
 {
     PlannedSweep ps;
@@ -495,27 +641,22 @@ PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &d
     for (int p = 0; p < n; ++p)
         if (!std::binary_search(tile.begin(), tile.end(), p)) outer.push_back(p);
     P.n = n; P.T = T; P.TB = T - kRegBits; P.n_outer = n - T;
-    P.relabel = 1;
-    for (int i = 0; i < T; ++i) { P.tsrc[i] = (uint8_t)tile[i]; P.tdst[i] = (uint8_t)dstpos[tile[i]]; }
-    for (int i = 0; i < P.n_outer; ++i) { P.osrc[i] = (uint8_t)outer[i]; P.odst[i] = (uint8_t)dstpos[outer[i]]; }
-    std::vector<int> order(T);
-    for (int i = 0; i < T; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return P.tdst[a] < P.tdst[b]; });
-    for (int i = 0; i < T; ++i) P.st_tb[i] = (uint8_t)order[i];
-    for (int i = 0; i < kSlots; ++i) {
-        uint64_t so = 0, dof = 0;
-        uint32_t l = 0;
-        for (int b = 0; b < kRegBits; ++b) {
-            if (!((i >> b) & 1)) continue;
-            so |= 1ull << tile[P.TB + b];
-            const int tb = order[P.TB + b];
-            dof |= 1ull << P.tdst[tb];
-            l |= 1u << tb;
-        }
-        P.ld_hi[i] = so;
-        P.st_off_hi[i] = dof;
-        P.st_l_hi[i] = (uint16_t)l;
+    P.scale = 1.0;
+    for (int i = 0; i < T; ++i) P.tsrc[i] = (uint8_t)tile[i];
+    for (int i = 0; i < P.n_outer; ++i) P.osrc[i] = (uint8_t)outer[i];
+    {
+        int pos[kMaxThrBits + 1];
+        for (int i = 0; i < P.TB; ++i) pos[i] = tile[i];
+        P.ld_nruns = make_runs(pos, P.TB, P.ld_runs);
     }
+    for (int i = 0; i < kSlots; ++i) {
+        uint64_t so = 0;
+        for (int b = 0; b < kRegBits; ++b)
+            if ((i >> b) & 1) so |= 1ull << tile[P.TB + b];
+        P.ld_hi[i] = so;
+        P.ld_sw_hi[i] = tile_swizzle((uint32_t)i << P.TB) * 16u;
+    }
+    set_relabel(P, dstpos);
     P.nrounds = 0; P.nops = 0; P.nphase = 0;
     return ps;
 }

@@ -111,6 +111,9 @@ private:
 
 // relabelling sweep: dstpos[p] = destination position of source bit p
 PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos);
+// turn the store side of an existing sweep into a relabelling one (out-of-place launch required)
+void set_relabel(SweepProgram &P, const std::vector<int> &dstpos);
+bool can_fuse_relabel(const SweepProgram &P, const std::vector<int> &dstpos);
 
 // reduce an angle in half-turns to [-1, 1)
 double wrap_half_turns(double a);

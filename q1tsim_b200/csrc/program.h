@@ -17,9 +17,12 @@ constexpr int kRegBits = 4;         // amplitudes per thread = 16
 constexpr int kSlots = 1 << kRegBits;
 constexpr int kMaxThrBits = kMaxTileBits - kRegBits;   // 9 -> 512 threads
 constexpr int kMaxRounds = 24;
-constexpr int kMaxOps = 112;
-constexpr int kMaxPhase = 64;
+constexpr int kMaxOps = 96;
+constexpr int kMaxPhase = 48;
 constexpr int kThrLoBits = 4;       // per-thread phase factor = lo[tid & 15] * hi[tid >> 4]
+constexpr int kMaxRuns = 9;         // bit-deposit runs (mask, shift) of a thread index
+constexpr int kOuterChunkBits = 6;  // outer tile index -> address via 6-bit lookup tables
+constexpr int kOuterChunks = 5;
 
 enum OpKind : uint8_t {
     OP_G1_GENERIC = 0,   // dense complex 2x2 on slot bit j
@@ -28,7 +31,11 @@ enum OpKind : uint8_t {
     OP_G1_SWAPX = 3,     // [[0,1],[1,0]]
     OP_PHASE = 4,        // multiply slots with bit j set by a per-thread phase
     OP_G1_DIAG = 5,      // [[m00,0],[0,m11]] (controlled-diagonal fallback)
+    OP_H_UNNORM = 6,     // [[1,1],[1,-1]]; the 1/sqrt(2) is folded into SweepProgram::scale
+    OP_PHASE_H = 7,      // OP_PHASE followed by OP_H_UNNORM on the same slot bit, fused
 };
+
+enum RoundKind : uint8_t { ROUND_GENERIC = 0, ROUND_PH = 1 };
 
 struct OpDesc {          // 96 bytes
     uint8_t kind;
@@ -43,11 +50,19 @@ struct OpDesc {          // 96 bytes
     uint64_t pad2;
 };
 
+struct BitRun {          // contributes ((v & mask) << shift) (>> -shift if negative) to a deposited index
+    uint32_t mask;
+    int32_t shift;
+};
+
 struct RoundDesc {
     uint8_t reg_tb[kRegBits];       // tile bit of slot bit j
-    uint8_t thr_tb[kMaxThrBits];    // tile bit of thread-index bit i
-    uint8_t pad[3];
-    uint16_t sw_slot[kSlots];       // swizzled shared-memory index contributed by slot s
+    uint8_t thr_tb[kMaxThrBits];    // tile bit of thread-index bit i (ascending)
+    uint8_t nruns;
+    uint8_t kind;                   // ROUND_GENERIC: op interpreter; ROUND_PH: straight-line PHASE_H ladder
+    uint8_t nsteps;                 // ROUND_PH: ops op_begin..op_begin+nsteps-1 act on slot bits 0..nsteps-1
+    BitRun runs[kMaxRuns];          // tid -> tile-local index of the thread
+    uint32_t sw_slot[kSlots];       // byte offset (swizzled index * 16) contributed by slot s
     uint16_t op_begin, op_end;
 };
 
@@ -58,26 +73,39 @@ struct SweepProgram {
     int32_t n_outer;      // n - T
     int32_t nrounds, nops, nphase;
     int32_t relabel;      // 1 if dst positions differ from src positions (out-of-place only)
+    int32_t generate;     // 1: the source column is a basis state |gen_idx[col]>, nothing is read
+    int32_t ld_nruns, st_nruns;
+    int32_t pad0;
+    double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];
     uint8_t osrc[kMaxBits], odst[kMaxBits];
-    // load: element e = tid | i<<TB lives at source offset dep(tid, tsrc[0..TB)) | ld_hi[i], tile index e
+    // tile base address of outer index o = OR over chunks c of o_src[c][(o >> 6c) & 63]
+    uint64_t o_src[kOuterChunks][1 << kOuterChunkBits];
+    uint64_t o_dst[kOuterChunks][1 << kOuterChunkBits];
+    // load: element e = tid | i<<TB lives at source offset dep(tid) | ld_hi[i], tile index e
+    BitRun ld_runs[kMaxRuns];          // tid -> source offset (shift < 64)
     uint64_t ld_hi[kSlots];
+    uint32_t ld_sw_hi[kSlots];         // swizzled byte offset of (i << TB)
     // store: element f = tid | i<<TB (ascending destination position)
     uint8_t st_tb[kMaxTileBits + 3];   // tile bit whose destination position is the f-th smallest
+    BitRun st_runs[kMaxRuns];          // tid -> destination offset
+    BitRun st_lruns[kMaxRuns];         // tid -> tile index
     uint64_t st_off_hi[kSlots];        // destination offset of the high part of f
-    uint16_t st_l_hi[kSlots];          // tile index of the high part of f
+    uint32_t st_l_hi[kSlots];          // swizzled byte offset of the tile index of the high part of f
     RoundDesc rounds[kMaxRounds];
     OpDesc ops[kMaxOps];
 };
 
 // per PHASE op, in global memory
-struct PhaseTab {
+struct alignas(16) PhaseTab {
+    double lo[2 * (1 << kThrLoBits)];                 // complex factors indexed by tid & 15 (16-byte aligned: read as double2)
+    double hi[2 * (1 << (kMaxThrBits - kThrLoBits))]; // complex factors indexed by tid >> 4
     double base;                      // half-turns: constant part of the angle for slots with bit j set
     double outer_coef[kMaxBits];      // half-turns per outer-index bit
-    double lo[2 * (1 << kThrLoBits)];                 // complex factors indexed by tid & 15
-    double hi[2 * (1 << (kMaxThrBits - kThrLoBits))]; // complex factors indexed by tid >> 4
+    double pad;
 };
+static_assert(sizeof(PhaseTab) % 16 == 0, "PhaseTab must keep 16-byte alignment in arrays");
 
 #ifdef __CUDACC__
 #define Q1T_HD __host__ __device__
