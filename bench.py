@@ -34,6 +34,7 @@ def parse_args():
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--shots", type=int, default=8192)
     ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--prefetch-ahead", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -178,10 +179,13 @@ def run_ours(args, rank, world, local):
     st = E.VectorState(n, shots, dev)
     if args.tile_bits:
         st.set_option("tile_bits", args.tile_bits)
+    if args.prefetch_ahead >= 0:
+        st.set_option("prefetch_ahead", args.prefetch_ahead)
     res = np.zeros(shots, dtype=np.uint64)
     rng = E.Rng(seed=2)
 
     def step():
+        # reset to |0..0> (lazy), queue the 480 gates, measure all shots
         st.reset_all()
         for m, b, name in gates:
             st.apply_gate(m, b, name)

@@ -31,7 +31,7 @@ namespace {
 struct PoolEntry { int device; size_t bytes; void *ptr; };
 std::mutex g_pool_mu;
 std::vector<PoolEntry> g_pool;
-const size_t kPoolMaxPerClass = 3;
+const size_t kPoolMaxPerClass = 4;
 
 void *pool_take(int device, size_t bytes)
 {
@@ -64,6 +64,17 @@ void pool_flush(int device)
         else ++i;
     }
 }
+// small scratch allocations go through the same cache (exact-size classes)
+cudaError_t scratch_alloc(int device, void **out, size_t bytes)
+{
+    if (void *p = pool_take(device, bytes)) { *out = p; return cudaSuccess; }
+    return cudaMalloc(out, bytes);
+}
+void scratch_free(int device, void *p, size_t bytes)
+{
+    if (!p) return;
+    if (!pool_give(device, bytes, p)) cudaFree(p);
+}
 }  // namespace
 
 int DeviceVectorState::cuda_fail(cudaError_t e, const char *what)
@@ -91,8 +102,16 @@ DeviceVectorState::~DeviceVectorState()
             if (c.buf && !pool_give(device_, bytes, c.buf)) cudaFree(c.buf);
         for (double2 *p : free_bufs_)
             if (!pool_give(device_, bytes, p)) cudaFree(p);
-        cudaFree(d_colptrs_); cudaFree(d_ptabs_); cudaFree(d_leaf_); cudaFree(d_block_); cudaFree(d_totals_);
-        cudaFree(d_chosen_); cudaFree(d_idx_); cudaFree(d_mat_); cudaFree(d_pair_); cudaFree(d_gen_);
+        scratch_free(device_, d_colptrs_, sizeof(double2 *) * colptrs_cap_);
+        scratch_free(device_, d_ptabs_, sizeof(PhaseTab) * kMaxPhase);
+        scratch_free(device_, d_leaf_, sizeof(double) * leaf_cap_);
+        scratch_free(device_, d_block_, sizeof(double) * block_cap_);
+        scratch_free(device_, d_totals_, sizeof(double) * totals_cap_);
+        scratch_free(device_, d_chosen_, sizeof(double) * draws_cap_);
+        scratch_free(device_, d_idx_, sizeof(uint64_t) * draws_cap_);
+        scratch_free(device_, d_mat_, sizeof(double2) << (2 * kMaxGenericBits));
+        scratch_free(device_, d_pair_, sizeof(double2 *) * 2);
+        scratch_free(device_, d_gen_, sizeof(unsigned long long) * gen_cap_);
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
         cudaStreamDestroy(stream_);
@@ -113,9 +132,9 @@ int DeviceVectorState::ensure_device()
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
-    CK(cudaMalloc(&d_ptabs_, sizeof(PhaseTab) * kMaxPhase));
-    CK(cudaMalloc(&d_mat_, sizeof(double2) << (2 * kMaxGenericBits)));
-    CK(cudaMalloc(&d_pair_, sizeof(double2 *) * 2));
+    CK(scratch_alloc(device_, (void **)&d_ptabs_, sizeof(PhaseTab) * kMaxPhase));
+    CK(scratch_alloc(device_, (void **)&d_mat_, sizeof(double2) << (2 * kMaxGenericBits)));
+    CK(scratch_alloc(device_, (void **)&d_pair_, sizeof(double2 *) * 2));
     return Q1T_OK;
 }
 
@@ -206,9 +225,9 @@ int DeviceVectorState::upload_colptrs(const std::vector<int> &which)
 {
     const size_t need = which.size();
     if (need > colptrs_cap_) {
-        if (d_colptrs_) { CK(cudaStreamSynchronize(stream_)); cudaFree(d_colptrs_); }
+        if (d_colptrs_) { CK(cudaStreamSynchronize(stream_)); scratch_free(device_, d_colptrs_, sizeof(double2 *) * colptrs_cap_); }
         colptrs_cap_ = std::max<size_t>(need * 2, 16);
-        CK(cudaMalloc(&d_colptrs_, sizeof(double2 *) * colptrs_cap_));
+        CK(scratch_alloc(device_, (void **)&d_colptrs_, sizeof(double2 *) * colptrs_cap_));
     }
     std::vector<double2 *> h(need);
     for (size_t i = 0; i < need; ++i) h[i] = cols_[which[i]].buf;
@@ -362,9 +381,9 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             c.basis = false;
         }
         if (which.size() > gen_cap_) {
-            if (d_gen_) cudaFree(d_gen_);
+            if (d_gen_) { CK(cudaStreamSynchronize(stream_)); scratch_free(device_, d_gen_, sizeof(unsigned long long) * gen_cap_); }
             gen_cap_ = std::max<size_t>(which.size() * 2, 16);
-            CK(cudaMalloc(&d_gen_, sizeof(unsigned long long) * gen_cap_));
+            CK(scratch_alloc(device_, (void **)&d_gen_, sizeof(unsigned long long) * gen_cap_));
         }
         CK(cudaMemcpyAsync(d_gen_, gen.data(), sizeof(unsigned long long) * gen.size(), cudaMemcpyHostToDevice, stream_));
     } else {
@@ -383,6 +402,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
         if (!ps.ptabs.empty())
             CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
         ps.prog.generate = (generate && si == 0) ? 1 : 0;
+        ps.prog.prefetch_ahead = (int)prefetch_ahead_;
         const bool last = si + 1 == sweeps.size();
         bool relabel = false;
         if (last && final_relabel && !ident && which.size() == cols_.size()) {
@@ -636,19 +656,19 @@ int DeviceVectorState::ensure_scratch(size_t ncols)
     const size_t nleaves = (size_t)1 << (n_ - leaf_bits);
     const size_t nblocks = (nleaves + kCanonBlock - 1) / kCanonBlock;
     if (ncols * nleaves > leaf_cap_) {
-        if (d_leaf_) cudaFree(d_leaf_);
+        if (d_leaf_) { CK(cudaStreamSynchronize(stream_)); scratch_free(device_, d_leaf_, sizeof(double) * leaf_cap_); }
         leaf_cap_ = ncols * nleaves;
-        CK(cudaMalloc(&d_leaf_, sizeof(double) * leaf_cap_));
+        CK(scratch_alloc(device_, (void **)&d_leaf_, sizeof(double) * leaf_cap_));
     }
     if (ncols * nblocks > block_cap_) {
-        if (d_block_) cudaFree(d_block_);
+        if (d_block_) { CK(cudaStreamSynchronize(stream_)); scratch_free(device_, d_block_, sizeof(double) * block_cap_); }
         block_cap_ = ncols * nblocks;
-        CK(cudaMalloc(&d_block_, sizeof(double) * block_cap_));
+        CK(scratch_alloc(device_, (void **)&d_block_, sizeof(double) * block_cap_));
     }
     if (ncols > totals_cap_) {
-        if (d_totals_) cudaFree(d_totals_);
-        totals_cap_ = ncols * 2;
-        CK(cudaMalloc(&d_totals_, sizeof(double) * totals_cap_));
+        if (d_totals_) { CK(cudaStreamSynchronize(stream_)); scratch_free(device_, d_totals_, sizeof(double) * totals_cap_); }
+        totals_cap_ = std::max<size_t>(ncols * 2, 16);
+        CK(scratch_alloc(device_, (void **)&d_totals_, sizeof(double) * totals_cap_));
     }
     return Q1T_OK;
 }
@@ -834,11 +854,12 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
         if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
         std::sort(chosen.begin(), chosen.end());
         if (cnt > draws_cap_) {
-            if (d_chosen_) cudaFree(d_chosen_);
-            if (d_idx_) cudaFree(d_idx_);
+            CK(cudaStreamSynchronize(stream_));
+            scratch_free(device_, d_chosen_, sizeof(double) * draws_cap_);
+            scratch_free(device_, d_idx_, sizeof(uint64_t) * draws_cap_);
             draws_cap_ = cnt;
-            CK(cudaMalloc(&d_chosen_, sizeof(double) * draws_cap_));
-            CK(cudaMalloc(&d_idx_, sizeof(uint64_t) * draws_cap_));
+            CK(scratch_alloc(device_, (void **)&d_chosen_, sizeof(double) * draws_cap_));
+            CK(scratch_alloc(device_, (void **)&d_idx_, sizeof(uint64_t) * draws_cap_));
         }
         idx.resize(cnt);
         if (cnt) {
@@ -952,6 +973,10 @@ int DeviceVectorState::set_option(const char *key, long value)
         int rc = run_queue();
         if (rc) return rc;
         tile_bits_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "prefetch_ahead")) {
+        prefetch_ahead_ = value < 0 ? 0 : value;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "fuse")) {

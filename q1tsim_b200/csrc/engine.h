@@ -66,6 +66,7 @@ private:
     std::vector<double2 *> free_bufs_;
     std::string err_;
     long tile_bits_ = 12;
+    long prefetch_ahead_ = 0;
     bool fuse_ = true;
 
     // device scratch

@@ -289,6 +289,16 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         const double2 *__restrict__ src = src_cols[col] + soff;
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw_tid ^ P.ld_sw_hi[i]), src + P.ld_hi[i]);
+        // pull the tile that a CTA one residency wave later will stage into L2 (one 128-byte line per 8 threads)
+        if (P.prefetch_ahead > 0 && (tid & 7u) == 0u) {
+            const unsigned long long o2 = o + (unsigned long long)P.prefetch_ahead;
+            if (o2 < (1ull << P.n_outer)) {
+                const double2 *nxt = src_cols[col] + (soff ^ outer_base(P.o_src, o, P.n_outer) ^ outer_base(P.o_src, o2, P.n_outer));
+#pragma unroll
+                for (int i = 0; i < kSlots; ++i)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + P.ld_hi[i]));
+            }
+        }
     } else {
         // the source is the basis state |gen_idx>: synthesise the tile instead of reading it
 #pragma unroll

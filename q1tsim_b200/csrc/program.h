@@ -75,7 +75,7 @@ struct SweepProgram {
     int32_t relabel;      // 1 if dst positions differ from src positions (out-of-place only)
     int32_t generate;     // 1: the source column is a basis state |gen_idx[col]>, nothing is read
     int32_t ld_nruns, st_nruns;
-    int32_t pad0;
+    int32_t prefetch_ahead;   // >0: prefetch the tile this many outer indices ahead into L2
     double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];
