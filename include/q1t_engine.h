@@ -111,6 +111,32 @@ int    q1t_column_totals(q1t_state *st, double *totals_out /* nr_columns */);
 int    q1t_flush(q1t_state *st);
 const char *q1t_last_error(const q1t_state *st);     /* st may be NULL: last constructor error */
 
+/* ---- shard primitives: building blocks of the multi-GPU composition (one process per GPU,
+ * rank r holds the amplitudes whose top log2(P) index bits equal r).  They expose
+ * the pieces of measure_into / measure_all_into (vectorstate.rs:106-161, 237-329) so that the
+ * host can chain the per-rank canonical totals in rank order and keep one generator stream. ---- */
+int    q1t_state_new_empty(size_t nr_bits, size_t nr_shots, int device, q1t_state **out);   /* one all-zero column */
+size_t q1t_nr_leaves(const q1t_state *st);            /* canonical leaves per column: 2^nr_bits / min(2^nr_bits, 1024) */
+/* canonical leaf totals of |amp|^2 per column (qbit < nr_bits: only amplitudes with that qubit == 0;
+ * SIZE_MAX: all).  out holds nr_columns * nr_leaves doubles. */
+int    q1t_leaf_totals(q1t_state *st, size_t qbit, double *out);
+/* resolve sorted draws of column col against caller-supplied inclusive leaf prefixes P[nr_leaves];
+ * `base` = total weight before this shard (0 on one GPU) */
+int    q1t_resolve_draws(q1t_state *st, size_t col, const double *P, double base, const double *chosen,
+                         size_t nr_draws, uint64_t *idx_out);
+/* collapse on a qubit that is a rank bit: every column is scaled by f0[c] (n0 == count), f1[c]
+ * (n0 == 0) or split into (f0-scaled, f1-scaled) copies; a factor 0 zeroes this rank's shard */
+int    q1t_scale_split_columns(q1t_state *st, const double *f0, const double *f1, const size_t *n0);
+/* collapse/renormalise/branch with (w0, n0) decided by the caller (vectorstate.rs:277-326) */
+int    q1t_collapse_columns(q1t_state *st, size_t qbit, const double *w0, const size_t *n0);
+/* replace all columns by basis states |idx[k]> (UINT64_MAX: an all-zero column) with counts[k] shots */
+int    q1t_replace_columns(q1t_state *st, size_t nr_columns, const uint64_t *idx, const size_t *counts);
+/* device pointer of a (flushed, materialised) column: 2^nr_bits complex128, for peer exchange */
+int    q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr);
+/* rand 0.7 Uniform(0,total) draws as WeightedIndex::sample makes them (vectorstate.rs:126) */
+double q1t_uniform_draw(q1t_rng rng, double total);
+void   q1t_uniform_draws(q1t_rng rng, double total, size_t n, double *out);
+
 /* execution statistics since creation / last reset of the counters */
 typedef struct {
     uint64_t gates_queued;        /* logical gates received */

@@ -11,7 +11,7 @@ using q1t::DeviceVectorState;
 
 static thread_local std::string g_ctor_error;
 
-static int make_state(size_t nr_bits, size_t nr_shots, int device, const double *coefs, q1t_state **out)
+static int make_state(size_t nr_bits, size_t nr_shots, int device, const double *coefs, q1t_state **out, bool empty = false)
 {
     if (!out) { g_ctor_error = "NULL output pointer"; return Q1T_ERR_INVALID_ARGUMENT; }
     *out = nullptr;
@@ -20,7 +20,7 @@ static int make_state(size_t nr_bits, size_t nr_shots, int device, const double 
     if (!st) { g_ctor_error = "out of host memory"; return Q1T_ERR_CUDA; }
     st->impl = new DeviceVectorState(nr_bits, nr_shots, device);
     st->owns = true;
-    const int rc = coefs ? st->impl->init_from_qubit_coefs(coefs) : st->impl->init_zero_state();
+    const int rc = empty ? st->impl->init_empty() : coefs ? st->impl->init_from_qubit_coefs(coefs) : st->impl->init_zero_state();
     if (rc) {
         g_ctor_error = st->impl->last_error();
         delete st->impl;
@@ -41,6 +41,10 @@ int q1t_state_from_qubit_coefs(const double *coefs, size_t nr_bits, size_t nr_sh
 {
     if (!coefs) { g_ctor_error = "NULL coefficient array"; return Q1T_ERR_INVALID_ARGUMENT; }
     return make_state(nr_bits, nr_shots, device, coefs, out);
+}
+int q1t_state_new_empty(size_t nr_bits, size_t nr_shots, int device, q1t_state **out)
+{
+    return make_state(nr_bits, nr_shots, device, nullptr, out, true);
 }
 void q1t_state_free(q1t_state *st)
 {
@@ -123,6 +127,39 @@ int q1t_write_amplitudes(q1t_state *st, size_t col, size_t off, size_t len, cons
 int q1t_marginal0(q1t_state *st, size_t qbit, double *out) { ST_OR_FAIL; return st->impl->marginal0(qbit, out); }
 int q1t_column_totals(q1t_state *st, double *out) { ST_OR_FAIL; return st->impl->column_totals(out); }
 int q1t_flush(q1t_state *st) { ST_OR_FAIL; return st->impl->flush(); }
+size_t q1t_nr_leaves(const q1t_state *st) { return st ? st->impl->nr_leaves() : 0; }
+int q1t_leaf_totals(q1t_state *st, size_t qbit, double *out) { ST_OR_FAIL; return st->impl->leaf_totals(qbit, out); }
+int q1t_resolve_draws(q1t_state *st, size_t col, const double *P, double base, const double *chosen, size_t nd, uint64_t *idx)
+{
+    ST_OR_FAIL;
+    return st->impl->resolve_draws(col, P, base, chosen, nd, idx);
+}
+int q1t_scale_split_columns(q1t_state *st, const double *f0, const double *f1, const size_t *n0)
+{
+    ST_OR_FAIL;
+    return st->impl->scale_split_columns(f0, f1, n0);
+}
+int q1t_collapse_columns(q1t_state *st, size_t qbit, const double *w0, const size_t *n0)
+{
+    ST_OR_FAIL;
+    return st->impl->collapse_columns(qbit, w0, n0);
+}
+int q1t_replace_columns(q1t_state *st, size_t ncols, const uint64_t *idx, const size_t *counts)
+{
+    ST_OR_FAIL;
+    return st->impl->replace_columns(ncols, idx, counts);
+}
+int q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr) { ST_OR_FAIL; return st->impl->column_ptr(col, ptr); }
+double q1t_uniform_draw(q1t_rng rng, double total)
+{
+    const q1t::UniformF64 u = q1t::uniform_new(0.0, total);
+    return q1t::uniform_sample(u, rng);
+}
+void q1t_uniform_draws(q1t_rng rng, double total, size_t n, double *out)
+{
+    const q1t::UniformF64 u = q1t::uniform_new(0.0, total);
+    for (size_t i = 0; i < n; ++i) out[i] = q1t::uniform_sample(u, rng);
+}
 const char *q1t_last_error(const q1t_state *st) { return st ? st->impl->last_error() : g_ctor_error.c_str(); }
 int q1t_get_stats(q1t_state *st, q1t_stats *out) { ST_OR_FAIL; if (!out) return Q1T_ERR_INVALID_ARGUMENT; *out = st->impl->stats; return Q1T_OK; }
 int q1t_reset_stats(q1t_state *st) { ST_OR_FAIL; std::memset(&st->impl->stats, 0, sizeof(q1t_stats)); return Q1T_OK; }

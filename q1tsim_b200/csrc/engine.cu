@@ -763,14 +763,28 @@ int DeviceVectorState::measure_into(size_t qbit, size_t cbit, uint64_t *res, siz
         if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
     }
     size_t start = 0;
+    for (size_t c = 0; c < cols_.size(); ++c) {
+        const size_t n0 = n0s[c], cnt = cols_[c].count;
+        for (size_t j = start; j < start + n0; ++j) res[j] &= zero_mask;
+        for (size_t j = start + n0; j < start + cnt; ++j) res[j] |= one_mask;
+        start += cnt;
+    }
+    if (!collapse) return Q1T_OK;
+    return collapse_columns(qbit, w0s.data(), n0s.data());
+}
+
+// collapse / renormalise / branch every column given (w0, n0) per column
+// (vectorstate.rs:277-326); column order after a split: [0-branch, 1-branch]
+int DeviceVectorState::collapse_columns(size_t qbit, const double *w0s, const size_t *n0s)
+{
+    if (qbit >= (size_t)n_) return fail(Q1T_ERR_INVALID_QBIT, "Invalid index for a quantum bit");
+    int rc = flush();
+    if (rc) return rc;
+    const int bitpos = n_ - 1 - (int)qbit;
     std::vector<Column> nc;
     for (size_t c = 0; c < cols_.size(); ++c) {
         Column col = cols_[c];
         const size_t n0 = n0s[c], cnt = col.count;
-        for (size_t j = start; j < start + n0; ++j) res[j] &= zero_mask;
-        for (size_t j = start + n0; j < start + cnt; ++j) res[j] |= one_mask;
-        start += cnt;
-        if (!collapse) continue;
         const double w0 = w0s[c];
         const double f0 = 1.0 / std::sqrt(w0), f1 = 1.0 / std::sqrt(1.0 - w0);
         if (col.basis) {
@@ -787,7 +801,7 @@ int DeviceVectorState::measure_into(size_t qbit, size_t cbit, uint64_t *res, siz
         } else {
             Column one;
             rc = alloc_column(&one.buf);
-            if (rc) { cols_[c] = col; return rc; }
+            if (rc) return rc;
             CK(launch_collapse(col.buf, col.buf, one.buf, n_, bitpos, f0, f1, stream_));
             col.count = n0;
             one.count = cnt - n0;
@@ -797,12 +811,168 @@ int DeviceVectorState::measure_into(size_t qbit, size_t cbit, uint64_t *res, siz
         stats.kernel_launches++;
         stats.sweep_column_passes++;
     }
-    (void)bit;
-    if (collapse) {
-        stats.sweeps++;
-        cols_.swap(nc);
-        CK(cudaStreamSynchronize(stream_));
+    stats.sweeps++;
+    cols_.swap(nc);
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// ---------------------------------------------------------------------------
+// shard primitives: building blocks of the multi-GPU composition
+// (q1tsim_b200/sharded.py).  The host chains the per-rank canonical leaf totals
+// in rank order, so the distributed reduction is the same fixed geometry as the
+// single-GPU one.
+// ---------------------------------------------------------------------------
+int DeviceVectorState::init_empty()
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    Column c;
+    rc = alloc_column(&c.buf);
+    if (rc) return rc;
+    c.count = shots_;
+    CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
+    cols_.push_back(c);
+    return Q1T_OK;
+}
+
+size_t DeviceVectorState::nr_leaves() const
+{
+    const int leaf_bits = n_ < kCanonLeafBits ? n_ : kCanonLeafBits;
+    return (size_t)1 << (n_ - leaf_bits);
+}
+
+// canonical leaf totals of every column (all amplitudes, or those with qubit `qbit` == 0)
+int DeviceVectorState::leaf_totals(size_t qbit, double *out)
+{
+    int rc = flush();
+    if (rc) return rc;
+    for (Column &c : cols_) {
+        rc = materialize(c);
+        if (rc) return rc;
     }
+    std::vector<int> all;
+    for (size_t c = 0; c < cols_.size(); ++c) all.push_back((int)c);
+    rc = ensure_scratch(all.size());
+    if (rc) return rc;
+    rc = upload_colptrs(all);
+    if (rc) return rc;
+    const uint64_t mask = qbit < (size_t)n_ ? 1ull << (n_ - 1 - (int)qbit) : 0ull;
+    time_begin();
+    CK(launch_leaf_totals(d_colptrs_, (int)all.size(), d_leaf_, n_, mask, 0, stream_));
+    time_end(stats.read_ms);
+    stats.kernel_launches++;
+    stats.read_passes += all.size();
+    CK(cudaMemcpyAsync(out, d_leaf_, sizeof(double) * all.size() * nr_leaves(), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// resolve sorted draws against caller-supplied inclusive leaf prefixes P (global chain)
+int DeviceVectorState::resolve_draws(size_t col, const double *P, double base, const double *chosen, size_t nd, uint64_t *idx)
+{
+    if (col >= cols_.size()) return fail(Q1T_ERR_INVALID_ARGUMENT, "column out of range");
+    int rc = flush();
+    if (rc) return rc;
+    rc = materialize(cols_[col]);
+    if (rc) return rc;
+    if (nd == 0) return Q1T_OK;
+    rc = ensure_scratch(1);
+    if (rc) return rc;
+    const size_t nl = nr_leaves(), nb = (nl + kCanonBlock - 1) / kCanonBlock;
+    if (nd > draws_cap_) {
+        CK(cudaStreamSynchronize(stream_));
+        scratch_free(device_, d_chosen_, sizeof(double) * draws_cap_);
+        scratch_free(device_, d_idx_, sizeof(uint64_t) * draws_cap_);
+        draws_cap_ = nd;
+        CK(scratch_alloc(device_, (void **)&d_chosen_, sizeof(double) * draws_cap_));
+        CK(scratch_alloc(device_, (void **)&d_idx_, sizeof(uint64_t) * draws_cap_));
+    }
+    CK(cudaMemcpyAsync(d_leaf_, P, sizeof(double) * nl, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemsetAsync(d_block_, 0, sizeof(double) * nb, stream_));      // P is already the full prefix
+    CK(cudaMemcpyAsync(d_chosen_, chosen, sizeof(double) * nd, cudaMemcpyHostToDevice, stream_));
+    CK(launch_resolve_draws(cols_[col].buf, d_leaf_, d_block_, n_, d_chosen_, nd, reinterpret_cast<unsigned long long *>(d_idx_), base, stream_));
+    stats.kernel_launches++;
+    CK(cudaMemcpyAsync(idx, d_idx_, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// collapse on a qubit that is a rank bit: this rank keeps (scaled by f0 / f1) or zeroes whole
+// columns; column structure follows n0 exactly as collapse_columns does
+int DeviceVectorState::scale_split_columns(const double *f0, const double *f1, const size_t *n0s)
+{
+    int rc = flush();
+    if (rc) return rc;
+    std::vector<Column> nc;
+    for (size_t c = 0; c < cols_.size(); ++c) {
+        rc = materialize(cols_[c]);
+        if (rc) return rc;
+        Column col = cols_[c];
+        const size_t n0 = n0s[c], cnt = col.count;
+        if (n0 == cnt) {
+            CK(launch_scale2(col.buf, col.buf, nullptr, n_, f0[c], 0.0, stream_));
+            nc.push_back(col);
+        } else if (n0 == 0) {
+            CK(launch_scale2(col.buf, col.buf, nullptr, n_, f1[c], 0.0, stream_));
+            nc.push_back(col);
+        } else {
+            Column one;
+            rc = alloc_column(&one.buf);
+            if (rc) return rc;
+            CK(launch_scale2(col.buf, col.buf, one.buf, n_, f0[c], f1[c], stream_));
+            col.count = n0;
+            one.count = cnt - n0;
+            nc.push_back(col);
+            nc.push_back(one);
+        }
+        stats.kernel_launches++;
+        stats.sweep_column_passes++;
+    }
+    stats.sweeps++;
+    cols_.swap(nc);
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// replace the column list by basis states (idx) or all-zero columns (idx == UINT64_MAX)
+int DeviceVectorState::replace_columns(size_t ncols, const uint64_t *idx, const size_t *counts)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    queue_.clear();
+    queue_cols_.clear();
+    CK(cudaStreamSynchronize(stream_));
+    for (Column &c : cols_)
+        if (c.buf) release_column(c.buf);
+    cols_.clear();
+    for (int l = 0; l < n_; ++l) perm_[l] = l;
+    for (size_t k = 0; k < ncols; ++k) {
+        Column c;
+        c.count = counts[k];
+        if (idx[k] == UINT64_MAX) {
+            rc = alloc_column(&c.buf);
+            if (rc) return rc;
+            CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
+        } else {
+            if (idx[k] >> n_) return fail(Q1T_ERR_INVALID_ARGUMENT, "basis index out of range");
+            c.basis = true;
+            c.basis_idx = idx[k];
+        }
+        cols_.push_back(c);
+    }
+    return Q1T_OK;
+}
+
+int DeviceVectorState::column_ptr(size_t col, void **ptr)
+{
+    if (col >= cols_.size() || !ptr) return fail(Q1T_ERR_INVALID_ARGUMENT, "column out of range");
+    int rc = flush();
+    if (rc) return rc;
+    rc = materialize(cols_[col]);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(stream_));
+    *ptr = cols_[col].buf;
     return Q1T_OK;
 }
 
@@ -866,7 +1036,7 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
             CK(cudaMemcpyAsync(d_chosen_, chosen.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice, stream_));
             time_begin();
             CK(launch_resolve_draws(cols_[c].buf, d_leaf_ + k * nleaves, d_block_ + k * nblocks, n_, d_chosen_, cnt,
-                                    reinterpret_cast<unsigned long long *>(d_idx_), stream_));
+                                    reinterpret_cast<unsigned long long *>(d_idx_), 0.0, stream_));
             time_end(stats.read_ms);
             stats.kernel_launches++;
             CK(cudaMemcpyAsync(idx.data(), d_idx_, sizeof(uint64_t) * cnt, cudaMemcpyDeviceToHost, stream_));

@@ -39,6 +39,16 @@ public:
     int reset(size_t bit, q1t_rng rng);
     int reset_all();
 
+    // shard primitives (multi-GPU composition)
+    int init_empty();
+    size_t nr_leaves() const;
+    int leaf_totals(size_t qbit, double *out);
+    int resolve_draws(size_t col, const double *P, double base, const double *chosen, size_t nd, uint64_t *idx);
+    int scale_split_columns(const double *f0, const double *f1, const size_t *n0s);
+    int collapse_columns(size_t qbit, const double *w0s, const size_t *n0s);
+    int replace_columns(size_t ncols, const uint64_t *idx, const size_t *counts);
+    int column_ptr(size_t col, void **ptr);
+
     int counts(size_t *out);
     size_t nr_columns() { return cols_.size(); }
     int read_amplitudes(size_t col, size_t offset, size_t len, double *out);

@@ -566,7 +566,7 @@ __device__ __forceinline__ double leaf_prefix(const double *__restrict__ inblock
 __global__ void resolve_draws_kernel(const double2 *__restrict__ st, const double *__restrict__ inblock,
                                      const double *__restrict__ bpref, int n, int leaf_bits,
                                      const double *__restrict__ chosen, unsigned long long ndraws,
-                                     unsigned long long *__restrict__ idx_out)
+                                     unsigned long long *__restrict__ idx_out, double base)
 {
     const unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (j >= ndraws) return;
@@ -577,7 +577,7 @@ __global__ void resolve_draws_kernel(const double2 *__restrict__ st, const doubl
         const unsigned long long mid = (lo + hi) >> 1;
         if (leaf_prefix(inblock, bpref, mid) <= ch) lo = mid + 1; else hi = mid;
     }
-    double run = lo == 0 ? 0.0 : leaf_prefix(inblock, bpref, lo - 1);
+    double run = lo == 0 ? base : leaf_prefix(inblock, bpref, lo - 1);   // base: weight before this shard
     const unsigned leaf = 1u << leaf_bits;
     const double2 *__restrict__ p = st + (lo << leaf_bits);
     unsigned found = 0xffffffffu, last_nz = 0xffffffffu;
@@ -624,12 +624,12 @@ cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int n
 
 cudaError_t launch_resolve_draws(const double2 *d_col, const double *d_leaf, const double *d_block, int n,
                                  const double *d_chosen, unsigned long long ndraws, unsigned long long *d_idx,
-                                 cudaStream_t stream)
+                                 double base, cudaStream_t stream)
 {
     if (ndraws == 0) return cudaSuccess;
     const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
     resolve_draws_kernel<<<(unsigned)((ndraws + 63) / 64), 64, 0, stream>>>(d_col, d_leaf, d_block, n, leaf_bits, d_chosen,
-                                                                         ndraws, d_idx);
+                                                                         ndraws, d_idx, base);
     return cudaGetLastError();
 }
 
@@ -688,6 +688,27 @@ cudaError_t launch_product_state(double2 *d_col, int n, const double2 *d_coefs, 
     unsigned long long blocks = (N + 255) / 256;
     if (blocks > 148ull * 16ull) blocks = 148ull * 16ull;
     product_state_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_col, n, d_coefs);
+    return cudaGetLastError();
+}
+
+// out0 = in * f0, out1 = in * f1 (either output may be null, out0 may alias in): collapse of a
+// qubit that is a rank bit of a sharded state -- the whole shard is kept (scaled) or zeroed
+__global__ void __launch_bounds__(256)
+scale2_kernel(const double2 *in, double2 *out0, double2 *out1, unsigned long long N, double f0, double f1)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < N;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2 v = in[i];
+        if (out0) out0[i] = make_double2(__dmul_rn(v.x, f0), __dmul_rn(v.y, f0));
+        if (out1) out1[i] = make_double2(__dmul_rn(v.x, f1), __dmul_rn(v.y, f1));
+    }
+}
+cudaError_t launch_scale2(const double2 *d_in, double2 *d_out0, double2 *d_out1, int n, double f0, double f1, cudaStream_t stream)
+{
+    const unsigned long long N = 1ull << n;
+    unsigned long long blocks = (N + 255) / 256;
+    if (blocks > 148ull * 16ull) blocks = 148ull * 16ull;
+    scale2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_in, d_out0, d_out1, N, f0, f1);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,545 @@
+"""Multi-GPU statevector: one process per GPU, the state sharded by its top
+log2(P) index bits.
+
+`ShardedState` offers the `QuState` interface of the reference
+(src/qustate.rs:5-89) for states too large for one GPU.  Rank r of P = 2^g holds
+the amplitudes whose top g index bits equal r (qubit 0 is the most significant
+index bit, vectorstate.rs:249-250, so qubits 0..g-1 start out "global").  Every
+rank runs the single-GPU engine on its 2^(n-g) shard; this module is the host
+composition around it:
+
+* gates that act diagonally on their global qubits (controls, controlled phases,
+  Z/S/T/RZ/U1...) never communicate: each rank applies the block of the gate
+  matrix selected by its own rank bits;
+* a gate that is non-diagonal on a global qubit first brings that qubit on chip
+  by a **qubit remap**: a pairwise exchange of half a shard with rank
+  r ^ (1 << i) (`torch.distributed` send/recv over NCCL/NVLink), after which the
+  logical->physical map is updated; `Swap` gates are pure relabels;
+* marginals and sampling chain the per-rank canonical leaf totals in rank order
+  on the host, so results equal the single-GPU (and oracle) canonical order bit
+  for bit; all ranks consume identical copies of the caller's generator.
+
+All ranks must make the same calls in the same order (SPMD).
+"""
+import math
+
+import numpy as np
+
+LEAF = 1024
+BLOCK = 1024
+ZERO_COLUMN = 0xFFFFFFFFFFFFFFFF
+SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+class EngineLocal:
+    """The CUDA engine as the per-rank local state (inner C ABI + shard primitives)."""
+
+    def __init__(self, n_local, shots, device, empty):
+        import ctypes as C
+        from . import engine as E
+        self.E, self.C = E, C
+        self.n_local, self.shots = n_local, shots
+        L = E.lib()
+        self.L = L
+        sz, dp, szp, u64p, vp = C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.c_void_p
+        L.q1t_state_new_empty.restype = C.c_int
+        L.q1t_state_new_empty.argtypes = [sz, sz, C.c_int, C.POINTER(vp)]
+        L.q1t_nr_leaves.restype = sz
+        L.q1t_nr_leaves.argtypes = [vp]
+        L.q1t_leaf_totals.restype = C.c_int
+        L.q1t_leaf_totals.argtypes = [vp, sz, dp]
+        L.q1t_resolve_draws.restype = C.c_int
+        L.q1t_resolve_draws.argtypes = [vp, sz, dp, C.c_double, dp, sz, u64p]
+        L.q1t_collapse_columns.restype = C.c_int
+        L.q1t_collapse_columns.argtypes = [vp, sz, dp, szp]
+        L.q1t_scale_split_columns.restype = C.c_int
+        L.q1t_scale_split_columns.argtypes = [vp, dp, dp, szp]
+        L.q1t_replace_columns.restype = C.c_int
+        L.q1t_replace_columns.argtypes = [vp, sz, u64p, szp]
+        L.q1t_column_device_ptr.restype = C.c_int
+        L.q1t_column_device_ptr.argtypes = [vp, sz, C.POINTER(vp)]
+        if empty:
+            self.st = E.VectorState.__new__(E.VectorState)
+            p = vp()
+            rc = L.q1t_state_new_empty(n_local, shots, device, C.byref(p))
+            if rc:
+                raise E.EngineError(rc, L.q1t_last_error(None).decode())
+            self.st._p, self.st.nr_bits, self.st.nr_shots = p, n_local, shots
+        else:
+            self.st = E.VectorState(n_local, shots, device)
+        self.device = device
+
+    # gates
+    def apply_gate(self, mat, qubits):
+        self.st.apply_gate(mat, qubits)
+
+    def apply_conditional_gate(self, control, mat, qubits):
+        self.st.apply_conditional_gate(control, mat, qubits)
+
+    # structure
+    @property
+    def ncols(self):
+        return self.st.ncols
+
+    @property
+    def counts(self):
+        return self.st.counts
+
+    @property
+    def nleaves(self):
+        return int(self.L.q1t_nr_leaves(self.st._p))
+
+    def read_column(self, col):
+        return self.st.column(col)
+
+    def write_column(self, col, amps):
+        self.st.set_column(col, amps)
+
+    # shard primitives
+    def leaf_totals(self, qubit):
+        C = self.C
+        out = np.zeros(self.ncols * self.nleaves, dtype=np.float64)
+        q = (1 << 64) - 1 if qubit is None else qubit
+        self.st._chk(self.L.q1t_leaf_totals(self.st._p, q, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.reshape(self.ncols, self.nleaves)
+
+    def resolve_draws(self, col, P, base, chosen):
+        C = self.C
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        chosen = np.ascontiguousarray(chosen, dtype=np.float64)
+        idx = np.zeros(max(chosen.size, 1), dtype=np.uint64)
+        self.st._chk(self.L.q1t_resolve_draws(self.st._p, col, P.ctypes.data_as(C.POINTER(C.c_double)), float(base),
+                                              chosen.ctypes.data_as(C.POINTER(C.c_double)), chosen.size,
+                                              idx.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return idx[:chosen.size]
+
+    def collapse_columns(self, qubit, w0, n0):
+        C = self.C
+        w0 = np.ascontiguousarray(w0, dtype=np.float64)
+        n0a = (C.c_size_t * max(len(n0), 1))(*[int(v) for v in n0])
+        self.st._chk(self.L.q1t_collapse_columns(self.st._p, qubit, w0.ctypes.data_as(C.POINTER(C.c_double)), n0a))
+
+    def scale_split_columns(self, f0, f1, n0):
+        C = self.C
+        f0 = np.ascontiguousarray(f0, dtype=np.float64)
+        f1 = np.ascontiguousarray(f1, dtype=np.float64)
+        n0a = (C.c_size_t * max(len(n0), 1))(*[int(v) for v in n0])
+        self.st._chk(self.L.q1t_scale_split_columns(self.st._p, f0.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    f1.ctypes.data_as(C.POINTER(C.c_double)), n0a))
+
+    def replace_columns(self, idx, counts):
+        C = self.C
+        ia = (C.c_uint64 * max(len(idx), 1))(*[int(v) for v in idx])
+        ca = (C.c_size_t * max(len(counts), 1))(*[int(v) for v in counts])
+        self.st._chk(self.L.q1t_replace_columns(self.st._p, len(idx), ia, ca))
+
+    def column_tensor(self, col):
+        """zero-copy torch view (2^n_local * 2,) float64 of a flushed column on the device"""
+        import torch
+        C = self.C
+        p = C.c_void_p()
+        self.st._chk(self.L.q1t_column_device_ptr(self.st._p, col, C.byref(p)))
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (2 << self.n_local,), "typestr": "<f8", "data": (p.value, False), "version": 2}
+        return torch.as_tensor(v, device=torch.device("cuda", self.device))
+
+    def draws(self, rng, total, n):
+        C = self.C
+        out = np.zeros(max(n, 1), dtype=np.float64)
+        self.L.q1t_uniform_draws.restype = None
+        self.L.q1t_uniform_draws.argtypes = [self.E._RngHandle, C.c_double, C.c_size_t, C.POINTER(C.c_double)]
+        self.L.q1t_uniform_draws(rng.handle, float(total), n, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out[:n]
+
+    def binomial(self, rng, n, p):
+        return rng.binomial(n, p)
+
+    def skip_words(self, rng, n):
+        self.draws(rng, 1.0, n)
+
+    def stats(self):
+        return self.st.stats()
+
+    def set_timing(self, on):
+        self.st.set_timing(on)
+
+    def reset_stats(self):
+        self.st.reset_stats()
+
+
+def _engine_factory(n_local, shots, device, empty):
+    return EngineLocal(n_local, shots, device, empty)
+
+
+def acts_diagonally(mat, k, positions):
+    """True if the k-qubit matrix never couples different values of the gate bits `positions`
+    (gate bit j is bit k-1-j of the matrix index, gates.rs:53-80)."""
+    m = np.asarray(mat)
+    G = 1 << k
+    mask = 0
+    for j in positions:
+        mask |= 1 << (k - 1 - j)
+    r = np.arange(G)
+    differ = (r[:, None] & mask) != (r[None, :] & mask)
+    return not np.any(m[differ] != 0)
+
+
+def select_block(mat, k, fixed):
+    """Sub-matrix for fixed values of some gate bits: fixed = {gate bit j: value}; returns the
+    matrix on the remaining gate bits (order preserved)."""
+    m = np.asarray(mat, dtype=np.complex128)
+    G = 1 << k
+    mask = want = 0
+    for j, v in fixed.items():
+        mask |= 1 << (k - 1 - j)
+        want |= int(v) << (k - 1 - j)
+    keep = [x for x in range(G) if (x & mask) == want]
+    return m[np.ix_(keep, keep)]
+
+
+class ShardedState:
+    """`QuState` over a state sharded across the ranks of a process group."""
+
+    def __init__(self, nr_bits, nr_shots, group=None, device=None, local_factory=None, lookahead=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.g = int(round(math.log2(self.P)))
+        if (1 << self.g) != self.P:
+            raise ValueError("the number of ranks must be a power of two")
+        self.n, self.shots = nr_bits, nr_shots
+        self.n_local = nr_bits - self.g
+        if self.n_local < 10:
+            raise ValueError("sharded states need at least 10 local qubits per rank (one canonical leaf)")
+        factory = local_factory or _engine_factory
+        self.device = self.rank if device is None else device
+        self.local = factory(self.n_local, nr_shots, self.device, self.rank != 0)
+        # where[q] = ("g", rank bit) | ("l", local engine qubit); canonical: q < g global
+        self.where = [self._canonical(q) for q in range(nr_bits)]
+        self.exchanges = 0
+        self.exchanged_bytes = 0
+        self.lookahead = lookahead        # optional callable(list of candidate logical qubits) -> victim
+
+    # ---- layout bookkeeping ------------------------------------------------
+    def _canonical(self, q):
+        return ("g", self.g - 1 - q) if q < self.g else ("l", q - self.g)
+
+    def _rank_bit(self, i):
+        return (self.rank >> i) & 1
+
+    def _qubit_at(self, place):
+        return self.where.index(place)
+
+    # ---- the exchange --------------------------------------------------------
+    def _exchange(self, gbit, victim_local):
+        """swap the contents of rank bit `gbit` and local engine qubit `victim_local`: every rank
+        trades the half of its shard where the local bit differs from its rank bit with rank
+        r ^ (1 << gbit) (qubit remap)."""
+        import torch
+        dist = self.dist
+        partner = self.rank ^ (1 << gbit)
+        mybit = self._rank_bit(gbit)
+        j = victim_local
+        if j > 3:
+            # exchanging a low index bit would mean millions of tiny strided messages: first move the
+            # victim to the top local qubit (a relabel inside the engine, one local sweep at most)
+            top = self._qubit_at(("l", 0))
+            vq = self._qubit_at(("l", j))
+            self.local.apply_gate(SWAP, [0, j])
+            self.where[top], self.where[vq] = ("l", j), ("l", 0)
+            j = 0
+        hi, lo = 1 << j, (1 << (self.n_local - 1 - j)) * 2            # doubles per contiguous run
+        max_piece = 1 << 27                                              # 1 GiB of doubles per message
+        for col in range(self.local.ncols):
+            t = self.local.column_tensor(col).view(hi, 2, lo)
+            half = t[:, 1 - mybit, :]
+            scratch = None
+            for h in range(hi):
+                run = half[h]
+                for off in range(0, lo, max_piece):
+                    piece = run[off:off + max_piece]
+                    if scratch is None or scratch.numel() != piece.numel():
+                        scratch = torch.empty_like(piece)
+                    ops = [dist.P2POp(dist.isend, piece, partner, self.group), dist.P2POp(dist.irecv, scratch, partner, self.group)]
+                    if self.rank > partner:
+                        ops.reverse()
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                    piece.copy_(scratch)
+                    self.exchanged_bytes += piece.numel() * 8
+            if t.is_cuda:
+                torch.cuda.synchronize(t.device)
+        self.exchanges += 1
+        qg, ql = self._qubit_at(("g", gbit)), self._qubit_at(("l", j))
+        self.where[qg], self.where[ql] = ("l", j), ("g", gbit)
+
+    def _bring_local(self, q, keep=()):
+        """make logical qubit q a local qubit; evict a local qubit not in `keep`"""
+        kind, i = self.where[q]
+        if kind == "l":
+            return
+        cands = [self._qubit_at(("l", j)) for j in range(min(4, self.n_local))]
+        cands = [c for c in cands if c not in keep] or [self._qubit_at(("l", j)) for j in range(self.n_local)
+                                                           if self._qubit_at(("l", j)) not in keep][:1]
+        victim = self.lookahead(cands) if self.lookahead else cands[0]
+        self._exchange(i, self.where[victim][1])
+
+    def canonicalize(self):
+        """restore the canonical layout (qubit q < g at rank bit g-1-q, others in index order)"""
+        for q in range(self.g):
+            want = ("g", self.g - 1 - q)
+            if self.where[q] == want:
+                continue
+            if self.where[q][0] == "g":
+                # q sits at another rank bit: bring it on chip first
+                self._bring_local(q, keep=())
+            # evict q to its rank bit: swap with whatever lives there
+            self._exchange(want[1], self.where[q][1])
+        # local part: qubit q >= g must be local engine qubit q - g
+        for q in range(self.g, self.n):
+            want = q - self.g
+            cur = self.where[q][1]
+            if cur != want:
+                other = self._qubit_at(("l", want))
+                self.local.apply_gate(SWAP, [cur, want])        # a relabel inside the engine
+                self.where[q], self.where[other] = ("l", want), ("l", cur)
+
+    # ---- gates -------------------------------------------------------------------
+    def apply_gate(self, mat, bits, desc="gate"):
+        m = np.asarray(mat, dtype=np.complex128)
+        k = len(bits)
+        if m.shape != (1 << k, 1 << k):
+            raise ValueError('Expected %d bits for "%s", got %d' % (int(round(math.log2(m.shape[0]))), desc, k))
+        if k == 2 and np.array_equal(m, SWAP):
+            a, b = bits
+            self.where[a], self.where[b] = self.where[b], self.where[a]      # swap.rs:78-88 as a relabel
+            return
+        glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
+        nondiag = [j for j in glob if not acts_diagonally(m, k, [j])]
+        for j in nondiag:
+            self._bring_local(bits[j], keep=[q for q in bits])
+        glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
+        local_m, local_bits = self._localize(m, bits, glob)
+        if local_m is not None:
+            self.local.apply_gate(local_m, local_bits)
+
+    def _localize(self, m, bits, glob):
+        k = len(bits)
+        if glob:
+            fixed = {j: self._rank_bit(self.where[bits[j]][1]) for j in glob}
+            m = select_block(m, k, fixed)
+        lbits = [self.where[q][1] for j, q in enumerate(bits) if j not in glob]
+        if not lbits:
+            s = m[0, 0]
+            if s == 1:
+                return None, None
+            return np.array([[s, 0], [0, s]], dtype=np.complex128), [0]      # a rank-dependent scalar
+        return m, lbits
+
+    def apply_unary_gate_all(self, mat, desc="gate"):
+        for q in range(self.n):
+            self.apply_gate(mat, [q], desc)
+
+    def apply_conditional_gate(self, control, mat, bits, desc="gate"):
+        m = np.asarray(mat, dtype=np.complex128)
+        k = len(bits)
+        if k == 2 and np.array_equal(m, SWAP):
+            # a conditional relabel cannot be virtual: run it as three CX on local qubits
+            for q in bits:
+                self._bring_local(q, keep=list(bits))
+        glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
+        for j in [j for j in glob if not acts_diagonally(m, k, [j])]:
+            self._bring_local(bits[j], keep=list(bits))
+        glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
+        local_m, local_bits = self._localize(m, bits, glob)
+        if local_m is None:
+            local_m, local_bits = np.eye(2, dtype=np.complex128), [0]        # columns still split identically
+        self.local.apply_conditional_gate(control, local_m, local_bits)
+
+    # ---- canonical reductions ----------------------------------------------------
+    def _gather(self, arr):
+        import torch
+        if self.P == 1:
+            return [np.asarray(arr)]
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        dev = torch.device("cuda", self.device) if self.dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        out = [torch.empty_like(t) for _ in range(self.P)]
+        self.dist.all_gather(out, t, group=self.group)
+        return [o.cpu().numpy() for o in out]
+
+    def _global_prefix(self, leaf):
+        """leaf: (ncols, nleaves_local) canonical leaf totals of this rank.  Returns
+        (P_local, base, ends): inclusive global leaf prefixes of this rank's leaves, the weight
+        before this rank, and the last prefix of every rank -- all per column, in the canonical
+        order of DESIGN.md 4.2 (blocks of 1024 leaves chained, block totals chained)."""
+        ncols, nl = leaf.shape
+        if nl >= BLOCK:
+            inblock = np.cumsum(leaf.reshape(ncols, nl // BLOCK, BLOCK), axis=2)
+            btot = np.ascontiguousarray(inblock[:, :, -1])
+            allb = np.concatenate(self._gather(btot), axis=1)                 # (ncols, P * nb) in rank order
+            bpre = np.cumsum(allb, axis=1)
+            nb = nl // BLOCK
+            first = self.rank * nb
+            before = np.concatenate([np.zeros((ncols, 1)), bpre[:, :-1]], axis=1)[:, first:first + nb]
+            Pl = (before[:, :, None] + inblock).reshape(ncols, nl)
+            base = before[:, 0].copy()
+            ends = bpre[:, nb - 1::nb]
+        else:
+            alll = np.concatenate(self._gather(leaf), axis=1)                  # (ncols, P * nl)
+            NL = alll.shape[1]
+            Pg = np.zeros_like(alll)
+            bprefix = np.zeros(ncols)
+            for b0 in range(0, NL, BLOCK):
+                ib = np.cumsum(alll[:, b0:b0 + BLOCK], axis=1)
+                Pg[:, b0:b0 + BLOCK] = bprefix[:, None] + ib
+                bprefix = bprefix + ib[:, -1]
+            Pl = np.ascontiguousarray(Pg[:, self.rank * nl:(self.rank + 1) * nl])
+            base = Pg[:, self.rank * nl - 1].copy() if self.rank else np.zeros(ncols)
+            ends = Pg[:, nl - 1::nl]
+        return Pl, base, np.ascontiguousarray(ends)
+
+    def marginal0(self, qbit):
+        """w0 per column in the canonical order (vectorstate.rs:252-261)"""
+        self.canonicalize()
+        kind, i = self.where[qbit]
+        if kind == "l":
+            leaf = self.local.leaf_totals(i)
+        else:
+            leaf = self.local.leaf_totals(None) if self._rank_bit(i) == 0 else np.zeros((self.local.ncols, self.local.nleaves))
+        _, _, ends = self._global_prefix(leaf)
+        return ends[:, -1].copy()
+
+    def column_totals(self):
+        self.canonicalize()
+        _, _, ends = self._global_prefix(self.local.leaf_totals(None))
+        return ends[:, -1].copy()
+
+    # ---- measurement ---------------------------------------------------------------
+    def _measure(self, qbit, cbit, res, rng, collapse):
+        if qbit >= self.n:
+            raise ValueError("Invalid index %d for a quantum bit" % qbit)
+        if res.size < self.shots:
+            raise ValueError("Not enough space to store %d measurement results in array of length %d" % (self.shots, res.size))
+        w0s = self.marginal0(qbit)
+        counts = self.local.counts
+        n0s = [self.local.binomial(rng, c, min(float(w), 1.0)) for w, c in zip(w0s, counts)]
+        one = np.uint64(1) << np.uint64(cbit)
+        start = 0
+        for n0, c in zip(n0s, counts):
+            res[start:start + n0] &= ~one
+            res[start + n0:start + c] |= one
+            start += c
+        if not collapse:
+            return
+        kind, i = self.where[qbit]
+        if kind == "l":
+            self.local.collapse_columns(i, w0s, n0s)
+        else:
+            f0 = 1.0 / np.sqrt(w0s) if self._rank_bit(i) == 0 else np.zeros_like(w0s)
+            f1 = np.zeros_like(w0s) if self._rank_bit(i) == 0 else 1.0 / np.sqrt(1.0 - w0s)
+            with np.errstate(divide="ignore"):
+                self.local.scale_split_columns(np.where(np.isfinite(f0), f0, 0.0), np.where(np.isfinite(f1), f1, 0.0), n0s)
+
+    def measure_into(self, qbit, cbit, res, rng):
+        self._measure(qbit, cbit, res, rng, True)
+
+    def peek_into(self, qbit, cbit, res, rng):
+        self._measure(qbit, cbit, res, rng, False)
+
+    def measure(self, qbit, rng):
+        res = np.zeros(self.shots, dtype=np.uint64)
+        self.measure_into(qbit, 0, res, rng)
+        return res
+
+    def _measure_all(self, cbits, res, rng, collapse):
+        if res.size < self.shots:
+            raise ValueError("Not enough space to store %d measurement results in array of length %d" % (self.shots, res.size))
+        if len(cbits) != self.n:
+            raise ValueError("Expected %d measurement bits, but got %d" % (self.n, len(cbits)))
+        self.canonicalize()
+        Pl, base, ends = self._global_prefix(self.local.leaf_totals(None))
+        counts = self.local.counts
+        groups = []                                   # (global basis index, multiplicity) per column, ascending
+        for c, cnt in enumerate(counts):
+            total = ends[c, -1]
+            chosen = np.sort(self.local.draws(rng, total, cnt))
+            # owner rank of a draw: number of rank-end prefixes (all but the last) that are <= chosen
+            owner = np.searchsorted(ends[c, :-1], chosen, side="right")
+            mine = chosen[owner == self.rank]
+            idx = self.local.resolve_draws(c, Pl[c], base[c], mine).astype(np.uint64) | (np.uint64(self.rank) << np.uint64(self.n_local))
+            per_rank = np.bincount(owner, minlength=self.P)
+            allidx = self._gather_var(idx, per_rank)
+            vals, mult = np.unique(allidx, return_counts=True)
+            groups.append((vals, mult))
+        mask = np.uint64(0)
+        for b in cbits:
+            mask |= np.uint64(1) << np.uint64(b)
+        off = 0
+        new_idx, new_cnt = [], []
+        for vals, mult in groups:
+            for v, m_ in zip(vals, mult):
+                word = 0
+                for q in range(self.n):
+                    if (int(v) >> (self.n - 1 - q)) & 1:
+                        word |= 1 << cbits[q]
+                res[off:off + m_] = (res[off:off + m_] & ~mask) | np.uint64(word)
+                off += int(m_)
+                new_idx.append(int(v))
+                new_cnt.append(int(m_))
+        if collapse:
+            lm = (1 << self.n_local) - 1
+            self.local.replace_columns([(v & lm) if (v >> self.n_local) == self.rank else ZERO_COLUMN for v in new_idx], new_cnt)
+
+    def _gather_var(self, idx, per_rank):
+        import torch
+        if self.P == 1:
+            return idx
+        mx = int(per_rank.max()) if per_rank.size else 0
+        buf = np.zeros(max(mx, 1), dtype=np.int64)
+        buf[:idx.size] = idx.astype(np.int64)
+        dev = torch.device("cuda", self.device) if self.dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(buf).to(dev)
+        out = [torch.empty_like(t) for _ in range(self.P)]
+        self.dist.all_gather(out, t, group=self.group)
+        return np.concatenate([o.cpu().numpy()[:int(per_rank[r])] for r, o in enumerate(out)]).astype(np.uint64)
+
+    def measure_all_into(self, cbits, res, rng):
+        self._measure_all(cbits, res, rng, True)
+
+    def peek_all_into(self, cbits, res, rng):
+        self._measure_all(cbits, res, rng, False)
+
+    def measure_all(self, rng):
+        res = np.zeros(self.shots, dtype=np.uint64)
+        self.measure_all_into(list(range(self.n)), res, rng)
+        return res
+
+    def reset(self, bit, rng):
+        m = self.measure(bit, rng)
+        x = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+        self.apply_conditional_gate((m != 0).astype(np.uint8), x, [bit], "X")
+
+    # ---- read-out (tests) ----------------------------------------------------------
+    @property
+    def counts(self):
+        return self.local.counts
+
+    def local_column(self, col):
+        """this rank's shard of a column in canonical order"""
+        self.canonicalize()
+        return self.local.read_column(col)
+
+    def gather_column(self, col):
+        """the full column on every rank (small states only)"""
+        import torch
+        loc = self.local_column(col)
+        if self.P == 1:
+            return loc
+        parts = self._gather(np.ascontiguousarray(loc).view(np.float64))
+        return np.concatenate([p.view(np.complex128) for p in parts])

@@ -1,0 +1,116 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; run with `gpurun --gpus 2 -- python -m pytest
+tests/test_gpu_sharded.py -m gpu`): the sharded engine over NCCL against the oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import oracle as O
+        from q1tsim_b200 import engine as E
+        from q1tsim_b200 import sharded as S
+        from q1tsim_b200 import workloads as W
+        shots = 1000
+        words = O.splitmix64_words(21, 8 * shots + 64)
+        out = {"rank": rank}
+        G = O.gate_matrix
+        # ---- gates on every qubit incl. the global ones, swaps, controlled gates ----
+        st = S.ShardedState(n, shots)
+        ref = O.OracleState(n, shots, mode=1, order=1)
+        O.lib().orc_set_threads(4)
+        rs = np.random.default_rng(5)
+        names = [("h", 0), ("x", 0), ("u3", 3), ("cx", 0), ("cu1", 1), ("cs", 0), ("swap", 0), ("rz", 1), ("ccx", 0), ("crx", 1), ("t", 0), ("cz", 0)]
+        for rep in range(36):
+            name, npar = names[rep % len(names)]
+            m = G(name, list(rs.uniform(-2, 2, size=npar)))
+            k = int(np.log2(m.shape[0]))
+            bits = [int(b) for b in rs.permutation(n)[:k]]
+            st.apply_gate(m, bits, name); ref.apply_gate(m, bits)
+        full = st.gather_column(0)
+        out["gates_rel_l2"] = float(np.linalg.norm(full - ref.column(0)) / np.linalg.norm(ref.column(0)))
+        out["exchanges"] = st.exchanges
+        # ---- QFT + sampling: identical amplitudes on both sides -> bit-exact outcomes ----
+        st = S.ShardedState(n, shots)
+        ref = O.OracleState(n, shots, mode=1, order=1)
+        for op in W.u3_layer_ops(n, seed=1) + W.qft_ops(n, measure=False):
+            m = G(op[1], op[2])
+            st.apply_gate(m, op[3], op[1]); ref.apply_gate(m, op[3])
+        out["qft_rel_l2"] = float(np.linalg.norm(st.gather_column(0) - ref.column(0)))
+        out["exchanges"] += st.exchanges
+        st.canonicalize()
+        psi = ref.column(0)
+        nl = 1 << st.n_local
+        st.local.write_column(0, psi[rank * nl:(rank + 1) * nl])
+        for qb in (0, 1, n - 1):
+            out["w0_%d" % qb] = (float(st.marginal0(qb)[0]), float(ref.marginal0(qb, order=1)[0]))
+        cb = list(range(n))
+        rs_, ro = np.zeros(shots, dtype=np.uint64), np.zeros(shots, dtype=np.uint64)
+        rng_s, rng_o = E.Rng(words=words), O.Rng(words=words)
+        st.peek_all_into(cb, rs_, rng_s); ref.peek_all_into(cb, ro, rng_o)
+        out["peek_equal"] = bool(np.array_equal(rs_, ro))
+        st.measure_into(0, 40, rs_, rng_s); ref.measure_into(0, 40, ro, rng_o)           # a global qubit
+        st.measure_into(n - 1, 41, rs_, rng_s); ref.measure_into(n - 1, 41, ro, rng_o)   # a local qubit
+        out["measure_equal"] = bool(np.array_equal(rs_, ro))
+        out["counts_equal"] = st.counts == ref.counts
+        st.measure_all_into(cb, rs_, rng_s); ref.measure_all_into(cb, ro, rng_o)
+        out["measure_all_equal"] = bool(np.array_equal(rs_, ro))
+        out["consumed"] = (rng_s.consumed, rng_o.consumed)
+        q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world,n", [(2, 16), (2, 21)])
+def test_sharded_engine_vs_oracle(world, n):
+    import torch.multiprocessing as mp
+    if _ngpu() < world:
+        pytest.skip("not enough GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for o in outs:
+        assert o["gates_rel_l2"] < 1e-10 and o["qft_rel_l2"] < 1e-10
+        assert o["exchanges"] >= 1
+        for k, v in o.items():
+            if k.startswith("w0_"):
+                assert v[0] == v[1], (k, v)
+        assert o["peek_equal"] and o["measure_equal"] and o["counts_equal"] and o["measure_all_equal"]
+        assert o["consumed"][0] == o["consumed"][1]
