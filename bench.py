@@ -287,11 +287,124 @@ def run_ours(args, rank, world, local):
     print(json.dumps(line))
 
 
+def run_sharded(args, rank, world, local):
+    """N > 1: weak scaling, QFT-(qubits + log2 N) sharded over N GPUs (16 GiB shard per GPU at the
+    default 30 + log2 N qubits), global-qubit remaps over NCCL."""
+    import math
+    import torch
+    import torch.distributed as dist
+    from q1tsim_b200 import engine as E
+    from q1tsim_b200 import sharded as S
+    from q1tsim_b200 import workloads as W
+    dev = local % max(E.lib().q1t_device_count(), 1)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    g = int(round(math.log2(world)))
+    n, shots = args.qubits + g, args.shots
+    ops = W.qft_ops(n, measure=True)
+    gates = [(E.gate_matrix(o[1], o[2]), o[3], o[1]) for o in ops if o[0] == "gate"]
+    ngates = len(gates)
+    cbits = list(range(n))
+    rng = E.Rng(seed=2)
+    res = np.zeros(shots, dtype=np.uint64)
+    acc = {"exchanges": 0, "bytes": 0, "seconds": 0.0, "launches": 0, "peer_ms": 0.0, "peer_bytes": 0}
+    last = {}
+
+    def step(timing=False):
+        st = S.ShardedState(n, shots, device=dev)
+        if timing:
+            st.local.set_timing(True)
+        st.run_ops(ops, E.gate_matrix, res, rng)        # gates with look-ahead remap planning + measure_all
+        acc["exchanges"] += st.exchanges
+        acc["bytes"] += st.exchanged_bytes
+        acc["seconds"] += st.exchange_seconds
+        stt = st.local.stats()
+        acc["launches"] += stt["kernel_launches"]
+        acc["peer_ms"] += stt["peer_swap_ms"]
+        acc["peer_bytes"] += stt["peer_swap_bytes"]
+        last.update(stt)
+        st.local.st.close()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    if os.environ.get("Q1T_BENCH_PROFILE") and rank == 0:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        step()
+        pr.disable()
+        with open(os.path.join(ROOT, "gpurun_out", "bench_profile.txt"), "w") as f:
+            pstats.Stats(pr, stream=f).sort_stats("cumulative").print_stats(45)
+    elif os.environ.get("Q1T_BENCH_PROFILE"):
+        step()
+    for k in acc:
+        acc[k] = 0
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    exch = dict(acc)
+    step(timing=True)
+    ts = dict(last)
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    sweep_ms = ts["sweep_ms"] / max(ts["sweeps"], 1)
+    sweep_bytes = ts["sweep_bytes"] / max(ts["sweeps"], 1)
+    achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    if rank != 0:
+        return
+    value = ngates * float(1 << n) * args.steps / dt
+    line = {
+        "metric": "qft_f64_gate_amp_updates_per_s", "value": value, "unit": "gate_amp_updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "QFT-%d f64 + measure_all, %d shots, input |0..0>, sharded by the top %d qubits" % (n, shots, g),
+                   "gates": ngates, "state_bytes": 16 << n, "shard_bytes": 16 << (n - g),
+                   "l2": "shards (16 GiB) are far larger than the 126 MB L2; no explicit flush",
+                   "parallelism": "%d ranks, state sharded by index bits, pairwise half-shard exchange over NCCL" % world},
+        "circuit_ms": 1e3 * dt / args.steps,
+        "e2e": {"value": value, "unit": "gate_amp_updates/s", "ms_per_step": 1e3 * dt / args.steps,
+                "h2d_bytes_per_step": int(shots * 8 + (16 << (n - g)) // 2048), "d2h_bytes_per_step": int(shots * 8 + (16 << (n - g)) // 2048),
+                "note": "the timed loop already goes through the public ShardedState API from host buffers (state construction, "
+                        "host planning, all H2D/D2H copies and NCCL exchanges inside the timed region)"},
+        "gpu_launches": int(exch["launches"]),
+        "exchange": {"remaps_per_step": exch["exchanges"] / args.steps, "bytes_sent_per_rank_per_step": exch["bytes"] / args.steps,
+                     "ms_per_step": 1e3 * exch["seconds"] / args.steps,
+                     "gb_per_s_per_direction": exch["bytes"] / max(exch["seconds"], 1e-9) / 1e9,
+                     "peer_swap_kernel_ms_per_step": exch["peer_ms"] / args.steps,
+                     "peer_swap_kernel_gb_per_s_per_direction": exch["peer_bytes"] / max(exch["peer_ms"] * 1e-3, 1e-9) / 1e9,
+                     "path": "CUDA IPC peer memory, in-place swap kernel" if os.environ.get("Q1T_PEER_MEMORY", "1") != "0" else "NCCL send/recv + staging copy"},
+        "roofline": {"bound": "hbm", "kernel": "sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_ms,
+                     "sweeps_per_step": ts["sweeps"], "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback"},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
     rank, world, local = dist_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif world > 1:
+        run_sharded(args, rank, world, local)
     else:
         run_ours(args, rank, world, local)
 

@@ -133,6 +133,13 @@ int    q1t_collapse_columns(q1t_state *st, size_t qbit, const double *w0, const 
 int    q1t_replace_columns(q1t_state *st, size_t nr_columns, const uint64_t *idx, const size_t *counts);
 /* device pointer of a (flushed, materialised) column: 2^nr_bits complex128, for peer exchange */
 int    q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr);
+/* Qubit remap over NVLink peer memory (one process per GPU): q1t_ipc_export gives the 64-byte CUDA IPC
+ * handle of a column; q1t_peer_swap maps the partner's handle and trades rank bit <-> local qubit
+ * `local_qubit` in place: my amplitudes whose local bit differs from my rank bit `my_bit` are exchanged
+ * with the partner's, each rank moving half of the pairs with one remote read + one remote write per
+ * amplitude, no staging buffer.  Both ranks must call it between two barriers. */
+int    q1t_ipc_export(q1t_state *st, size_t col, unsigned char *handle64);
+int    q1t_peer_swap(q1t_state *st, size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit);
 /* rand 0.7 Uniform(0,total) draws as WeightedIndex::sample makes them (vectorstate.rs:126) */
 double q1t_uniform_draw(q1t_rng rng, double total);
 void   q1t_uniform_draws(q1t_rng rng, double total, size_t n, double *out);
@@ -150,6 +157,8 @@ typedef struct {
     uint64_t sweep_bytes;         /* algorithmic bytes of the sweep launches: 32 B per amplitude, 16 B when the input is generated */
     double   sweep_ms;            /* device time of sweep kernels (CUDA events), if timing enabled */
     double   read_ms;             /* device time of read passes */
+    double   peer_swap_ms;        /* device time of q1t_peer_swap kernels (always measured) */
+    uint64_t peer_swap_bytes;     /* bytes this rank moved over NVLink in q1t_peer_swap (remote reads + remote writes) */
 } q1t_stats;
 int q1t_get_stats(q1t_state *st, q1t_stats *out);
 int q1t_reset_stats(q1t_state *st);

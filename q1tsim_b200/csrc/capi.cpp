@@ -150,6 +150,12 @@ int q1t_replace_columns(q1t_state *st, size_t ncols, const uint64_t *idx, const 
     return st->impl->replace_columns(ncols, idx, counts);
 }
 int q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr) { ST_OR_FAIL; return st->impl->column_ptr(col, ptr); }
+int q1t_ipc_export(q1t_state *st, size_t col, unsigned char *handle64) { ST_OR_FAIL; return st->impl->ipc_export(col, handle64); }
+int q1t_peer_swap(q1t_state *st, size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit)
+{
+    ST_OR_FAIL;
+    return st->impl->peer_swap(col, peer_handle64, local_qubit, my_bit);
+}
 double q1t_uniform_draw(q1t_rng rng, double total)
 {
     const q1t::UniformF64 u = q1t::uniform_new(0.0, total);

@@ -215,8 +215,10 @@ int DeviceVectorState::materialize(Column &c)
     int rc = alloc_column(&c.buf);
     if (rc) return rc;
     CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
-    CK(launch_set_basis(c.buf, c.basis_idx, stream_));
-    stats.kernel_launches++;
+    if (c.basis_idx != UINT64_MAX) {        // UINT64_MAX: a lazy all-zero column (shard that does not hold the basis state)
+        CK(launch_set_basis(c.buf, c.basis_idx, stream_));
+        stats.kernel_launches++;
+    }
     c.basis = false;
     return Q1T_OK;
 }
@@ -375,7 +377,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     if (generate) {
         for (size_t i = 0; i < which.size(); ++i) {
             Column &c = cols_[which[i]];
-            gen[i] = physical_index(c.basis_idx, perm_);
+            gen[i] = c.basis_idx == UINT64_MAX ? ~0ull : physical_index(c.basis_idx, perm_);
             int rc = alloc_column(&c.buf);
             if (rc) return rc;
             c.basis = false;
@@ -713,7 +715,7 @@ int DeviceVectorState::marginal0(size_t qbit, double *w0_out)
     if (rc) return rc;
     size_t k = 0;
     for (size_t c = 0; c < cols_.size(); ++c) {
-        if (cols_[c].basis) w0_out[c] = (cols_[c].basis_idx & bit) ? 0.0 : 1.0;
+        if (cols_[c].basis) w0_out[c] = (cols_[c].basis_idx == UINT64_MAX || (cols_[c].basis_idx & bit)) ? 0.0 : 1.0;
         else w0_out[c] = tot[k++];
     }
     return Q1T_OK;
@@ -728,7 +730,7 @@ int DeviceVectorState::column_totals(double *out)
     rc = reduce_columns(0, 0, tot, dev);
     if (rc) return rc;
     size_t k = 0;
-    for (size_t c = 0; c < cols_.size(); ++c) out[c] = cols_[c].basis ? 1.0 : tot[k++];
+    for (size_t c = 0; c < cols_.size(); ++c) out[c] = cols_[c].basis ? (cols_[c].basis_idx == UINT64_MAX ? 0.0 : 1.0) : tot[k++];
     return Q1T_OK;
 }
 
@@ -827,11 +829,10 @@ int DeviceVectorState::init_empty()
 {
     int rc = ensure_device();
     if (rc) return rc;
-    Column c;
-    rc = alloc_column(&c.buf);
-    if (rc) return rc;
+    Column c;                   // lazy all-zero column: generated by the first sweep, never memset + read
     c.count = shots_;
-    CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
+    c.basis = true;
+    c.basis_idx = UINT64_MAX;
     cols_.push_back(c);
     return Q1T_OK;
 }
@@ -950,17 +951,61 @@ int DeviceVectorState::replace_columns(size_t ncols, const uint64_t *idx, const 
     for (size_t k = 0; k < ncols; ++k) {
         Column c;
         c.count = counts[k];
-        if (idx[k] == UINT64_MAX) {
-            rc = alloc_column(&c.buf);
-            if (rc) return rc;
-            CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
-        } else {
-            if (idx[k] >> n_) return fail(Q1T_ERR_INVALID_ARGUMENT, "basis index out of range");
-            c.basis = true;
-            c.basis_idx = idx[k];
-        }
+        if (idx[k] != UINT64_MAX && (idx[k] >> n_)) return fail(Q1T_ERR_INVALID_ARGUMENT, "basis index out of range");
+        c.basis = true;                 // lazy: |idx>, or the all-zero column for UINT64_MAX
+        c.basis_idx = idx[k];
         cols_.push_back(c);
     }
+    return Q1T_OK;
+}
+
+// peer exchange over CUDA IPC: export a column, swap in place with a partner's mapped column
+int DeviceVectorState::ipc_export(size_t col, unsigned char *handle64)
+{
+    void *p = nullptr;
+    int rc = column_ptr(col, &p);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle64, &h, 64);
+    return Q1T_OK;
+}
+
+int DeviceVectorState::peer_swap(size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit)
+{
+    if (col >= cols_.size() || local_qubit >= (size_t)n_ || n_ < 2) return fail(Q1T_ERR_INVALID_ARGUMENT, "peer_swap: bad argument");
+    void *mine = nullptr;
+    int rc = column_ptr(col, &mine);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, peer_handle64, 64);
+    // mapping a 16 GiB peer allocation costs milliseconds: keep mappings open for the life of the process
+    // (the partner's buffers come from its buffer cache, so the same few handles keep coming back)
+    static std::mutex ipc_mu;
+    static std::vector<std::pair<std::string, void *>> ipc_open;
+    void *theirs = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ipc_mu);
+        const std::string key(reinterpret_cast<const char *>(peer_handle64), 64);
+        for (auto &kv : ipc_open)
+            if (kv.first == key) theirs = kv.second;
+        if (!theirs) {
+            CK(cudaIpcOpenMemHandle(&theirs, h, cudaIpcMemLazyEnablePeerAccess));
+            ipc_open.push_back(std::make_pair(key, theirs));
+        }
+    }
+    const int L = n_ - 1 - (int)local_qubit;
+    cudaEventRecord(ev0_, stream_);
+    cudaError_t e = launch_peer_swap(static_cast<double2 *>(mine), static_cast<double2 *>(theirs), n_, L, my_bit ? 1 : 0, stream_);
+    cudaEventRecord(ev1_, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    float ms = 0;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, ev0_, ev1_);
+    if (e != cudaSuccess) return cuda_fail(e, "peer_swap");
+    stats.peer_swap_ms += ms;
+    stats.peer_swap_bytes += (16ull << n_) / 2;      // a quarter shard read remotely + a quarter written remotely
+    stats.kernel_launches++;
     return Q1T_OK;
 }
 
@@ -1009,6 +1054,7 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
     size_t k = 0;
     for (size_t c = 0; c < cols_.size(); ++c) {
         const size_t cnt = cols_[c].count;
+        if (cols_[c].basis && cols_[c].basis_idx == UINT64_MAX) return fail(Q1T_ERR_INVALID_ARGUMENT, "state column has zero norm");
         if (cols_[c].basis) {
             // WeightedIndex over a unit vector: every draw consumes one word and returns basis_idx
             for (size_t j = 0; j < cnt; ++j) (void)rng.next_u64(rng.ctx);

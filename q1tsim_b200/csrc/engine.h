@@ -48,6 +48,8 @@ public:
     int collapse_columns(size_t qbit, const double *w0s, const size_t *n0s);
     int replace_columns(size_t ncols, const uint64_t *idx, const size_t *counts);
     int column_ptr(size_t col, void **ptr);
+    int ipc_export(size_t col, unsigned char *handle64);
+    int peer_swap(size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit);
 
     int counts(size_t *out);
     size_t nr_columns() { return cols_.size(); }

@@ -244,6 +244,22 @@ __device__ __forceinline__ void round_ph(char *tile_b, unsigned swT, const Round
     for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
 }
 
+// LINPHASE: product of independent one-qubit phases on any set of index bits (the linear part
+// of the phase polynomial): thread/tile bits through F, register bits through m[0..3]
+__device__ __forceinline__ void linphase_apply(double2 (&a)[kSlots], const OpDesc &op, double2 F)
+{
+    double2 f[kSlots];
+    f[0] = F;
+#pragma unroll
+    for (int i = 0; i < kRegBits; ++i) {
+        const double2 q = make_double2(op.m[2 * i], op.m[2 * i + 1]);
+#pragma unroll
+        for (int u = 0; u < (1 << i); ++u) f[u | (1 << i)] = cmul(f[u], q);
+    }
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) a[s] = cmul(a[s], f[s]);
+}
+
 #define Q1T_DISPATCH_J(fn, ...)          \
     switch (op.j) {                      \
     case 0: fn<0>(__VA_ARGS__); break;   \
@@ -355,13 +371,14 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         for (int k = R.op_begin; k < R.op_end; ++k) {
             const OpDesc &op = P.ops[k];
             const unsigned kind = op.kind;
-            if (kind == OP_PHASE_H || kind == OP_PHASE) {
+            if (kind == OP_PHASE_H || kind == OP_PHASE || kind == OP_LINPHASE) {
                 const PhaseTab &pt = ptabs[op.phase_id];
                 const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
                 const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
                 const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
                 const double2 F = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
                 if (kind == OP_PHASE_H) { Q1T_DISPATCH_J(phase_h_apply, a, op, F) }
+                else if (kind == OP_LINPHASE) linphase_apply(a, op, F);
                 else { Q1T_DISPATCH_J(phase_apply, a, op, F) }
             } else if (kind == OP_H_UNNORM) {
                 Q1T_DISPATCH_J(h_unnorm, a)
@@ -709,6 +726,42 @@ cudaError_t launch_scale2(const double2 *d_in, double2 *d_out0, double2 *d_out1,
     unsigned long long blocks = (N + 255) / 256;
     if (blocks > 148ull * 16ull) blocks = 148ull * 16ull;
     scale2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_in, d_out0, d_out1, N, f0, f1);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// qubit remap between two ranks over NVLink peer memory (multi-GPU).
+// Rank bit a of this rank and index bit L of the shard trade places: my element at
+// index l (l_L = 1-a) is exchanged with the partner's element at l ^ (1<<L).  The
+// 2^(n-1) pairs are split between the two ranks (this rank takes the half whose top
+// remaining bit equals a), so every pair is swapped exactly once, in place, with
+// no staging buffer: one remote read + one remote write per 16 bytes handled.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+peer_swap_kernel(double2 *__restrict__ mine, double2 *__restrict__ theirs, int n, int L, int a)
+{
+    const unsigned long long npairs = 1ull << (n - 2);       // pairs handled by this rank
+    const unsigned long long sel = (unsigned long long)a << (n - 2);
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < npairs;
+         p += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long q = sel | p;                 // n-1 bits: all index bits except L
+        const unsigned long long lo = q & ((1ull << L) - 1ull);
+        const unsigned long long base = ((q >> L) << (L + 1)) | lo;
+        const unsigned long long lm = base | ((unsigned long long)(1 - a) << L);
+        const unsigned long long lt = base | ((unsigned long long)a << L);
+        const double2 x = mine[lm];
+        const double2 y = theirs[lt];
+        mine[lm] = y;
+        theirs[lt] = x;
+    }
+}
+cudaError_t launch_peer_swap(double2 *d_mine, double2 *d_theirs, int n, int L, int a, cudaStream_t stream)
+{
+    const unsigned long long npairs = 1ull << (n - 2);
+    unsigned long long blocks = (npairs + 255) / 256;
+    if (blocks > 148ull * 32ull) blocks = 148ull * 32ull;
+    if (blocks == 0) blocks = 1;
+    peer_swap_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_mine, d_theirs, n, L, a);
     return cudaGetLastError();
 }
 

@@ -31,6 +31,7 @@ cudaError_t launch_scale2(const double2 *d_in, double2 *d_out0, double2 *d_out1,
 cudaError_t launch_collapse(const double2 *d_in, double2 *d_out0, double2 *d_out1, int n, int bitpos, double f0,
                             double f1, cudaStream_t stream);
 cudaError_t launch_product_state(double2 *d_col, int n, const double2 *d_coefs, cudaStream_t stream);
+cudaError_t launch_peer_swap(double2 *d_mine, double2 *d_theirs, int n, int L, int a, cudaStream_t stream);
 cudaError_t launch_set_basis(double2 *d_col, unsigned long long idx, cudaStream_t stream);
 
 }  // namespace q1t

@@ -352,14 +352,29 @@ void Planner::finish()
             else if (in_tile(t)) score += 1;
             if (score > best_score) { best_score = score; best = t; }
         }
-        if (best < 0) break;
+        if (best < 0 || best_score < 4) break;        // only bits with quadratic partners need their own op
         if (nops_ + 1 > (size_t)kMaxOps || nphase_ + 1 > (size_t)kMaxPhase) { close_sweep(); open_sweep(); }
         place_target(best);
         emit_phase_for(best);
     }
-    if (pd_.c0 != 0.0) {
-        place_target(0);
-        emit_phase_for(0);
+    // what is left is separable: c0 + sum_b lin_b x_b  ->  one LINPHASE op in a round of its own
+    bool any_lin = pd_.c0 != 0.0;
+    for (int t = 0; t < n_; ++t) any_lin = any_lin || pd_.lin[t] != 0.0;
+    if (any_lin) {
+        if (nops_ + 1 > (size_t)kMaxOps || nphase_ + 1 > (size_t)kMaxPhase || (int)rounds_.size() >= kMaxRounds) { close_sweep(); open_sweep(); }
+        OpB op;
+        op.is_phase = true;
+        op.is_lin = true;
+        op.base = pd_.c0;
+        for (int t = 0; t < n_; ++t)
+            if (pd_.lin[t] != 0.0) op.partners.push_back(std::make_pair(t, pd_.lin[t]));
+        pd_.c0 = 0.0;
+        std::fill(pd_.lin.begin(), pd_.lin.end(), 0.0);
+        RoundB r;                                     // register bits: any tile bit will do
+        r.regs.push_back(tile_.empty() ? 0 : tile_.back());
+        op.target = r.regs[0];
+        rounds_.push_back(r);
+        emit_op(op);
     }
     close_sweep();
     open_sweep();
@@ -464,6 +479,36 @@ void Planner::close_sweep()
                         else op.cmask |= 1ull << tb;
                     } else op.cmask |= 1ull << (T + outer_index[p]);
                 }
+            } else if (ob.is_lin) {
+                op.kind = OP_LINPHASE;
+                op.phase_id = (uint32_t)nphase;
+                PhaseTab pt;
+                std::memset(&pt, 0, sizeof pt);
+                double lo_ang[1 << kThrLoBits] = { 0 }, hi_ang[1 << (kMaxThrBits - kThrLoBits)] = { 0 };
+                pt.base = wrap_half_turns(ob.base);
+                for (int q = 0; q < kRegBits; ++q) { op.m[2 * q] = 1.0; op.m[2 * q + 1] = 0.0; }
+                for (const auto &pr : ob.partners) {
+                    const int p = pr.first;
+                    const double v = pr.second;
+                    if (tile_index[p] >= 0) {
+                        const int tb = tile_index[p];
+                        if (slot_of_tb[tb] >= 0) sincospi_host(v, op.m[2 * slot_of_tb[tb] + 1], op.m[2 * slot_of_tb[tb]]);
+                        else {
+                            const int ti = thr_index_of_tb[tb];
+                            if (ti < kThrLoBits) {
+                                for (int x = 0; x < (1 << kThrLoBits); ++x)
+                                    if ((x >> ti) & 1) lo_ang[x] += v;
+                            } else {
+                                for (int x = 0; x < (1 << (kMaxThrBits - kThrLoBits)); ++x)
+                                    if ((x >> (ti - kThrLoBits)) & 1) hi_ang[x] += v;
+                            }
+                        }
+                    } else pt.outer_coef[outer_index[p]] = v;
+                }
+                for (int x = 0; x < (1 << kThrLoBits); ++x) sincospi_host(lo_ang[x], pt.lo[2 * x + 1], pt.lo[2 * x]);
+                for (int x = 0; x < (1 << (kMaxThrBits - kThrLoBits)); ++x) sincospi_host(hi_ang[x], pt.hi[2 * x + 1], pt.hi[2 * x]);
+                ps.ptabs.push_back(pt);
+                ++nphase;
             } else {
                 op.kind = OP_PHASE;
                 if (!ob.has_c0 && oi + 1 < rb.ops.size()) {

@@ -80,6 +80,7 @@ public:
 private:
     struct OpB {
         bool is_phase = false;
+        bool is_lin = false;            // separable linear phase on all bits in `partners` (+ c0)
         int target = 0;                 // physical
         uint64_t cmask = 0;             // physical (G1)
         double m[8] = { 0 };

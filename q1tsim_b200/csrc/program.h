@@ -33,6 +33,7 @@ enum OpKind : uint8_t {
     OP_G1_DIAG = 5,      // [[m00,0],[0,m11]] (controlled-diagonal fallback)
     OP_H_UNNORM = 6,     // [[1,1],[1,-1]]; the 1/sqrt(2) is folded into SweepProgram::scale
     OP_PHASE_H = 7,      // OP_PHASE followed by OP_H_UNNORM on the same slot bit, fused
+    OP_LINPHASE = 8,     // separable diagonal: every slot s times F(thread, tile) * prod_{j: s_j = 1} m[j]
 };
 
 enum RoundKind : uint8_t { ROUND_GENERIC = 0, ROUND_PH = 1 };

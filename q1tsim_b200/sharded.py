@@ -16,7 +16,7 @@ composition around it:
   r ^ (1 << i) (`torch.distributed` send/recv over NCCL/NVLink), after which the
   logical->physical map is updated; `Swap` gates are pure relabels;
 * marginals and sampling chain the per-rank canonical leaf totals in rank order
-  on the host, so results equal the single-GPU (and oracle) canonical order bit
+  on the host, so results equal the single-GPU canonical order bit
   for bit; all ranks consume identical copies of the caller's generator.
 
 All ranks must make the same calls in the same order (SPMD).
@@ -146,6 +146,21 @@ class EngineLocal:
         v.__cuda_array_interface__ = {"shape": (2 << self.n_local,), "typestr": "<f8", "data": (p.value, False), "version": 2}
         return torch.as_tensor(v, device=torch.device("cuda", self.device))
 
+    def ipc_export(self, col):
+        C = self.C
+        buf = (C.c_ubyte * 64)()
+        self.L.q1t_ipc_export.restype = C.c_int
+        self.L.q1t_ipc_export.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_ubyte)]
+        self.st._chk(self.L.q1t_ipc_export(self.st._p, col, buf))
+        return bytes(buf)
+
+    def peer_swap(self, col, handle, local_qubit, my_bit):
+        C = self.C
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self.L.q1t_peer_swap.restype = C.c_int
+        self.L.q1t_peer_swap.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_ubyte), C.c_size_t, C.c_int]
+        self.st._chk(self.L.q1t_peer_swap(self.st._p, col, buf, local_qubit, my_bit))
+
     def draws(self, rng, total, n):
         C = self.C
         out = np.zeros(max(n, 1), dtype=np.float64)
@@ -222,8 +237,11 @@ class ShardedState:
         # where[q] = ("g", rank bit) | ("l", local engine qubit); canonical: q < g global
         self.where = [self._canonical(q) for q in range(nr_bits)]
         self.exchanges = 0
-        self.exchanged_bytes = 0
-        self.lookahead = lookahead        # optional callable(list of candidate logical qubits) -> victim
+        self.exchanged_bytes = 0          # bytes this rank sent (== received)
+        self.exchange_seconds = 0.0
+        self.lookahead = lookahead        # optional callable(rank bit, keep) -> victim logical qubit
+        import os
+        self.peer_memory = os.environ.get("Q1T_PEER_MEMORY", "1") != "0"
 
     # ---- layout bookkeeping ------------------------------------------------
     def _canonical(self, q):
@@ -255,7 +273,30 @@ class ShardedState:
             j = 0
         hi, lo = 1 << j, (1 << (self.n_local - 1 - j)) * 2            # doubles per contiguous run
         max_piece = 1 << 27                                              # 1 GiB of doubles per message
+        import time
+        import os
+        dbg = os.environ.get("Q1T_SHARD_DEBUG")
+        t_a = time.perf_counter()
         for col in range(self.local.ncols):
+            self.local.column_tensor(col)            # run queued sweeps / relabels before the clock starts
+        t_b = time.perf_counter()
+        if self.P > 1:
+            dist.barrier(group=self.group)
+        t_start = time.perf_counter()
+        if dbg:
+            print("[rank %d] exchange: flush %.1f ms, barrier %.1f ms" % (self.rank, 1e3 * (t_b - t_a), 1e3 * (t_start - t_b)), flush=True)
+        use_peer = self.peer_memory and hasattr(self.local, "peer_swap") and self.n_local >= 2
+        if use_peer:
+            # in-place swap over NVLink peer memory: no staging, no NCCL on the data path
+            for col in range(self.local.ncols):
+                mine = torch.frombuffer(bytearray(self.local.ipc_export(col)), dtype=torch.uint8).cuda(self.device)
+                allh = [torch.empty_like(mine) for _ in range(self.P)]
+                dist.all_gather(allh, mine, group=self.group)
+                dist.barrier(group=self.group)              # partner's column is flushed and exported
+                self.local.peer_swap(col, bytes(allh[partner].cpu().numpy().tobytes()), j, mybit)
+                self.exchanged_bytes += (16 << self.n_local) // 2
+            dist.barrier(group=self.group)
+        for col in range(self.local.ncols if not use_peer else 0):
             t = self.local.column_tensor(col).view(hi, 2, lo)
             half = t[:, 1 - mybit, :]
             scratch = None
@@ -274,6 +315,7 @@ class ShardedState:
                     self.exchanged_bytes += piece.numel() * 8
             if t.is_cuda:
                 torch.cuda.synchronize(t.device)
+        self.exchange_seconds += time.perf_counter() - t_start
         self.exchanges += 1
         qg, ql = self._qubit_at(("g", gbit)), self._qubit_at(("l", j))
         self.where[qg], self.where[ql] = ("l", j), ("g", gbit)
@@ -283,10 +325,10 @@ class ShardedState:
         kind, i = self.where[q]
         if kind == "l":
             return
-        cands = [self._qubit_at(("l", j)) for j in range(min(4, self.n_local))]
-        cands = [c for c in cands if c not in keep] or [self._qubit_at(("l", j)) for j in range(self.n_local)
-                                                           if self._qubit_at(("l", j)) not in keep][:1]
-        victim = self.lookahead(cands) if self.lookahead else cands[0]
+        victim = self.lookahead(i, keep) if self.lookahead else None
+        if victim is None or self.where[victim][0] != "l" or victim in keep:
+            cands = [self._qubit_at(("l", j)) for j in range(self.n_local)]
+            victim = [c for c in cands if c not in keep][0]
         self._exchange(i, self.where[victim][1])
 
     def canonicalize(self):
@@ -310,17 +352,33 @@ class ShardedState:
                 self.where[q], self.where[other] = ("l", want), ("l", cur)
 
     # ---- gates -------------------------------------------------------------------
+    _gate_info = {}
+
+    @classmethod
+    def _info(cls, m, k):
+        """(is_swap, per-gate-bit diagonal flags), cached per matrix object"""
+        hit = cls._gate_info.get(id(m))
+        if hit is not None and hit[0] is m:
+            return hit[1], hit[2]
+        is_swap = k == 2 and np.array_equal(m, SWAP)
+        diag = [acts_diagonally(m, k, [j]) for j in range(k)]
+        if len(cls._gate_info) > 4096:
+            cls._gate_info.clear()
+        cls._gate_info[id(m)] = (m, is_swap, diag)
+        return is_swap, diag
+
     def apply_gate(self, mat, bits, desc="gate"):
-        m = np.asarray(mat, dtype=np.complex128)
+        m = mat if isinstance(mat, np.ndarray) and mat.dtype == np.complex128 else np.asarray(mat, dtype=np.complex128)
         k = len(bits)
         if m.shape != (1 << k, 1 << k):
             raise ValueError('Expected %d bits for "%s", got %d' % (int(round(math.log2(m.shape[0]))), desc, k))
-        if k == 2 and np.array_equal(m, SWAP):
+        is_swap, diag = self._info(m, k)
+        if is_swap:
             a, b = bits
             self.where[a], self.where[b] = self.where[b], self.where[a]      # swap.rs:78-88 as a relabel
             return
         glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
-        nondiag = [j for j in glob if not acts_diagonally(m, k, [j])]
+        nondiag = [j for j in glob if not diag[j]]
         for j in nondiag:
             self._bring_local(bits[j], keep=[q for q in bits])
         glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
@@ -480,18 +538,14 @@ class ShardedState:
         mask = np.uint64(0)
         for b in cbits:
             mask |= np.uint64(1) << np.uint64(b)
-        off = 0
-        new_idx, new_cnt = [], []
-        for vals, mult in groups:
-            for v, m_ in zip(vals, mult):
-                word = 0
-                for q in range(self.n):
-                    if (int(v) >> (self.n - 1 - q)) & 1:
-                        word |= 1 << cbits[q]
-                res[off:off + m_] = (res[off:off + m_] & ~mask) | np.uint64(word)
-                off += int(m_)
-                new_idx.append(int(v))
-                new_cnt.append(int(m_))
+        vals = np.concatenate([v for v, _ in groups]) if groups else np.zeros(0, dtype=np.uint64)
+        mult = np.concatenate([m_ for _, m_ in groups]) if groups else np.zeros(0, dtype=np.int64)
+        words = np.zeros(vals.size, dtype=np.uint64)
+        for q in range(self.n):                       # qubit q -> classical bit cbits[q] (vectorised over outcomes)
+            words |= ((vals >> np.uint64(self.n - 1 - q)) & np.uint64(1)) << np.uint64(cbits[q])
+        tot = int(mult.sum())
+        res[:tot] = (res[:tot] & ~mask) | np.repeat(words, mult)
+        new_idx, new_cnt = [int(v) for v in vals], [int(m_) for m_ in mult]
         if collapse:
             lm = (1 << self.n_local) - 1
             self.local.replace_columns([(v & lm) if (v >> self.n_local) == self.rank else ZERO_COLUMN for v in new_idx], new_cnt)
@@ -524,6 +578,92 @@ class ShardedState:
         m = self.measure(bit, rng)
         x = np.array([[0, 1], [1, 0]], dtype=np.complex128)
         self.apply_conditional_gate((m != 0).astype(np.uint8), x, [bit], "X")
+
+    # ---- whole op lists with look-ahead ------------------------------------------------
+    def run_ops(self, ops, gate_matrix, res=None, rng=None):
+        """Apply an op list (q1tsim_b200.workloads format).  Knowing the future lets every
+        remap evict the local qubit whose data is destined for that rank bit (following the
+        remaining `Swap` relabels) and that no later gate touches non-diagonally, so the
+        final canonicalisation usually needs no further exchange."""
+        key = (id(ops), len(ops))
+        cached = getattr(ShardedState, "_plan_cache", {}).get(key)
+        if cached is not None and cached[0] == (self.n, self.g):
+            _, mats, dest, busy, nxt = cached
+            return self._run_planned(ops, gate_matrix, res, rng, mats, dest, busy, nxt)
+        mats = []
+        for op in ops:
+            mats.append(np.asarray(gate_matrix(op[1], op[2]), dtype=np.complex128) if op[0] == "gate" else None)
+        nops = len(ops)
+        dest = [None] * (nops + 1)       # dest[t][q]: logical qubit that the data labelled q at time t ends as
+        busy = [None] * (nops + 1)       # busy[t][q]: a later op acts non-diagonally on label q (or measures it alone)
+        INF = 1 << 60
+        nxt = [None] * (nops + 1)        # nxt[t][q]: index of the next op >= t that needs label q on chip
+        dest[nops] = list(range(self.n))
+        busy[nops] = [False] * self.n
+        nxt[nops] = [INF] * self.n
+        for t in range(nops - 1, -1, -1):
+            d, b, x = list(dest[t + 1]), list(busy[t + 1]), list(nxt[t + 1])
+            op = ops[t]
+            if op[0] == "gate":
+                bits, m = op[3], mats[t]
+                if len(bits) == 2 and np.array_equal(m, SWAP):
+                    a, c = bits
+                    d[a], d[c] = d[c], d[a]
+                    b[a], b[c] = b[c], b[a]
+                    x[a], x[c] = x[c], x[a]
+                else:
+                    for j, q in enumerate(bits):
+                        if not acts_diagonally(m, len(bits), [j]):
+                            b[q] = True
+                            x[q] = t
+            elif op[0] in ("cond",):
+                for q in op[5]:
+                    b[q] = True
+                    x[q] = t
+            dest[t], busy[t], nxt[t] = d, b, x
+        if not hasattr(ShardedState, "_plan_cache"):
+            ShardedState._plan_cache = {}
+        ShardedState._plan_cache[key] = ((self.n, self.g), mats, dest, busy, nxt)
+        return self._run_planned(ops, gate_matrix, res, rng, mats, dest, busy, nxt)
+
+    def _run_planned(self, ops, gate_matrix, res, rng, mats, dest, busy, nxt):
+        state = {"t": 0}
+
+        def policy(gbit, keep):
+            t = state["t"]
+            want = self.g - 1 - gbit                      # logical qubit whose canonical home is this rank bit
+            for v in range(self.n):
+                if self.where[v][0] == "l" and v not in keep and not busy[t + 1][v] and dest[t + 1][v] == want:
+                    return v
+            best, far = None, -1                          # otherwise Belady: the qubit needed again latest
+            for v in range(self.n):
+                if self.where[v][0] == "l" and v not in keep and nxt[t + 1][v] > far:
+                    best, far = v, nxt[t + 1][v]
+            return best
+
+        old = self.lookahead
+        self.lookahead = policy
+        try:
+            for t, op in enumerate(ops):
+                state["t"] = t
+                k = op[0]
+                if k == "gate":
+                    self.apply_gate(mats[t], op[3], str(op[1]))
+                elif k == "cond":
+                    word = np.zeros(res.size, dtype=np.uint64)
+                    for idst, isrc in enumerate(op[1]):
+                        word |= ((res >> np.uint64(isrc)) & np.uint64(1)) << np.uint64(idst)
+                    self.apply_conditional_gate((word == np.uint64(op[2])).astype(np.uint8), gate_matrix(op[3], op[4]), op[5])
+                elif k in ("measure", "peek") and op[3] == "Z":
+                    (self.measure_into if k == "measure" else self.peek_into)(op[1], op[2], res, rng)
+                elif k in ("measure_all", "peek_all") and op[2] == "Z":
+                    (self.measure_all_into if k == "measure_all" else self.peek_all_into)(op[1], res, rng)
+                elif k == "barrier":
+                    pass
+                else:
+                    raise NotImplementedError("run_ops: %r (basis-change sandwiches: use the single-GPU Circuit)" % (op,))
+        finally:
+            self.lookahead = old
 
     # ---- read-out (tests) ----------------------------------------------------------
     @property

@@ -65,8 +65,13 @@ def _worker(rank, world, port, n, case, q):
                 out["w0_%d" % qb] = (float(st.marginal0(qb)[0]), float(ref.marginal0(qb, order=1)[0]))
             out["total"] = (float(st.column_totals()[0]), float(ref.column_totals(order=1)[0]))
         elif case == "qft_sample":
-            for op in W.u3_layer_ops(n, seed=1) + W.qft_ops(n, measure=False):
-                both(op[1], op[2], op[3])
+            ops = W.u3_layer_ops(n, seed=1) + W.qft_ops(n, measure=False)
+            st.run_ops(ops, G)                       # look-ahead remap planning
+            for op in ops:
+                ref.apply_gate(G(op[1], op[2]), op[3])
+            g_ = st.g
+            out["canonical_after_run"] = all(st.where[q_] == st._canonical(q_) for q_ in range(g_))
+            out["exchanges_run"] = st.exchanges
             out["amp_err"] = float(np.linalg.norm(st.gather_column(0) - ref.column(0)))
             psi = ref.column(0)                       # identical amplitudes -> bit-exact sampling
             nl = 1 << st.n_local
@@ -130,6 +135,8 @@ def test_sharded_gates_and_marginals(world, n):
 def test_sharded_qft_sampling_bit_exact(world, n):
     for o in _run(world, n, "qft_sample"):
         assert o["amp_err"] < 1e-12
+        assert o["canonical_after_run"]          # look-ahead: global qubits already home, no extra exchange
+        assert o["exchanges_run"] <= 3 * int(np.log2(world))
         assert o["peek_equal"] and o["measure_equal"] and o["counts_equal"]
         assert o["consumed"][0] == o["consumed"][1]
         assert o["col_err"] == 0.0
