@@ -44,14 +44,18 @@ void *pool_take(int device, size_t bytes)
         }
     return nullptr;
 }
-// returns false if the caller must cudaFree the buffer itself
+// returns false if the caller must cudaFree the buffer itself.  Budget: at most kPoolMaxPerClass
+// buffers per size, and never more than 72 % of the device memory parked in the cache.
 bool pool_give(int device, size_t bytes, void *ptr)
 {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    size_t same = 0;
+    size_t same = 0, cached = 0;
     for (const PoolEntry &e : g_pool)
-        if (e.device == device && e.bytes == bytes) ++same;
+        if (e.device == device) { cached += e.bytes; if (e.bytes == bytes) ++same; }
     if (same >= kPoolMaxPerClass) return false;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+    if (total_b && cached + bytes > total_b / 100 * 72) return false;
     g_pool.push_back({ device, bytes, ptr });
     return true;
 }
@@ -163,8 +167,16 @@ int DeviceVectorState::alloc_column(double2 **out)
 void DeviceVectorState::release_column(double2 *p)
 {
     if (!p) return;
-    // keep at most two spare buffers (relabel scratch + one split target)
-    if (free_bufs_.size() < 2 && n_ <= 31) free_bufs_.push_back(p);
+    // keep spare buffers (relabel scratch + one split target) as long as live + spare columns stay
+    // within ~80 % of the device memory; large shards keep exactly one spare
+    size_t live = 0;
+    for (const Column &c : cols_)
+        if (c.buf) ++live;
+    const size_t bytes = sizeof(double2) << n_;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+    const bool fits = total_b == 0 || (live + free_bufs_.size() + 1) * bytes <= total_b / 100 * 80;
+    if (free_bufs_.size() < 2 && fits) free_bufs_.push_back(p);
     else { cudaStreamSynchronize(stream_); cudaFree(p); }
 }
 
@@ -984,8 +996,11 @@ int DeviceVectorState::peer_swap(size_t col, const unsigned char *peer_handle64,
     // (the partner's buffers come from its buffer cache, so the same few handles keep coming back)
     static std::mutex ipc_mu;
     static std::vector<std::pair<std::string, void *>> ipc_open;
+    // Large shards (> 31 qubits) are not pooled: the partner frees them eagerly, and memory that is
+    // still mapped here would stay allocated there -- map and unmap around the kernel instead.
+    const bool keep_mapping = n_ <= 31;   // big shards may be freed by their owner right after: never leave them mapped
     void *theirs = nullptr;
-    {
+    if (keep_mapping) {
         std::lock_guard<std::mutex> lk(ipc_mu);
         const std::string key(reinterpret_cast<const char *>(peer_handle64), 64);
         for (auto &kv : ipc_open)
@@ -994,6 +1009,8 @@ int DeviceVectorState::peer_swap(size_t col, const unsigned char *peer_handle64,
             CK(cudaIpcOpenMemHandle(&theirs, h, cudaIpcMemLazyEnablePeerAccess));
             ipc_open.push_back(std::make_pair(key, theirs));
         }
+    } else {
+        CK(cudaIpcOpenMemHandle(&theirs, h, cudaIpcMemLazyEnablePeerAccess));
     }
     const int L = n_ - 1 - (int)local_qubit;
     cudaEventRecord(ev0_, stream_);
@@ -1002,6 +1019,7 @@ int DeviceVectorState::peer_swap(size_t col, const unsigned char *peer_handle64,
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     float ms = 0;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, ev0_, ev1_);
+    if (!keep_mapping) cudaIpcCloseMemHandle(theirs);
     if (e != cudaSuccess) return cuda_fail(e, "peer_swap");
     stats.peer_swap_ms += ms;
     stats.peer_swap_bytes += (16ull << n_) / 2;      // a quarter shard read remotely + a quarter written remotely
