@@ -35,6 +35,7 @@ def parse_args():
     ap.add_argument("--shots", type=int, default=8192)
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--prefetch-ahead", type=int, default=-1)
+    ap.add_argument("--direct", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -181,6 +182,8 @@ def run_ours(args, rank, world, local):
         st.set_option("tile_bits", args.tile_bits)
     if args.prefetch_ahead >= 0:
         st.set_option("prefetch_ahead", args.prefetch_ahead)
+    if args.direct >= 0:
+        st.set_option("direct", args.direct)
     res = np.zeros(shots, dtype=np.uint64)
     rng = E.Rng(seed=2)
 

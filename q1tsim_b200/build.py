@@ -20,9 +20,12 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant="", defines=()):
+    """variant: suffix for an A/B build (lib/libq1tsim<variant>.so) compiled with extra -D defines"""
+    global LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    LIB = os.path.join(LIBDIR, "libq1tsim%s.so" % variant)
+    objdir = os.path.join(LIBDIR, "obj" + variant)
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "q1t_engine.h"))
@@ -36,7 +39,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, src + ".o")
         objs.append(obj)
         if force or _stale(obj, [sp] + headers):
-            cmd = ["nvcc"] + NVCC_FLAGS + ["-x", "cu", "-c", sp, "-o", obj]
+            cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-x", "cu", "-c", sp, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
@@ -49,4 +52,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose=True, variant=var[0] if var else "", defines=defs))

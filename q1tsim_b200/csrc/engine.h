@@ -79,6 +79,7 @@ private:
     std::string err_;
     long tile_bits_ = 12;
     long prefetch_ahead_ = 0;
+    bool direct_ = true;
     bool fuse_ = true;
 
     // device scratch

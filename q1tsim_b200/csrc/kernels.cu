@@ -207,22 +207,74 @@ __device__ __forceinline__ void phase_h_apply(double2 (&a)[kSlots], const OpDesc
 // and then applies the unnormalised butterfly -- a radix-2^NS decimation stage
 // of the QFT/FFT with per-thread twiddles, but for arbitrary phase coefficients.
 // ---------------------------------------------------------------------------
+// where a round's amplitudes come from and go to
+struct RoundIO {
+    char *tile_b;                 // shared-memory tile
+    unsigned swT;                 // swizzled byte offset of this thread
+    const double2 *gsrc;          // != null: read from global (direct load), slot offsets P.dl_slot
+    double2 *gdst;                // != null: write to global (direct store), slot offsets P.ds_slot
+    bool zero_fill;               // generated input on the direct path
+    unsigned gen_slot;            // slot that holds the basis element (0xffffffff: none)
+    double scale;
+};
+
+__device__ __forceinline__ void round_load(double2 (&a)[kSlots], const RoundIO &io, const RoundDesc &R, const SweepProgram &P)
+{
+    if (io.gsrc) {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) a[s] = __ldcs(io.gsrc + P.dl_slot[s]);
+    } else if (io.zero_fill) {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)io.gen_slot ? 1.0 : 0.0, 0.0);
+    } else {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(io.tile_b + (io.swT ^ R.sw_slot[s]));
+    }
+}
+
+__device__ __forceinline__ void round_store(const double2 (&a)[kSlots], const RoundIO &io, const RoundDesc &R, const SweepProgram &P)
+{
+    if (io.gdst) {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) st_global_cs(io.gdst + P.ds_slot[s], make_double2(a[s].x * io.scale, a[s].y * io.scale));
+    } else {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(io.tile_b + (io.swT ^ R.sw_slot[s])) = a[s];
+    }
+}
+
 template <int NS>
-__device__ __forceinline__ void round_ph(char *tile_b, unsigned swT, const RoundDesc &R, const SweepProgram &P,
+__device__ __forceinline__ void round_ph(const RoundIO &io, const RoundDesc &R, const SweepProgram &P,
                                          const PhaseTab *__restrict__ ptabs, const double2 *s_tileF, unsigned tid)
 {
     double2 a[kSlots];
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
     const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
+#ifdef Q1T_HOIST_F
+    // the per-thread factors do not depend on the amplitudes: fetch them all first so that their
+    // table loads and multiplies overlap the amplitude loads instead of heading every step
+    double2 F[NS];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
         const OpDesc &op = P.ops[R.op_begin + j];
         const PhaseTab &pt = ptabs[op.phase_id];
         const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
         const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
+        F[j] = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
+    }
+#endif
+    round_load(a, io, R, P);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const OpDesc &op = P.ops[R.op_begin + j];
         double2 f[1 << (NS - 1)];
+#ifdef Q1T_HOIST_F
+        f[0] = F[j];
+#else
+        const PhaseTab &pt = ptabs[op.phase_id];
+        const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
+        const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
         f[0] = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
+#endif
 #pragma unroll
         for (int i = 0; i < j; ++i) {
             const double2 q = make_double2(op.m[2 * i], op.m[2 * i + 1]);
@@ -240,8 +292,7 @@ __device__ __forceinline__ void round_ph(char *tile_b, unsigned swT, const Round
             a[s1] = make_double2(x.x - tr, x.y - ti);
         }
     }
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
+    round_store(a, io, R, P);
 }
 
 // LINPHASE: product of independent one-qubit phases on any set of index bits (the linear part
@@ -282,7 +333,13 @@ __device__ __forceinline__ unsigned long long outer_base(const uint64_t (&tab)[k
 // ---------------------------------------------------------------------------
 // the sweep kernel
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
+// INTERP = false: programs whose rounds are all ROUND_PH ladders (or that have no rounds at all):
+// the op interpreter is compiled out, which leaves a small straight-line kernel.
+#ifndef Q1T_LADDER_MIN_CTAS
+#define Q1T_LADDER_MIN_CTAS 2
+#endif
+template <bool INTERP, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
              const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx)
 {
@@ -296,29 +353,23 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
     const int col = blockIdx.y;
     char *const tile_b = reinterpret_cast<char *>(tile);
 
-    // ---- stage the tile in shared memory ----
-    const unsigned sw_tid = tile_swizzle(tid) * 16u;      // tid < 2^TB <= 512: swizzle of the low part
-    if (!P.generate) {
-        // coalesced: consecutive tid -> consecutive source addresses
-        unsigned long long soff = outer_base(P.o_src, o, P.n_outer);
-        for (int k = 0; k < P.ld_nruns; ++k) soff |= (unsigned long long)(tid & P.ld_runs[k].mask) << P.ld_runs[k].shift;
-        const double2 *__restrict__ src = src_cols[col] + soff;
+    const bool dload = P.direct_load != 0, dstore = P.direct_store != 0 && P.nrounds > 0;
+    const unsigned long long obase_src = outer_base(P.o_src, o, P.n_outer);
+
+    // ---- bring the tile in, unless round 0 reads global memory itself ----
+    if (!dload) {
+        const unsigned sw_tid = tile_swizzle(tid) * 16u;
+        if (!P.generate) {
+            // coalesced: consecutive tid -> consecutive source addresses
+            unsigned long long soff = obase_src;
+            for (int k = 0; k < P.ld_nruns; ++k) soff |= (unsigned long long)(tid & P.ld_runs[k].mask) << P.ld_runs[k].shift;
+            const double2 *__restrict__ src = src_cols[col] + soff;
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw_tid ^ P.ld_sw_hi[i]), src + P.ld_hi[i]);
-        // pull the tile that a CTA one residency wave later will stage into L2 (one 128-byte line per 8 threads)
-        if (P.prefetch_ahead > 0 && (tid & 7u) == 0u) {
-            const unsigned long long o2 = o + (unsigned long long)P.prefetch_ahead;
-            if (o2 < (1ull << P.n_outer)) {
-                const double2 *nxt = src_cols[col] + (soff ^ outer_base(P.o_src, o, P.n_outer) ^ outer_base(P.o_src, o2, P.n_outer));
+            for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw_tid ^ P.ld_sw_hi[i]), src + P.ld_hi[i]);
+        } else {
 #pragma unroll
-                for (int i = 0; i < kSlots; ++i)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + P.ld_hi[i]));
-            }
+            for (int i = 0; i < kSlots; ++i) *reinterpret_cast<double2 *>(tile_b + (sw_tid ^ P.ld_sw_hi[i])) = make_double2(0.0, 0.0);
         }
-    } else {
-        // the source is the basis state |gen_idx>: synthesise the tile instead of reading it
-#pragma unroll
-        for (int i = 0; i < kSlots; ++i) *reinterpret_cast<double2 *>(tile_b + (sw_tid ^ P.ld_sw_hi[i])) = make_double2(0.0, 0.0);
     }
     // per-tile phase factors (depend on the outer index bits only)
     for (int pid = tid; pid < P.nphase; pid += blockDim.x) {
@@ -330,19 +381,20 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         sincospi(ang, &s, &c);
         s_tileF[pid] = make_double2(c, s);
     }
-    if (!P.generate) {
-        cp_async_commit_wait_all();
-    } else {
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned long long g = gen_idx[col];
-            unsigned long long tmask = 0;
-            unsigned l = 0;
-            for (int i = 0; i < T; ++i) {
-                tmask |= 1ull << P.tsrc[i];
-                l |= (unsigned)((g >> P.tsrc[i]) & 1ull) << i;
-            }
-            if ((g & ~tmask) == outer_base(P.o_src, o, P.n_outer)) tile[tile_swizzle(l)] = make_double2(1.0, 0.0);
+    // the basis element of a generated input (it lives in exactly one tile of the grid)
+    unsigned gen_l = 0xffffffffu;
+    if (P.generate) {
+        const unsigned long long g = gen_idx[col];
+        if ((g & ~P.tile_mask_src) == obase_src) {
+            gen_l = 0;
+            for (int i = 0; i < T; ++i) gen_l |= (unsigned)((g >> P.tsrc[i]) & 1ull) << i;
+        }
+    }
+    if (!dload) {
+        if (!P.generate) cp_async_commit_wait_all();
+        else {
+            __syncthreads();
+            if (tid == 0 && gen_l != 0xffffffffu) tile[tile_swizzle(gen_l)] = make_double2(1.0, 0.0);
         }
     }
     __syncthreads();
@@ -352,22 +404,53 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         const RoundDesc &R = P.rounds[r];
         unsigned thrL = 0;
         for (int k = 0; k < R.nruns; ++k) thrL |= (tid & R.runs[k].mask) << R.runs[k].shift;
-        const unsigned swT = tile_swizzle(thrL) * 16u;
-        if (R.kind == ROUND_PH) {
-            switch (R.nsteps) {
-            case 1: round_ph<1>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
-            case 2: round_ph<2>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
-            case 3: round_ph<3>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
-            default: round_ph<4>(tile_b, swT, R, P, ptabs, s_tileF, tid); break;
+        RoundIO io;
+        io.tile_b = tile_b;
+        io.swT = tile_swizzle(thrL) * 16u;
+        io.gsrc = nullptr;
+        io.gdst = nullptr;
+        io.zero_fill = false;
+        io.gen_slot = 0xffffffffu;
+        io.scale = P.scale;
+        if (r == 0 && dload) {
+            if (!P.generate) {
+                unsigned long long off = obase_src;
+                for (int k = 0; k < P.dl_nruns; ++k) off |= (unsigned long long)(tid & P.dl_runs[k].mask) << P.dl_runs[k].shift;
+                io.gsrc = src_cols[col] + off;
+            } else {
+                io.zero_fill = true;
+                if (gen_l != 0xffffffffu) {
+                    unsigned regmask = 0, slot = 0;
+                    for (int j = 0; j < kRegBits; ++j) {
+                        regmask |= 1u << R.reg_tb[j];
+                        slot |= ((gen_l >> R.reg_tb[j]) & 1u) << j;
+                    }
+                    if ((gen_l & ~regmask) == thrL) io.gen_slot = slot;
+                }
             }
-            __syncthreads();
+        } else if (r > 0) {
+            if (R.sync_before == 2) __syncthreads();
+            else __syncwarp();
+        }
+        if (r + 1 == P.nrounds && dstore) {
+            unsigned long long off = outer_base(P.o_dst, o, P.n_outer);
+            for (int k = 0; k < P.ds_nruns; ++k) off |= (unsigned long long)(tid & P.ds_runs[k].mask) << P.ds_runs[k].shift;
+            io.gdst = dst_cols[col] + off;
+        }
+
+        if (!INTERP || R.kind == ROUND_PH) {
+            switch (R.nsteps) {
+            case 1: round_ph<1>(io, R, P, ptabs, s_tileF, tid); break;
+            case 2: round_ph<2>(io, R, P, ptabs, s_tileF, tid); break;
+            case 3: round_ph<3>(io, R, P, ptabs, s_tileF, tid); break;
+            default: round_ph<4>(io, R, P, ptabs, s_tileF, tid); break;
+            }
             continue;
         }
+        if (!INTERP) continue;
         double2 a[kSlots];
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
+        round_load(a, io, R, P);
         const unsigned long long vbase = vhi | thrL;
-
         for (int k = R.op_begin; k < R.op_end; ++k) {
             const OpDesc &op = P.ops[k];
             const unsigned kind = op.kind;
@@ -393,10 +476,11 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
                 }
             }
         }
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
-        __syncthreads();
+        round_store(a, io, R, P);
     }
+    if (dstore) return;
+    const double scale = P.scale;
+    __syncthreads();
 
     // ---- store the tile (coalesced in the destination layout) ----
     unsigned long long doff = outer_base(P.o_dst, o, P.n_outer);
@@ -408,7 +492,6 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         l_lo |= sh >= 0 ? v << sh : v >> -sh;
     }
     double2 *__restrict__ dst = dst_cols[col] + doff;
-    const double scale = P.scale;
     const unsigned sw_lo = tile_swizzle(l_lo) * 16u;
     if (scale == 1.0) {
 #pragma unroll
@@ -431,13 +514,21 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
     const size_t smem = sizeof(double2) << prog.T;
     static bool smem_set = false;
     if (!smem_set) {
-        e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << kMaxTileBits));
+        e = cudaFuncSetAttribute(sweep_kernel<true, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << kMaxTileBits));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(sweep_kernel<false, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << kMaxTileBits));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(sweep_kernel<false, 256, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12));
         if (e != cudaSuccess) return e;
         smem_set = true;
     }
+    bool ladders_only = true;
+    for (int r = 0; r < prog.nrounds; ++r) ladders_only = ladders_only && prog.rounds[r].kind == ROUND_PH;
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
-    sweep_kernel<<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+    if (ladders_only && prog.TB <= 8) sweep_kernel<false, 256, Q1T_LADDER_MIN_CTAS><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+    else if (ladders_only) sweep_kernel<false, 512, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+    else sweep_kernel<true, 512, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
     return cudaGetLastError();
 }
 

@@ -77,6 +77,69 @@ static void fill_outer_tables(SweepProgram &P)
         }
 }
 
+// Decide which rounds can skip shared-memory staging and how wide each inter-round barrier must be.
+//  - round 0 may read straight from global memory when tile bits 0,1,2 (128 contiguous bytes) are its
+//    three lowest thread bits; the last round may write straight to global memory when the three
+//    lowest destination bits are its three lowest thread bits;
+//  - between two rounds a __syncwarp is enough when every warp-index bit (tid bit >= 5) stands for
+//    the same tile bit in both rounds: each warp then re-reads only what it wrote itself.
+static void setup_direct(SweepProgram &P)
+{
+    P.tile_mask_src = 0;
+    for (int i = 0; i < P.T; ++i) P.tile_mask_src |= 1ull << P.tsrc[i];
+    P.direct_load = P.direct_store = 0;
+    P.dl_nruns = P.ds_nruns = 0;
+    for (int r = 0; r < P.nrounds; ++r) {
+        RoundDesc &R = P.rounds[r];
+        R.sync_before = 2;
+        if (r > 0) {
+            const RoundDesc &Q = P.rounds[r - 1];
+            bool warp_local = true;
+            for (int i = 5; i < P.TB; ++i)
+                if (R.thr_tb[i] != Q.thr_tb[i]) warp_local = false;
+            if (warp_local) R.sync_before = 1;
+        }
+    }
+    if (P.nrounds == 0 || P.TB < 3) return;
+    {
+        const RoundDesc &R = P.rounds[0];
+        bool ok = true;
+        for (int i = 0; i < 3; ++i) ok = ok && R.thr_tb[i] == i && P.tsrc[i] == i;
+        if (ok) {
+            int pos[kMaxThrBits + 1];
+            for (int i = 0; i < P.TB; ++i) pos[i] = P.tsrc[R.thr_tb[i]];
+            P.dl_nruns = make_runs(pos, P.TB, P.dl_runs);
+            for (int s = 0; s < kSlots; ++s) {
+                uint64_t off = 0;
+                for (int j = 0; j < kRegBits; ++j)
+                    if ((s >> j) & 1) off |= 1ull << P.tsrc[R.reg_tb[j]];
+                P.dl_slot[s] = off;
+            }
+            P.direct_load = 1;
+        }
+    }
+    {
+        const RoundDesc &R = P.rounds[P.nrounds - 1];
+        bool ok = true;
+        int pos[kMaxThrBits + 1];
+        for (int i = 0; i < P.TB; ++i) {
+            pos[i] = P.tdst[R.thr_tb[i]];
+            if (i < 3 && pos[i] != i) ok = false;
+            if (i > 0 && pos[i] <= pos[i - 1]) ok = false;
+        }
+        if (ok) {
+            P.ds_nruns = make_runs(pos, P.TB, P.ds_runs);
+            for (int s = 0; s < kSlots; ++s) {
+                uint64_t off = 0;
+                for (int j = 0; j < kRegBits; ++j)
+                    if ((s >> j) & 1) off |= 1ull << P.tdst[R.reg_tb[j]];
+                P.ds_slot[s] = off;
+            }
+            P.direct_store = 1;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // lowering
 // ---------------------------------------------------------------------------
@@ -594,6 +657,7 @@ void Planner::close_sweep()
     }
     P.nops = nops;
     P.nphase = nphase;
+    setup_direct(P);
     stats.sweeps += 1;
     stats.rounds += P.nrounds;
     stats.ops += nops;
@@ -652,6 +716,7 @@ void set_relabel(SweepProgram &P, const std::vector<int> &dstpos)
         P.st_l_hi[i] = tile_swizzle(l) * 16u;
     }
     fill_outer_tables(P);
+    setup_direct(P);
 }
 
 // can a relabel be fused into this (gate) sweep?  the sources of the three lowest

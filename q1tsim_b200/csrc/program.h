@@ -62,6 +62,8 @@ struct RoundDesc {
     uint8_t nruns;
     uint8_t kind;                   // ROUND_GENERIC: op interpreter; ROUND_PH: straight-line PHASE_H ladder
     uint8_t nsteps;                 // ROUND_PH: ops op_begin..op_begin+nsteps-1 act on slot bits 0..nsteps-1
+    uint8_t sync_before;            // 0 none, 1 __syncwarp (data only moves inside warps), 2 __syncthreads
+    uint8_t pad1[3];
     BitRun runs[kMaxRuns];          // tid -> tile-local index of the thread
     uint32_t sw_slot[kSlots];       // byte offset (swizzled index * 16) contributed by slot s
     uint16_t op_begin, op_end;
@@ -77,6 +79,10 @@ struct SweepProgram {
     int32_t generate;     // 1: the source column is a basis state |gen_idx[col]>, nothing is read
     int32_t ld_nruns, st_nruns;
     int32_t prefetch_ahead;   // >0: prefetch the tile this many outer indices ahead into L2
+    int32_t direct_load;      // round 0 reads its amplitudes straight from global memory (no staging pass)
+    int32_t direct_store;     // the last round writes its amplitudes straight to global memory
+    int32_t dl_nruns, ds_nruns;
+    uint64_t tile_mask_src;   // source positions of the tile bits
     double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];
@@ -94,6 +100,12 @@ struct SweepProgram {
     BitRun st_lruns[kMaxRuns];         // tid -> tile index
     uint64_t st_off_hi[kSlots];        // destination offset of the high part of f
     uint32_t st_l_hi[kSlots];          // swizzled byte offset of the tile index of the high part of f
+    // direct paths: thread -> offset runs and slot -> offset tables of round 0 (source layout)
+    // and of the last round (destination layout)
+    BitRun dl_runs[kMaxRuns];
+    uint64_t dl_slot[kSlots];
+    BitRun ds_runs[kMaxRuns];
+    uint64_t ds_slot[kSlots];
     RoundDesc rounds[kMaxRounds];
     OpDesc ops[kMaxOps];
 };

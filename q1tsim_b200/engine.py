@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libq1tsim.so")
+LIB_PATH = os.environ.get("Q1T_LIB") or os.path.join(_HERE, "lib", "libq1tsim.so")   # Q1T_LIB: A/B builds
 
 ERROR_KINDS = {
     -1: "InvalidNrBits", -2: "InvalidQBit", -3: "NotEnoughSpace", -4: "InvalidNrMeasurementBits",
