@@ -417,6 +417,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
         ps.prog.generate = (generate && si == 0) ? 1 : 0;
         ps.prog.prefetch_ahead = (int)prefetch_ahead_;
+        ps.prog.dbg_skip = (int)dbg_skip_;
         if (!direct_) {                       // A/B switch: always stage through shared memory, CTA-wide barriers
             ps.prog.direct_load = ps.prog.direct_store = 0;
             for (int r = 0; r < ps.prog.nrounds; ++r) ps.prog.rounds[r].sync_before = 2;
@@ -1211,6 +1212,10 @@ int DeviceVectorState::set_option(const char *key, long value)
         int rc = run_queue();
         if (rc) return rc;
         tile_bits_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "dbg_skip")) {
+        dbg_skip_ = value;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "direct")) {

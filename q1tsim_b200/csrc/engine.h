@@ -80,6 +80,7 @@ private:
     long tile_bits_ = 12;
     long prefetch_ahead_ = 0;
     bool direct_ = true;
+    long dbg_skip_ = 0;
     bool fuse_ = true;
 
     // device scratch

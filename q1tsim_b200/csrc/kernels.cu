@@ -220,9 +220,12 @@ struct RoundIO {
 
 __device__ __forceinline__ void round_load(double2 (&a)[kSlots], const RoundIO &io, const RoundDesc &R, const SweepProgram &P)
 {
-    if (io.gsrc) {
+    if (io.gsrc && !(P.dbg_skip & 1)) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) a[s] = __ldcs(io.gsrc + P.dl_slot[s]);
+    } else if (io.gsrc) {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) a[s] = make_double2(1.0 + s, (double)threadIdx.x);
     } else if (io.zero_fill) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)io.gen_slot ? 1.0 : 0.0, 0.0);
@@ -234,7 +237,12 @@ __device__ __forceinline__ void round_load(double2 (&a)[kSlots], const RoundIO &
 
 __device__ __forceinline__ void round_store(const double2 (&a)[kSlots], const RoundIO &io, const RoundDesc &R, const SweepProgram &P)
 {
-    if (io.gdst) {
+    if (io.gdst && (P.dbg_skip & 2)) {
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) acc += a[s].x * io.scale + a[s].y;
+        if (acc == 1.2345e-300) st_global_cs(io.gdst, make_double2(acc, acc));     // keeps the arithmetic alive
+    } else if (io.gdst) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) st_global_cs(io.gdst + P.ds_slot[s], make_double2(a[s].x * io.scale, a[s].y * io.scale));
     } else {

@@ -83,6 +83,8 @@ struct SweepProgram {
     int32_t direct_store;     // the last round writes its amplitudes straight to global memory
     int32_t dl_nruns, ds_nruns;
     uint64_t tile_mask_src;   // source positions of the tile bits
+    int32_t dbg_skip;         // timing experiments only: bit0 = skip loads, bit1 = skip stores (results are wrong)
+    int32_t pad_dbg;
     double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];
