@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -94,6 +95,10 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
 {
     perm_.resize(n_);
     for (int i = 0; i < n_; ++i) perm_[i] = i;
+    // A/B switches for whole-process experiments (bench.py, tools/): same as set_option()
+    if (const char *e = std::getenv("Q1T_COALESCE_BITS")) { const long v = std::atol(e); if (v == 2 || v == 3) coalesce_bits_ = v; }
+    if (const char *e = std::getenv("Q1T_BALANCE")) balance_ = std::atol(e);
+    if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
 }
 
 DeviceVectorState::~DeviceVectorState()
@@ -497,7 +502,25 @@ int DeviceVectorState::run_queue(bool final_relabel)
         }
         return Q1T_OK;
     }
-    Planner pl(n_, (int)tile_bits_);
+    // two packings are tried on the host (planning is cheap): greedy (fill every tile) and balanced
+    // (never open a round the tile cannot fill); the one with fewer sweeps, then fewer rounds, runs
+    bool balance = balance_ > 0;
+    if (balance_ < 0) {
+        bool fusable = true;
+        for (const LoweredGate &g : q) fusable = fusable && (g.kind == LoweredGate::POLY || g.kind == LoweredGate::G1);
+        if (fusable) {
+            uint64_t cost[2][2];
+            for (int b = 0; b < 2; ++b) {
+                Planner trial(n_, (int)tile_bits_, (int)coalesce_bits_, b != 0);
+                for (const LoweredGate &g : q) trial.add(g);
+                trial.finish();
+                cost[b][0] = trial.stats.sweeps;
+                cost[b][1] = trial.stats.rounds;
+            }
+            balance = cost[1][0] < cost[0][0] || (cost[1][0] == cost[0][0] && cost[1][1] < cost[0][1]);
+        }
+    }
+    Planner pl(n_, (int)tile_bits_, (int)coalesce_bits_, balance);
     for (const LoweredGate &g : q) {
         if (g.kind == LoweredGate::POLY || g.kind == LoweredGate::G1) {
             pl.add(g);
@@ -1212,6 +1235,19 @@ int DeviceVectorState::set_option(const char *key, long value)
         int rc = run_queue();
         if (rc) return rc;
         tile_bits_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "coalesce_bits")) {
+        if (value < 2 || value > 3) return fail(Q1T_ERR_INVALID_ARGUMENT, "coalesce_bits must be 2 or 3");
+        int rc = run_queue();
+        if (rc) return rc;
+        coalesce_bits_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "balance")) {
+        int rc = run_queue();
+        if (rc) return rc;
+        balance_ = value;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "dbg_skip")) {

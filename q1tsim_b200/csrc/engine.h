@@ -78,6 +78,8 @@ private:
     std::vector<double2 *> free_bufs_;
     std::string err_;
     long tile_bits_ = 12;
+    long coalesce_bits_ = 3;                 // low index bits kept contiguous per tile (3 = 128 B, 2 = 64 B)
+    long balance_ = -1;                      // sweep packing: -1 try both, 0 greedy, 1 balanced
     long prefetch_ahead_ = 0;
     bool direct_ = true;
     long dbg_skip_ = 0;

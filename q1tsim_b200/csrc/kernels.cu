@@ -19,6 +19,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cstdlib>
 
 namespace q1t {
 
@@ -44,6 +45,13 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 __device__ __forceinline__ void st_global_cs(double2 *p, double2 v)
 {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ((v & mask) << shift) with shift of either sign (bit-deposit runs of a thread index)
+__device__ __forceinline__ unsigned long long run_bits(unsigned v, const BitRun &r)
+{
+    const unsigned long long m = v & r.mask;
+    return r.shift >= 0 ? m << r.shift : m >> -r.shift;
 }
 
 // insert a zero bit at position J into p
@@ -172,8 +180,8 @@ __device__ __forceinline__ void phase_apply(double2 (&a)[kSlots], const OpDesc &
         const int s1 = ins0<J>(u) | (1 << J);
         a[s1] = cmul(a[s1], f[u]);
     }
-    if (op.flags & 8u) {
-        const double2 c0 = make_double2(op.m[6], op.m[7]);
+    if (op.flags & kFlagC0) {
+        const double2 c0 = make_double2(op.m[8], op.m[9]);
 #pragma unroll
         for (int u = 0; u < kSlots / 2; ++u) {
             const int s0 = ins0<J>(u);
@@ -201,7 +209,8 @@ __device__ __forceinline__ void phase_h_apply(double2 (&a)[kSlots], const OpDesc
 }
 
 // ---------------------------------------------------------------------------
-// ROUND_PH: NS fused (phase, Hadamard-butterfly) steps on slot bits 0..NS-1,
+// ROUND_PH: NS fused (phase, Hadamard-butterfly) steps on the top NS slot bits
+// kRegBits-NS..kRegBits-1 (lower slots are padding that only acts as partner bits),
 // straight-line code.  Step j multiplies the bit-j=1 half by
 //   F_j(thread, tile) * prod_{i<j, slot bit i set} q_{j,i}
 // and then applies the unnormalised butterfly -- a radix-2^NS decimation stage
@@ -251,55 +260,61 @@ __device__ __forceinline__ void round_store(const double2 (&a)[kSlots], const Ro
     }
 }
 
-template <int NS>
-__device__ __forceinline__ void round_ph(const RoundIO &io, const RoundDesc &R, const SweepProgram &P,
-                                         const PhaseTab *__restrict__ ptabs, const double2 *s_tileF, unsigned tid)
-{
-    double2 a[kSlots];
-    const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
-#ifdef Q1T_HOIST_F
-    // the per-thread factors do not depend on the amplitudes: fetch them all first so that their
-    // table loads and multiplies overlap the amplitude loads instead of heading every step
-    double2 F[NS];
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-        const OpDesc &op = P.ops[R.op_begin + j];
-        const PhaseTab &pt = ptabs[op.phase_id];
-        const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
-        const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
-        F[j] = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
+// Step J of a ladder round: the pairs of slot bit J whose already-processed slot bits (< J) read
+// u get the factor f(u) = F * prod_{i in u} q_i.  The factors are produced depth-first (at most
+// J + 1 of them alive) instead of as a 2^J-entry table, which keeps 32 amplitudes + factors
+// within the register budget of 3 CTAs per SM.
+template <int J, int I>
+struct LadderStep {
+    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const OpDesc &op, double2 f, int u)
+    {
+        LadderStep<J, I - 1>::run(a, op, f, u);
+        const double2 q = make_double2(op.m[2 * I], op.m[2 * I + 1]);
+        LadderStep<J, I - 1>::run(a, op, cmul(f, q), u | (1 << I));
     }
-#endif
-    round_load(a, io, R, P);
+};
+template <int J>
+struct LadderStep<J, -1> {
+    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const OpDesc &, double2 f, int u)
+    {
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
-        const OpDesc &op = P.ops[R.op_begin + j];
-        double2 f[1 << (NS - 1)];
-#ifdef Q1T_HOIST_F
-        f[0] = F[j];
-#else
-        const PhaseTab &pt = ptabs[op.phase_id];
-        const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
-        const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
-        f[0] = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
-#endif
-#pragma unroll
-        for (int i = 0; i < j; ++i) {
-            const double2 q = make_double2(op.m[2 * i], op.m[2 * i + 1]);
-#pragma unroll
-            for (int u = 0; u < (1 << i); ++u) f[u | (1 << i)] = cmul(f[u], q);
-        }
-#pragma unroll
-        for (int p = 0; p < kSlots / 2; ++p) {
-            const int s0 = ((p >> j) << (j + 1)) | (p & ((1 << j) - 1)), s1 = s0 | (1 << j);
-            const double2 ff = f[p & ((1 << j) - 1)];
+        for (int h = 0; h < (kSlots >> (J + 1)); ++h) {
+            const int s0 = (h << (J + 1)) | u, s1 = s0 | (1 << J);
             const double2 x = a[s0], y = a[s1];
-            const double tr = fma(y.x, ff.x, -(y.y * ff.y));
-            const double ti = fma(y.x, ff.y, y.y * ff.x);
+            const double tr = fma(y.x, f.x, -(y.y * f.y));
+            const double ti = fma(y.x, f.y, y.y * f.x);
             a[s0] = make_double2(x.x + tr, x.y + ti);
             a[s1] = make_double2(x.x - tr, x.y - ti);
         }
     }
+};
+
+template <int NS, int J>
+struct LadderSteps {
+    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const RoundDesc &R, const SweepProgram &P,
+                                               const PhaseTab *__restrict__ ptabs, const double2 *s_hiF, int he_bits, unsigned il, unsigned ih)
+    {
+        const OpDesc &op = P.ops[R.op_begin + J - (kRegBits - NS)];
+        const double2 lo = __ldg(reinterpret_cast<const double2 *>(ptabs[op.phase_id].lo) + il);
+        const double2 hi = s_hiF[(op.phase_id << he_bits) + ih];          // hi[ih] * tile factor
+        LadderStep<J, J - 1>::run(a, op, cmul(lo, hi), 0);
+        LadderSteps<NS, J + 1>::run(a, R, P, ptabs, s_hiF, he_bits, il, ih);
+    }
+};
+template <int NS>
+struct LadderSteps<NS, kRegBits> {
+    static __device__ __forceinline__ void run(double2 (&)[kSlots], const RoundDesc &, const SweepProgram &,
+                                               const PhaseTab *__restrict__, const double2 *, int, unsigned, unsigned) {}
+};
+
+template <int NS>
+__device__ __forceinline__ void round_ph(const RoundIO &io, const RoundDesc &R, const SweepProgram &P,
+                                         const PhaseTab *__restrict__ ptabs, const double2 *s_hiF, int he_bits, unsigned tid)
+{
+    double2 a[kSlots];
+    const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
+    round_load(a, io, R, P);
+    LadderSteps<NS, kRegBits - NS>::run(a, R, P, ptabs, s_hiF, he_bits, il, ih);
     round_store(a, io, R, P);
 }
 
@@ -319,6 +334,16 @@ __device__ __forceinline__ void linphase_apply(double2 (&a)[kSlots], const OpDes
     for (int s = 0; s < kSlots; ++s) a[s] = cmul(a[s], f[s]);
 }
 
+#if Q1T_REG_BITS >= 5
+#define Q1T_DISPATCH_J(fn, ...)          \
+    switch (op.j) {                      \
+    case 0: fn<0>(__VA_ARGS__); break;   \
+    case 1: fn<1>(__VA_ARGS__); break;   \
+    case 2: fn<2>(__VA_ARGS__); break;   \
+    case 3: fn<3>(__VA_ARGS__); break;   \
+    default: fn<4>(__VA_ARGS__); break;  \
+    }
+#else
 #define Q1T_DISPATCH_J(fn, ...)          \
     switch (op.j) {                      \
     case 0: fn<0>(__VA_ARGS__); break;   \
@@ -326,6 +351,7 @@ __device__ __forceinline__ void linphase_apply(double2 (&a)[kSlots], const OpDes
     case 2: fn<2>(__VA_ARGS__); break;   \
     default: fn<3>(__VA_ARGS__); break;  \
     }
+#endif
 
 __device__ __forceinline__ unsigned long long outer_base(const uint64_t (&tab)[kOuterChunks][1 << kOuterChunkBits],
                                                          unsigned long long o, int n_outer)
@@ -343,16 +369,12 @@ __device__ __forceinline__ unsigned long long outer_base(const uint64_t (&tab)[k
 // ---------------------------------------------------------------------------
 // INTERP = false: programs whose rounds are all ROUND_PH ladders (or that have no rounds at all):
 // the op interpreter is compiled out, which leaves a small straight-line kernel.
-#ifndef Q1T_LADDER_MIN_CTAS
-#define Q1T_LADDER_MIN_CTAS 2
-#endif
 template <bool INTERP, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
              const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx)
 {
     extern __shared__ double2 tile[];
-    __shared__ double2 s_tileF[kMaxPhase];
 
     const SweepProgram &P = c_prog;
     const int T = P.T, TB = P.TB;
@@ -360,6 +382,8 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
     const unsigned long long o = blockIdx.x;
     const int col = blockIdx.y;
     char *const tile_b = reinterpret_cast<char *>(tile);
+    // per-tile phase factors behind the tile: s_hiF[pid][ih] = hi[ih] * exp(i*pi*angle(outer bits))
+    double2 *const s_hiF = tile + (1u << T);
 
     const bool dload = P.direct_load != 0, dstore = P.direct_store != 0 && P.nrounds > 0;
     const unsigned long long obase_src = outer_base(P.o_src, o, P.n_outer);
@@ -379,15 +403,21 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
             for (int i = 0; i < kSlots; ++i) *reinterpret_cast<double2 *>(tile_b + (sw_tid ^ P.ld_sw_hi[i])) = make_double2(0.0, 0.0);
         }
     }
-    // per-tile phase factors (depend on the outer index bits only)
-    for (int pid = tid; pid < P.nphase; pid += blockDim.x) {
-        const PhaseTab &pt = ptabs[pid];
-        double ang = pt.base;
-        for (int i = 0; i < P.n_outer; ++i)
-            if ((o >> i) & 1ull) ang += pt.outer_coef[i];
-        double s, c;
-        sincospi(ang, &s, &c);
-        s_tileF[pid] = make_double2(c, s);
+    // per-tile phase factors: the part that depends on the outer index bits only, folded into the
+    // table of the high thread bits (one complex multiply per thread and step less)
+    const int he_bits = TB > kThrLoBits ? TB - kThrLoBits : 0;
+    {
+        for (int e = tid; e < (P.nphase << he_bits); e += blockDim.x) {
+            const int pid = e >> he_bits, ih = e & ((1 << he_bits) - 1);
+            const PhaseTab &pt = ptabs[pid];
+            double ang = pt.base;
+            for (int i = 0; i < P.n_outer; ++i)
+                if ((o >> i) & 1ull) ang += pt.outer_coef[i];
+            double sn, cs;
+            sincospi(ang, &sn, &cs);
+            const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
+            s_hiF[e] = cmul(hi, make_double2(cs, sn));
+        }
     }
     // the basis element of a generated input (it lives in exactly one tile of the grid)
     unsigned gen_l = 0xffffffffu;
@@ -411,7 +441,7 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
     for (int r = 0; r < P.nrounds; ++r) {
         const RoundDesc &R = P.rounds[r];
         unsigned thrL = 0;
-        for (int k = 0; k < R.nruns; ++k) thrL |= (tid & R.runs[k].mask) << R.runs[k].shift;
+        for (int k = 0; k < R.nruns; ++k) thrL |= (unsigned)run_bits(tid, R.runs[k]);
         RoundIO io;
         io.tile_b = tile_b;
         io.swT = tile_swizzle(thrL) * 16u;
@@ -442,16 +472,21 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         }
         if (r + 1 == P.nrounds && dstore) {
             unsigned long long off = outer_base(P.o_dst, o, P.n_outer);
-            for (int k = 0; k < P.ds_nruns; ++k) off |= (unsigned long long)(tid & P.ds_runs[k].mask) << P.ds_runs[k].shift;
+            for (int k = 0; k < P.ds_nruns; ++k) off |= run_bits(tid, P.ds_runs[k]);
             io.gdst = dst_cols[col] + off;
         }
 
         if (!INTERP || R.kind == ROUND_PH) {
             switch (R.nsteps) {
-            case 1: round_ph<1>(io, R, P, ptabs, s_tileF, tid); break;
-            case 2: round_ph<2>(io, R, P, ptabs, s_tileF, tid); break;
-            case 3: round_ph<3>(io, R, P, ptabs, s_tileF, tid); break;
-            default: round_ph<4>(io, R, P, ptabs, s_tileF, tid); break;
+            case 1: round_ph<1>(io, R, P, ptabs, s_hiF, he_bits, tid); break;
+            case 2: round_ph<2>(io, R, P, ptabs, s_hiF, he_bits, tid); break;
+            case 3: round_ph<3>(io, R, P, ptabs, s_hiF, he_bits, tid); break;
+#if Q1T_REG_BITS >= 5
+            case 4: round_ph<4>(io, R, P, ptabs, s_hiF, he_bits, tid); break;
+            default: round_ph<5>(io, R, P, ptabs, s_hiF, he_bits, tid); break;
+#else
+            default: round_ph<4>(io, R, P, ptabs, s_hiF, he_bits, tid); break;
+#endif
             }
             continue;
         }
@@ -466,8 +501,7 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
                 const PhaseTab &pt = ptabs[op.phase_id];
                 const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
                 const double2 lo = __ldg(reinterpret_cast<const double2 *>(pt.lo) + il);
-                const double2 hi = __ldg(reinterpret_cast<const double2 *>(pt.hi) + ih);
-                const double2 F = cmul(cmul(lo, hi), s_tileF[op.phase_id]);
+                const double2 F = cmul(lo, s_hiF[(op.phase_id << he_bits) + ih]);
                 if (kind == OP_PHASE_H) { Q1T_DISPATCH_J(phase_h_apply, a, op, F) }
                 else if (kind == OP_LINPHASE) linphase_apply(a, op, F);
                 else { Q1T_DISPATCH_J(phase_apply, a, op, F) }
@@ -514,19 +548,201 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
     }
 }
 
+// ---------------------------------------------------------------------------
+// the ladder kernel: sweeps whose rounds are all ROUND_PH ladders (QFT-like circuits).
+//
+// Persistent CTAs (a few per SM) walk over the tiles.  A CTA is a serial chain
+// per tile (tables -> loads -> rounds -> stores) and only 2-3 CTAs fit on an SM,
+// so the chain is software-pipelined: as soon as every thread of the CTA holds
+// the amplitudes of the tile's LAST round in registers the shared-memory tile is
+// dead, and the cp.async loads and phase tables of the NEXT tile are issued into
+// it before the last round's arithmetic and global stores.
+// ---------------------------------------------------------------------------
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
+              const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx)
+{
+    extern __shared__ double2 tile[];
+    const SweepProgram &P = c_prog;
+    const int T = P.T, TB = P.TB;
+    const unsigned tid = threadIdx.x;
+    const int col = blockIdx.y;
+    const unsigned long long ntiles = 1ull << P.n_outer;
+    char *const tile_b = reinterpret_cast<char *>(tile);
+    const int he_bits = TB > kThrLoBits ? TB - kThrLoBits : 0;
+    const int ntab = P.nphase << he_bits;
+    double2 *const s_hiF = tile + (1u << T);             // [2][ntab]: hi[ih] * exp(i*pi*angle(outer bits)), double-buffered
+    double2 *const s_tileF = s_hiF + 2 * ntab;           // [nphase]
+    const bool generate = P.generate != 0;
+    const bool staged_store = P.direct_store == 0;
+    const double scale = P.scale;
+    const double2 *__restrict__ const src = src_cols[col];
+    double2 *__restrict__ const dst = dst_cols[col];
+
+    // thread-constant address parts
+    const unsigned sw_tid = tile_swizzle(tid) * 16u;
+    unsigned long long soff_t = 0;
+    for (int k = 0; k < P.ld_nruns; ++k) soff_t |= (unsigned long long)(tid & P.ld_runs[k].mask) << P.ld_runs[k].shift;
+    unsigned long long doff_t = 0;
+    unsigned sw_lo = 0;
+    if (staged_store) {
+        unsigned l_lo = 0;
+        for (int k = 0; k < P.st_nruns; ++k) {
+            doff_t |= (unsigned long long)(tid & P.st_runs[k].mask) << P.st_runs[k].shift;
+            const int sh = P.st_lruns[k].shift;
+            const unsigned v = tid & P.st_lruns[k].mask;
+            l_lo |= sh >= 0 ? v << sh : v >> -sh;
+        }
+        sw_lo = tile_swizzle(l_lo) * 16u;
+    } else {
+        for (int k = 0; k < P.ds_nruns; ++k) doff_t |= run_bits(tid, P.ds_runs[k]);
+    }
+    const unsigned long long gen_g = generate ? gen_idx[col] : 0ull;
+
+    auto issue_loads = [&](unsigned long long o) {
+        const double2 *__restrict__ p = src + (outer_base(P.o_src, o, P.n_outer) | soff_t);
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw_tid ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    auto tables_phase1 = [&](unsigned long long o) {
+        for (int pid = tid; pid < P.nphase; pid += blockDim.x) {
+            const PhaseTab &pt = ptabs[pid];
+            double ang = pt.base;
+            for (int i = 0; i < P.n_outer; ++i)
+                if ((o >> i) & 1ull) ang += pt.outer_coef[i];
+            double sn, cs;
+            sincospi(ang, &sn, &cs);
+            s_tileF[pid] = make_double2(cs, sn);
+        }
+    };
+    auto tables_phase2 = [&](int buf) {
+        for (int e = tid; e < ntab; e += blockDim.x) {
+            const int pid = e >> he_bits, ih = e & ((1 << he_bits) - 1);
+            const double2 hi = __ldg(reinterpret_cast<const double2 *>(ptabs[pid].hi) + ih);
+            s_hiF[buf * ntab + e] = cmul(hi, s_tileF[pid]);
+        }
+    };
+
+    unsigned long long o = blockIdx.x;
+    if (o >= ntiles) return;
+    if (!generate) issue_loads(o);
+    tables_phase1(o);
+    __syncthreads();
+    tables_phase2(0);
+    int buf = 0;
+    for (; o < ntiles; o += gridDim.x, buf ^= 1) {
+        const unsigned long long o_next = o + gridDim.x;
+        const bool has_next = o_next < ntiles;
+        if (!generate) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                       // tile o and its tables are visible to the whole CTA
+        const double2 *const hiF = s_hiF + buf * ntab;
+        for (int r = 0; r < P.nrounds; ++r) {
+            const RoundDesc &R = P.rounds[r];
+            const bool last = r + 1 == P.nrounds;
+            unsigned thrL = 0;
+            for (int k = 0; k < R.nruns; ++k) thrL |= (unsigned)run_bits(tid, R.runs[k]);
+            const unsigned swT = tile_swizzle(thrL) * 16u;
+            if (r > 0) {
+                if (R.sync_before == 2) __syncthreads();
+                else __syncwarp();
+            }
+            double2 a[kSlots];
+            if (r == 0 && generate) {
+                // the basis element lives in exactly one tile of the grid and one slot of one thread
+                unsigned gen_slot = 0xffffffffu;
+                if ((gen_g & ~P.tile_mask_src) == outer_base(P.o_src, o, P.n_outer)) {
+                    unsigned gen_l = 0, regmask = 0, slot = 0;
+                    for (int i = 0; i < T; ++i) gen_l |= (unsigned)((gen_g >> P.tsrc[i]) & 1ull) << i;
+                    for (int j = 0; j < kRegBits; ++j) {
+                        regmask |= 1u << R.reg_tb[j];
+                        slot |= ((gen_l >> R.reg_tb[j]) & 1u) << j;
+                    }
+                    if ((gen_l & ~regmask) == thrL) gen_slot = slot;
+                }
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)gen_slot ? 1.0 : 0.0, 0.0);
+            } else {
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
+            }
+            if (last && !staged_store) {
+                if (has_next) tables_phase1(o_next);
+                __syncthreads();               // all amplitudes of the tile are in registers: the buffer is dead
+                if (has_next) {
+                    if (!generate) issue_loads(o_next);
+                    tables_phase2(buf ^ 1);
+                }
+            }
+            const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
+            switch (R.nsteps) {
+            case 1: LadderSteps<1, kRegBits - 1>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+            case 2: LadderSteps<2, kRegBits - 2>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+            case 3: LadderSteps<3, kRegBits - 3>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+#if Q1T_REG_BITS >= 5
+            case 4: LadderSteps<4, kRegBits - 4>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+            default: LadderSteps<5, kRegBits - 5>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+#else
+            default: LadderSteps<4, kRegBits - 4>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+#endif
+            }
+            if (last && !staged_store) {
+                double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | doff_t);
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) st_global_cs(q + P.ds_slot[s], make_double2(a[s].x * scale, a[s].y * scale));
+            } else {
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
+            }
+        }
+        if (staged_store) {
+            // the destination layout differs from the last round's thread layout (fused relabel):
+            // one more trip through shared memory, stores coalesced in destination order
+            __syncthreads();
+            double2 v[kSlots];
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) v[i] = *reinterpret_cast<const double2 *>(tile_b + (sw_lo ^ P.st_l_hi[i]));
+            if (has_next) tables_phase1(o_next);
+            __syncthreads();
+            if (has_next) {
+                if (!generate) issue_loads(o_next);
+                tables_phase2(buf ^ 1);
+            }
+            double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | doff_t);
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) st_global_cs(q + P.st_off_hi[i], make_double2(v[i].x * scale, v[i].y * scale));
+        }
+    }
+}
+
+// threads per CTA: 2^(T - kRegBits).  The ladder-only kernel for tiles up to 2^12 runs with several
+// CTAs per SM; everything else (op interpreter, 2^13 tiles) with one.
+constexpr int kSmallThreads = 1 << (12 - kRegBits);
+constexpr int kMaxThreads = 1 << kMaxThrBits;
+#ifndef Q1T_LADDER_MIN_CTAS
+#define Q1T_LADDER_MIN_CTAS (Q1T_REG_BITS >= 5 ? 3 : 2)
+#endif
+
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream)
 {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
-    const size_t smem = sizeof(double2) << prog.T;
+    const int he_bits = prog.TB > kThrLoBits ? prog.TB - kThrLoBits : 0;
+    const size_t smem = (sizeof(double2) << prog.T) + (sizeof(double2) * (size_t)prog.nphase << he_bits);
     static bool smem_set = false;
     if (!smem_set) {
-        e = cudaFuncSetAttribute(sweep_kernel<true, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << kMaxTileBits));
+        const int max_smem = (int)((sizeof(double2) << kMaxTileBits) + sizeof(double2) * kMaxPhase * kHiEntries);
+        e = cudaFuncSetAttribute(sweep_kernel<true, kMaxThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(sweep_kernel<false, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << kMaxTileBits));
+        e = cudaFuncSetAttribute(sweep_kernel<false, kMaxThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(sweep_kernel<false, 256, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12));
+        e = cudaFuncSetAttribute(sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * kHiEntries));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         smem_set = true;
     }
@@ -534,9 +750,37 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
     for (int r = 0; r < prog.nrounds; ++r) ladders_only = ladders_only && prog.rounds[r].kind == ROUND_PH;
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
-    if (ladders_only && prog.TB <= 8) sweep_kernel<false, 256, Q1T_LADDER_MIN_CTAS><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
-    else if (ladders_only) sweep_kernel<false, 512, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
-    else sweep_kernel<true, 512, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+    static const bool pipe = !(std::getenv("Q1T_LADDER_PIPE") && std::atoi(std::getenv("Q1T_LADDER_PIPE")) == 0);
+    if (pipe && ladders_only && prog.nrounds > 0 && (int)block.x <= kSmallThreads && !prog.dbg_skip) {
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (2 * kHiEntries + 1)));
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            ctas_per_sm = Q1T_LADDER_MIN_CTAS;
+        }
+        const size_t lsmem = (sizeof(double2) << prog.T) + sizeof(double2) * (((size_t)prog.nphase << he_bits) * 2 + prog.nphase);
+        int dev = 0, nsm = 148, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, (int)block.x, lsmem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        // persistent grid: every column gets the same share of the resident CTAs
+        unsigned long long per_col = (unsigned long long)nsm * occ / (unsigned)ncols;
+        if (per_col < 1) per_col = 1;
+        if (per_col > (1ull << prog.n_outer)) per_col = 1ull << prog.n_outer;
+        dim3 pgrid((unsigned)per_col, (unsigned)ncols, 1);
+        ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+        return cudaGetLastError();
+    }
+    if (ladders_only && (int)block.x <= kSmallThreads)
+        sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+    else if (ladders_only) sweep_kernel<false, kMaxThreads, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+    else sweep_kernel<true, kMaxThreads, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
     return cudaGetLastError();
 }
 

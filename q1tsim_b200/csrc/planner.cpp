@@ -44,7 +44,9 @@ static inline uint64_t deposit(uint64_t v, const int *positions, int nbits)
     return r;
 }
 
-// tid bit i -> target bit pos[i] (strictly ascending): group into (mask, shift) runs
+// tid bit i -> target bit pos[i]: group consecutive tid bits with equal displacement into
+// (mask, shift) runs.  Ascending pos gives shifts >= 0; the per-round thread maps and the direct
+// store may be in any order (negative shifts), which the kernels handle through run_bits()
 static int make_runs(const int *pos, int nbits, BitRun *runs)
 {
     int nr = 0;
@@ -87,6 +89,7 @@ static void setup_direct(SweepProgram &P)
 {
     P.tile_mask_src = 0;
     for (int i = 0; i < P.T; ++i) P.tile_mask_src |= 1ull << P.tsrc[i];
+    const int C = P.coalesce;
     P.direct_load = P.direct_store = 0;
     P.dl_nruns = P.ds_nruns = 0;
     for (int r = 0; r < P.nrounds; ++r) {
@@ -100,11 +103,12 @@ static void setup_direct(SweepProgram &P)
             if (warp_local) R.sync_before = 1;
         }
     }
-    if (P.nrounds == 0 || P.TB < 3) return;
+    if (P.nrounds == 0 || P.TB < C) return;
     {
         const RoundDesc &R = P.rounds[0];
         bool ok = true;
-        for (int i = 0; i < 3; ++i) ok = ok && R.thr_tb[i] == i && P.tsrc[i] == i;
+        for (int i = 0; i < C; ++i) ok = ok && R.thr_tb[i] == i && P.tsrc[i] == i;
+        for (int i = 1; i < P.TB; ++i) ok = ok && R.thr_tb[i] > R.thr_tb[i - 1];
         if (ok) {
             int pos[kMaxThrBits + 1];
             for (int i = 0; i < P.TB; ++i) pos[i] = P.tsrc[R.thr_tb[i]];
@@ -124,8 +128,7 @@ static void setup_direct(SweepProgram &P)
         int pos[kMaxThrBits + 1];
         for (int i = 0; i < P.TB; ++i) {
             pos[i] = P.tdst[R.thr_tb[i]];
-            if (i < 3 && pos[i] != i) ok = false;
-            if (i > 0 && pos[i] <= pos[i - 1]) ok = false;
+            if (i < C && pos[i] != i) ok = false;
         }
         if (ok) {
             P.ds_nruns = make_runs(pos, P.TB, P.ds_runs);
@@ -285,7 +288,8 @@ bool PendingDiag::empty() const
 // ---------------------------------------------------------------------------
 // planner
 // ---------------------------------------------------------------------------
-Planner::Planner(int n, int tile_bits) : n_(n), T_(std::min(tile_bits, n))
+Planner::Planner(int n, int tile_bits, int coalesce_bits, bool balance)
+    : n_(n), T_(std::min(tile_bits, n)), C_(std::max(1, std::min(coalesce_bits, 3))), balance_(balance)
 {
     pd_.init(n);
     open_sweep();
@@ -296,7 +300,7 @@ void Planner::open_sweep()
     tile_.clear();
     rounds_.clear();
     nops_ = nphase_ = 0;
-    for (int p = 0; p < 3 && p < n_; ++p) tile_.push_back(p);   // coalescing bits: 8 amplitudes = 128 B
+    for (int p = 0; p < C_ && p < n_; ++p) tile_.push_back(p);  // coalescing bits: 8 amplitudes = 128 B (4 = 64 B)
 }
 
 bool Planner::in_tile(int p) const { return std::find(tile_.begin(), tile_.end(), p) != tile_.end(); }
@@ -315,7 +319,12 @@ bool Planner::place_target(int t)
                 return true;
             }
         }
-        if ((int)rounds_.size() < kMaxRounds && (in_tile(t) || (int)tile_.size() < T_)) {
+        // balance: a further round whose register bits the tile can no longer supply (fewer than
+        // kRegBits free tile bits left) costs a full shared-memory round trip for a few steps; a
+        // fresh sweep takes those steps along for free if it has to come anyway
+        const bool starve = balance_ && attempt == 0 && !rounds_.empty() && !in_tile(t) &&
+                            T_ - (int)tile_.size() < kRegBits && (int)rounds_.back().regs.size() >= kRegBits;
+        if (!starve && (int)rounds_.size() < kMaxRounds && (in_tile(t) || (int)tile_.size() < T_)) {
             if (!in_tile(t)) tile_.push_back(t);
             RoundB r;
             r.regs.push_back(t);
@@ -466,6 +475,7 @@ void Planner::close_sweep()
     for (int p = 0; p < n_; ++p)
         if (!std::binary_search(tile.begin(), tile.end(), p)) outer.push_back(p);
     P.n = n_; P.T = T; P.TB = T - kRegBits; P.n_outer = n_ - T;
+    P.coalesce = std::min(C_, n_);
     P.relabel = 0;
     int tile_index[kMaxBits], outer_index[kMaxBits];
     for (int p = 0; p < kMaxBits; ++p) { tile_index[p] = -1; outer_index[p] = -1; }
@@ -496,19 +506,40 @@ void Planner::close_sweep()
     for (int r = 0; r < P.nrounds; ++r) {
         RoundB &rb = rounds_[r];
         RoundDesc &R = P.rounds[r];
-        // register bits as tile-bit indices, padded with the highest free tile bits
+        // register bits as tile-bit indices.  Slot bits kRegBits-cnt.. are the round's targets in
+        // placement order, so that a chain of (phase, Hadamard) steps is a ladder whatever the
+        // positions of its bits; the low slots are padding (the highest free tile bits), which a
+        // ladder step treats like already-processed partner bits
         std::vector<int> regs;
         for (int p : rb.regs) regs.push_back(tile_index[p]);
-        for (int tb = T - 1; tb >= 0 && (int)regs.size() < kRegBits; --tb)
-            if (std::find(regs.begin(), regs.end(), tb) == regs.end()) regs.push_back(tb);
-        std::sort(regs.begin(), regs.end());
+        {
+            std::vector<int> pads;
+            for (int tb = T - 1; tb >= 0 && (int)(regs.size() + pads.size()) < kRegBits; --tb)
+                if (std::find(regs.begin(), regs.end(), tb) == regs.end()) pads.push_back(tb);
+            regs.insert(regs.begin(), pads.begin(), pads.end());
+        }
         int slot_of_tb[kMaxTileBits + 3];
         for (int tb = 0; tb < T; ++tb) slot_of_tb[tb] = -1;
         for (int j = 0; j < kRegBits; ++j) { R.reg_tb[j] = (uint8_t)regs[j]; slot_of_tb[regs[j]] = j; }
-        // thread bits: the remaining tile bits in ascending order (tid bit i -> tile bit thr[i])
+        // thread bits: the remaining tile bits (tid bit i -> tile bit thr[i]).  The eight lanes of a
+        // quarter warp make one 128-byte shared-memory wavefront; tile_swizzle() folds tile bit b
+        // into bank-group bit b % 3, so tid bits 0..2 take the lowest tile bits with three different
+        // residues (conflict-free LDS/STS.128); the others follow in ascending order
         std::vector<int> ordered;
-        for (int tb = 0; tb < T; ++tb)
-            if (slot_of_tb[tb] < 0) ordered.push_back(tb);
+        {
+            std::vector<int> rest;
+            for (int tb = 0; tb < T; ++tb)
+                if (slot_of_tb[tb] < 0) rest.push_back(tb);
+            bool used[3] = { false, false, false };
+            for (size_t i = 0; i < rest.size() && ordered.size() < 3;) {
+                if (!used[rest[i] % 3]) {
+                    used[rest[i] % 3] = true;
+                    ordered.push_back(rest[i]);
+                    rest.erase(rest.begin() + i);
+                } else ++i;
+            }
+            ordered.insert(ordered.end(), rest.begin(), rest.end());
+        }
         int thr_index_of_tb[kMaxTileBits + 3];
         for (int tb = 0; tb < T; ++tb) thr_index_of_tb[tb] = -1;
         for (int i = 0; i < P.TB; ++i) { R.thr_tb[i] = (uint8_t)ordered[i]; thr_index_of_tb[ordered[i]] = i; }
@@ -533,7 +564,7 @@ void Planner::close_sweep()
                 P.scale *= ob.m[0];
             } else if (!ob.is_phase) {
                 op.kind = (uint8_t)ob.kind;
-                std::memcpy(op.m, ob.m, sizeof op.m);
+                std::memcpy(op.m, ob.m, sizeof ob.m);
                 for (int p = 0; p < n_; ++p) {
                     if (!((ob.cmask >> p) & 1ull)) continue;
                     if (tile_index[p] >= 0) {
@@ -588,8 +619,8 @@ void Planner::close_sweep()
                 double lo_ang[1 << kThrLoBits] = { 0 }, hi_ang[1 << (kMaxThrBits - kThrLoBits)] = { 0 };
                 pt.base = wrap_half_turns(ob.base + (ob.has_c0 ? ob.c0 : 0.0));
                 if (ob.has_c0) {
-                    op.flags |= 8u;
-                    sincospi_host(ob.c0, op.m[7], op.m[6]);
+                    op.flags |= kFlagC0;
+                    sincospi_host(ob.c0, op.m[9], op.m[8]);
                 }
                 for (const auto &pr : ob.partners) {
                     const int p = pr.first;
@@ -626,13 +657,14 @@ void Planner::close_sweep()
         R.kind = ROUND_GENERIC;
         R.nsteps = 0;
         const int cnt = nops - R.op_begin;
+        const int j0 = kRegBits - cnt;                       // first slot bit of the ladder
         bool ladder = cnt >= 1 && cnt <= kRegBits;
         for (int i = 0; ladder && i < cnt; ++i) {
             const OpDesc &op = P.ops[R.op_begin + i];
-            if (op.j != i) ladder = false;
+            if (op.j != j0 + i) ladder = false;
             else if (op.kind == OP_H_UNNORM) continue;
             else if (op.kind != OP_PHASE_H) ladder = false;
-            else if (op.flags >> i) ladder = false;          // partner among later slot bits, or a c0 term
+            else if (op.flags >> op.j) ladder = false;       // partner among later slot bits, or a c0 term
         }
         if (ladder && nphase + cnt <= kMaxPhase) {
             for (int i = 0; i < cnt; ++i) {
@@ -648,7 +680,7 @@ void Planner::close_sweep()
                     ps.ptabs.push_back(pt);
                     ++nphase;
                 }
-                for (int q = 0; q < i; ++q)
+                for (int q = 0; q < op.j; ++q)
                     if (!(op.flags & (1u << q))) { op.m[2 * q] = 1.0; op.m[2 * q + 1] = 0.0; }
             }
             R.kind = ROUND_PH;
@@ -725,8 +757,8 @@ bool can_fuse_relabel(const SweepProgram &P, const std::vector<int> &dstpos)
 {
     int found = 0;
     for (int i = 0; i < P.T; ++i)
-        if (dstpos[P.tsrc[i]] < 3) ++found;
-    return found >= (P.n < 3 ? P.n : 3);
+        if (dstpos[P.tsrc[i]] < P.coalesce) ++found;
+    return found >= (P.n < P.coalesce ? P.n : P.coalesce);
 }
 
 PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos)
@@ -751,6 +783,7 @@ PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &d
     for (int p = 0; p < n; ++p)
         if (!std::binary_search(tile.begin(), tile.end(), p)) outer.push_back(p);
     P.n = n; P.T = T; P.TB = T - kRegBits; P.n_outer = n - T;
+    P.coalesce = std::min(3, n);
     P.scale = 1.0;
     for (int i = 0; i < T; ++i) P.tsrc[i] = (uint8_t)tile[i];
     for (int i = 0; i < P.n_outer; ++i) P.osrc[i] = (uint8_t)outer[i];

@@ -61,7 +61,9 @@ struct PendingDiag {
 
 class Planner {
 public:
-    Planner(int n, int tile_bits);
+    // coalesce_bits: low index bits every tile keeps contiguous (3 = 128-byte runs, 2 = 64-byte runs)
+    // balance: close a sweep rather than open a round that the tile cannot fill with register bits
+    Planner(int n, int tile_bits, int coalesce_bits = 3, bool balance = false);
     // feed gates in program order
     void add(const LoweredGate &g);           // POLY or G1 only
     // flush everything that is pending (diagonal terms included) into sweeps
@@ -95,7 +97,8 @@ private:
         std::vector<int> regs;          // physical
         std::vector<OpB> ops;
     };
-    int n_, T_;
+    int n_, T_, C_;
+    bool balance_;
     std::vector<int> tile_;             // physical bits in the open sweep's tile
     std::vector<RoundB> rounds_;
     size_t nops_ = 0, nphase_ = 0;

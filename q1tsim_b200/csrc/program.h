@@ -13,13 +13,18 @@ namespace q1t {
 
 constexpr int kMaxBits = 40;        // index bits of one column (one GPU's shard)
 constexpr int kMaxTileBits = 13;    // 2^13 * 16 B = 128 KiB of shared memory
-constexpr int kRegBits = 4;         // amplitudes per thread = 16
+#ifndef Q1T_REG_BITS
+#define Q1T_REG_BITS 5
+#endif
+constexpr int kRegBits = Q1T_REG_BITS;   // amplitudes per thread = 2^kRegBits (4 or 5)
+static_assert(Q1T_REG_BITS == 4 || Q1T_REG_BITS == 5, "4 or 5 register bits");
 constexpr int kSlots = 1 << kRegBits;
-constexpr int kMaxThrBits = kMaxTileBits - kRegBits;   // 9 -> 512 threads
+constexpr int kMaxThrBits = kMaxTileBits - kRegBits;   // 9 -> 512 threads (8 -> 256 with 5 register bits)
 constexpr int kMaxRounds = 24;
 constexpr int kMaxOps = 96;
 constexpr int kMaxPhase = 48;
 constexpr int kThrLoBits = 4;       // per-thread phase factor = lo[tid & 15] * hi[tid >> 4]
+constexpr int kHiEntries = 1 << (kMaxThrBits - kThrLoBits);
 constexpr int kMaxRuns = 9;         // bit-deposit runs (mask, shift) of a thread index
 constexpr int kOuterChunkBits = 6;  // outer tile index -> address via 6-bit lookup tables
 constexpr int kOuterChunks = 5;
@@ -38,14 +43,15 @@ enum OpKind : uint8_t {
 
 enum RoundKind : uint8_t { ROUND_GENERIC = 0, ROUND_PH = 1 };
 
-struct OpDesc {          // 96 bytes
+constexpr uint8_t kFlagC0 = 0x80;
+struct OpDesc {          // 112 bytes
     uint8_t kind;
     uint8_t j;           // slot bit
-    uint8_t flags;       // PHASE: bit0..2 = partner q[i] is non-unit, bit3 = has c0 factor
+    uint8_t flags;       // PHASE: bit0..kRegBits-2 = partner q[i] is non-unit, kFlagC0 = has c0 factor
     uint8_t pad0;
     uint32_t cslot;      // G1: slot bits that must be 1 (controls that are register bits)
     uint64_t cmask;      // G1: virtual-index bits (outer<<T | tile-local) that must be 1, register bits excluded
-    double m[8];         // G1: m00,m01,m10,m11 (re,im).  PHASE: q[0..2] partner factors (other slot bits ascending), m[6..7] = c0 factor
+    double m[10];        // G1: m00,m01,m10,m11 (re,im).  PHASE: q[0..kRegBits-2] partner factors (other slot bits ascending), m[8..9] = c0 factor
     uint32_t phase_id;   // PHASE: row of the phase tables
     uint32_t pad1;
     uint64_t pad2;
@@ -84,7 +90,7 @@ struct SweepProgram {
     int32_t dl_nruns, ds_nruns;
     uint64_t tile_mask_src;   // source positions of the tile bits
     int32_t dbg_skip;         // timing experiments only: bit0 = skip loads, bit1 = skip stores (results are wrong)
-    int32_t pad_dbg;
+    int32_t coalesce;         // low index bits kept contiguous in every tile (3 = 128 B, 2 = 64 B)
     double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];
