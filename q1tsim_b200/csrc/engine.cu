@@ -416,6 +416,14 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     bool ident = true;
     for (int l = 0; l < n_; ++l)
         if (perm_[l] != l) ident = false;
+    // the deferred Hadamard normalisations of the whole batch are applied once: for free in the
+    // generated basis element, otherwise at the store of the last sweep
+    {
+        double total = 1.0;
+        for (PlannedSweep &ps : sweeps) { total *= ps.prog.scale; ps.prog.scale = 1.0; ps.prog.gen_scale = 1.0; }
+        if (generate) sweeps.front().prog.gen_scale = total;
+        else sweeps.back().prog.scale = total;
+    }
     for (size_t si = 0; si < sweeps.size(); ++si) {
         PlannedSweep &ps = sweeps[si];
         if (!ps.ptabs.empty())

@@ -237,7 +237,7 @@ __device__ __forceinline__ void round_load(double2 (&a)[kSlots], const RoundIO &
         for (int s = 0; s < kSlots; ++s) a[s] = make_double2(1.0 + s, (double)threadIdx.x);
     } else if (io.zero_fill) {
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)io.gen_slot ? 1.0 : 0.0, 0.0);
+        for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)io.gen_slot ? P.gen_scale : 0.0, 0.0);
     } else {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(io.tile_b + (io.swT ^ R.sw_slot[s]));
@@ -289,22 +289,25 @@ struct LadderStep<J, -1> {
     }
 };
 
-template <int NS, int J>
+template <int NS, int J, bool LO_SHARED = false>
 struct LadderSteps {
     static __device__ __forceinline__ void run(double2 (&a)[kSlots], const RoundDesc &R, const SweepProgram &P,
-                                               const PhaseTab *__restrict__ ptabs, const double2 *s_hiF, int he_bits, unsigned il, unsigned ih)
+                                               const PhaseTab *__restrict__ ptabs, const double2 *s_hiF, int he_bits, unsigned il, unsigned ih,
+                                               const double2 *s_lo = nullptr)
     {
         const OpDesc &op = P.ops[R.op_begin + J - (kRegBits - NS)];
-        const double2 lo = __ldg(reinterpret_cast<const double2 *>(ptabs[op.phase_id].lo) + il);
+        const double2 lo = LO_SHARED ? s_lo[(op.phase_id << kThrLoBits) + il]
+                                     : __ldg(reinterpret_cast<const double2 *>(ptabs[op.phase_id].lo) + il);
         const double2 hi = s_hiF[(op.phase_id << he_bits) + ih];          // hi[ih] * tile factor
         LadderStep<J, J - 1>::run(a, op, cmul(lo, hi), 0);
-        LadderSteps<NS, J + 1>::run(a, R, P, ptabs, s_hiF, he_bits, il, ih);
+        LadderSteps<NS, J + 1, LO_SHARED>::run(a, R, P, ptabs, s_hiF, he_bits, il, ih, s_lo);
     }
 };
-template <int NS>
-struct LadderSteps<NS, kRegBits> {
+template <int NS, bool LO_SHARED>
+struct LadderSteps<NS, kRegBits, LO_SHARED> {
     static __device__ __forceinline__ void run(double2 (&)[kSlots], const RoundDesc &, const SweepProgram &,
-                                               const PhaseTab *__restrict__, const double2 *, int, unsigned, unsigned) {}
+                                               const PhaseTab *__restrict__, const double2 *, int, unsigned, unsigned,
+                                               const double2 * = nullptr) {}
 };
 
 template <int NS>
@@ -432,7 +435,7 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
         if (!P.generate) cp_async_commit_wait_all();
         else {
             __syncthreads();
-            if (tid == 0 && gen_l != 0xffffffffu) tile[tile_swizzle(gen_l)] = make_double2(1.0, 0.0);
+            if (tid == 0 && gen_l != 0xffffffffu) tile[tile_swizzle(gen_l)] = make_double2(P.gen_scale, 0.0);
         }
     }
     __syncthreads();
@@ -574,6 +577,13 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     const int ntab = P.nphase << he_bits;
     double2 *const s_hiF = tile + (1u << T);             // [2][ntab]: hi[ih] * exp(i*pi*angle(outer bits)), double-buffered
     double2 *const s_tileF = s_hiF + 2 * ntab;           // [nphase]
+    double2 *const s_lo = s_tileF + P.nphase;            // [nphase][16]  copies of the PhaseTab rows: the CTA is
+    double2 *const s_hi = s_lo + (P.nphase << kThrLoBits);   // [ntab]    persistent, global memory is read once
+    double *const s_coef = reinterpret_cast<double *>(s_hi + ntab);   // [nphase][n_outer + 1], last = base
+    const int ncoef = P.n_outer + 1;
+    // per-thread source / destination offsets: kept in shared memory, not in registers -- with 32
+    // amplitudes per thread the compiler spilled them, and a local-memory reload is an L2 round trip
+    unsigned long long *const s_off = reinterpret_cast<unsigned long long *>(s_coef + ((P.nphase * ncoef + 1) & ~1));
     const bool generate = P.generate != 0;
     const bool staged_store = P.direct_store == 0;
     const double scale = P.scale;
@@ -599,35 +609,65 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         for (int k = 0; k < P.ds_nruns; ++k) doff_t |= run_bits(tid, P.ds_runs[k]);
     }
     const unsigned long long gen_g = generate ? gen_idx[col] : 0ull;
+    s_off[2 * tid] = soff_t;            // only ever read back by the same thread
+    s_off[2 * tid + 1] = doff_t;
 
     auto issue_loads = [&](unsigned long long o) {
-        const double2 *__restrict__ p = src + (outer_base(P.o_src, o, P.n_outer) | soff_t);
+        const double2 *__restrict__ p = src + (outer_base(P.o_src, o, P.n_outer) | s_off[2 * tid]);
+        unsigned sw = sw_tid;
+        asm volatile("" : "+r"(sw));      // keeps the 32 destination addresses from being hoisted out of the tile loop (and spilled)
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw_tid ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+        for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
         asm volatile("cp.async.commit_group;\n" ::);
     };
+    // phase 1: angle of every phase op for tile o.  One warp per op, lanes over the outer bits,
+    // butterfly sum; then one sincospi per lane.  (All warps take part: a single warp doing this
+    // alone kept the other three waiting at the barrier.)
     auto tables_phase1 = [&](unsigned long long o) {
-        for (int pid = tid; pid < P.nphase; pid += blockDim.x) {
-            const PhaseTab &pt = ptabs[pid];
-            double ang = pt.base;
-            for (int i = 0; i < P.n_outer; ++i)
-                if ((o >> i) & 1ull) ang += pt.outer_coef[i];
+        if (blockDim.x < 32) {                 // tiny tiles (n < 10): no full warp, plain loop
+            for (int pid = tid; pid < P.nphase; pid += blockDim.x) {
+                double ang = s_coef[pid * ncoef + P.n_outer];
+                for (int i = 0; i < P.n_outer; ++i)
+                    if ((o >> i) & 1ull) ang += s_coef[pid * ncoef + i];
+                double sn, cs;
+                sincospi(ang, &sn, &cs);
+                s_tileF[pid] = make_double2(cs, sn);
+            }
+            return;
+        }
+        const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+        double mine = 0.0;
+        int k = 0;
+        for (int pid = warp; pid < P.nphase; pid += nwarps, ++k) {
+            double part = lane == 0 ? s_coef[pid * ncoef + P.n_outer] : 0.0;
+            for (int i = lane; i < P.n_outer; i += 32)
+                if ((o >> i) & 1ull) part += s_coef[pid * ncoef + i];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (lane == k) mine = part;
+        }
+        if (lane < k) {
             double sn, cs;
-            sincospi(ang, &sn, &cs);
-            s_tileF[pid] = make_double2(cs, sn);
+            sincospi(mine, &sn, &cs);
+            s_tileF[warp + lane * nwarps] = make_double2(cs, sn);
         }
     };
     auto tables_phase2 = [&](int buf) {
-        for (int e = tid; e < ntab; e += blockDim.x) {
-            const int pid = e >> he_bits, ih = e & ((1 << he_bits) - 1);
-            const double2 hi = __ldg(reinterpret_cast<const double2 *>(ptabs[pid].hi) + ih);
-            s_hiF[buf * ntab + e] = cmul(hi, s_tileF[pid]);
-        }
+        for (int e = tid; e < ntab; e += blockDim.x) s_hiF[buf * ntab + e] = cmul(s_hi[e], s_tileF[e >> he_bits]);
     };
 
     unsigned long long o = blockIdx.x;
     if (o >= ntiles) return;
     if (!generate) issue_loads(o);
+    for (int e = tid; e < (P.nphase << kThrLoBits); e += blockDim.x)
+        s_lo[e] = __ldg(reinterpret_cast<const double2 *>(ptabs[e >> kThrLoBits].lo) + (e & ((1 << kThrLoBits) - 1)));
+    for (int e = tid; e < ntab; e += blockDim.x)
+        s_hi[e] = __ldg(reinterpret_cast<const double2 *>(ptabs[e >> he_bits].hi) + (e & ((1 << he_bits) - 1)));
+    for (int e = tid; e < P.nphase * ncoef; e += blockDim.x) {
+        const int pid = e / ncoef, i = e - pid * ncoef;
+        s_coef[e] = i < P.n_outer ? ptabs[pid].outer_coef[i] : ptabs[pid].base;
+    }
+    __syncthreads();
     tables_phase1(o);
     __syncthreads();
     tables_phase2(0);
@@ -662,7 +702,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                     if ((gen_l & ~regmask) == thrL) gen_slot = slot;
                 }
 #pragma unroll
-                for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)gen_slot ? 1.0 : 0.0, 0.0);
+                for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)gen_slot ? P.gen_scale : 0.0, 0.0);
             } else {
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
@@ -677,20 +717,24 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             }
             const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
             switch (R.nsteps) {
-            case 1: LadderSteps<1, kRegBits - 1>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
-            case 2: LadderSteps<2, kRegBits - 2>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
-            case 3: LadderSteps<3, kRegBits - 3>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+            case 1: LadderSteps<1, kRegBits - 1, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
+            case 2: LadderSteps<2, kRegBits - 2, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
+            case 3: LadderSteps<3, kRegBits - 3, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
 #if Q1T_REG_BITS >= 5
-            case 4: LadderSteps<4, kRegBits - 4>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
-            default: LadderSteps<5, kRegBits - 5>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+            case 4: LadderSteps<4, kRegBits - 4, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
+            default: LadderSteps<5, kRegBits - 5, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
 #else
-            default: LadderSteps<4, kRegBits - 4>::run(a, R, P, ptabs, hiF, he_bits, il, ih); break;
+            default: LadderSteps<4, kRegBits - 4, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
 #endif
             }
             if (last && !staged_store) {
-                double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | doff_t);
+                double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
+                if (scale != 1.0) {
 #pragma unroll
-                for (int s = 0; s < kSlots; ++s) st_global_cs(q + P.ds_slot[s], make_double2(a[s].x * scale, a[s].y * scale));
+                    for (int s = 0; s < kSlots; ++s) a[s] = make_double2(a[s].x * scale, a[s].y * scale);
+                }
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) st_global_cs(q + P.ds_slot[s], a[s]);
             } else {
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
@@ -700,18 +744,31 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             // the destination layout differs from the last round's thread layout (fused relabel):
             // one more trip through shared memory, stores coalesced in destination order
             __syncthreads();
-            double2 v[kSlots];
+            double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
+            unsigned swl = sw_lo;
+            asm volatile("" : "+r"(swl));     // as in issue_loads: no hoisting of the 32 addresses
+            {   // first half: read and store right away
+                double2 v[kSlots / 2];
 #pragma unroll
-            for (int i = 0; i < kSlots; ++i) v[i] = *reinterpret_cast<const double2 *>(tile_b + (sw_lo ^ P.st_l_hi[i]));
-            if (has_next) tables_phase1(o_next);
-            __syncthreads();
-            if (has_next) {
-                if (!generate) issue_loads(o_next);
-                tables_phase2(buf ^ 1);
+                for (int i = 0; i < kSlots / 2; ++i) v[i] = *reinterpret_cast<const double2 *>(tile_b + (swl ^ P.st_l_hi[i]));
+#pragma unroll
+                for (int i = 0; i < kSlots / 2; ++i)
+                    st_global_cs(q + P.st_off_hi[i], scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i]);
             }
-            double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | doff_t);
+            {   // second half: once it is in registers the tile is dead -> prefetch, then store
+                double2 v[kSlots / 2];
 #pragma unroll
-            for (int i = 0; i < kSlots; ++i) st_global_cs(q + P.st_off_hi[i], make_double2(v[i].x * scale, v[i].y * scale));
+                for (int i = 0; i < kSlots / 2; ++i) v[i] = *reinterpret_cast<const double2 *>(tile_b + (swl ^ P.st_l_hi[kSlots / 2 + i]));
+                if (has_next) tables_phase1(o_next);
+                __syncthreads();
+                if (has_next) {
+                    if (!generate) issue_loads(o_next);
+                    tables_phase2(buf ^ 1);
+                }
+#pragma unroll
+                for (int i = 0; i < kSlots / 2; ++i)
+                    st_global_cs(q + P.st_off_hi[kSlots / 2 + i], scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i]);
+            }
         }
     }
 }
@@ -755,14 +812,16 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         static int ctas_per_sm = 0;
         if (!ctas_per_sm) {
             e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (2 * kHiEntries + 1)));
+                                     (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (3 * kHiEntries + 1 + (1 << kThrLoBits)) + sizeof(double) * kMaxPhase * (kMaxBits + 1) + 16 * kSmallThreads + 16));
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
             ctas_per_sm = Q1T_LADDER_MIN_CTAS;
         }
-        const size_t lsmem = (sizeof(double2) << prog.T) + sizeof(double2) * (((size_t)prog.nphase << he_bits) * 2 + prog.nphase);
+        const size_t lsmem = (sizeof(double2) << prog.T) +
+                             sizeof(double2) * (((size_t)prog.nphase << he_bits) * 3 + prog.nphase + ((size_t)prog.nphase << kThrLoBits)) +
+                             sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x;
         int dev = 0, nsm = 148, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

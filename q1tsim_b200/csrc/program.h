@@ -92,6 +92,7 @@ struct SweepProgram {
     int32_t dbg_skip;         // timing experiments only: bit0 = skip loads, bit1 = skip stores (results are wrong)
     int32_t coalesce;         // low index bits kept contiguous in every tile (3 = 128 B, 2 = 64 B)
     double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
+    double gen_scale;     // value of the basis element of a generated input (1, or the normalisation of the whole batch of sweeps)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];
     uint8_t osrc[kMaxBits], odst[kMaxBits];
