@@ -98,6 +98,7 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
     // A/B switches for whole-process experiments (bench.py, tools/): same as set_option()
     if (const char *e = std::getenv("Q1T_COALESCE_BITS")) { const long v = std::atol(e); if (v == 2 || v == 3) coalesce_bits_ = v; }
     if (const char *e = std::getenv("Q1T_BALANCE")) balance_ = std::atol(e);
+    if (const char *e = std::getenv("Q1T_TRACK_SUPPORT")) track_support_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
 }
 
@@ -299,12 +300,19 @@ int DeviceVectorState::lower_and_queue(const double *mat, size_t dim, const size
         return fail(e.find("duplicate") != std::string::npos ? Q1T_ERR_INVALID_ARGUMENT : Q1T_ERR_UNSUPPORTED, e);
     stats.gates_queued++;
     if (lg.kind == LoweredGate::POLY && lg.nb == 0) return Q1T_OK;          // identity
-    if (lg.kind == LoweredGate::SWAP && n_ >= 5 && fuse_) {
+    if (lg.kind == LoweredGate::SWAP && n_ >= 5 && fuse_ && !no_relabel_) {
         // zero-byte relabel: exchange the physical homes of the two logical bits
+        int la = -1, lb = -1;
         for (int l = 0; l < n_; ++l) {
-            if (perm_[l] == lg.b[0]) perm_[l] = lg.b[1];
-            else if (perm_[l] == lg.b[1]) perm_[l] = lg.b[0];
+            if (perm_[l] == lg.b[0]) { perm_[l] = lg.b[1]; la = l; }
+            else if (perm_[l] == lg.b[1]) { perm_[l] = lg.b[0]; lb = l; }
         }
+        // a lazy basis column is kept as a LOGICAL index: Swap|idx> exchanges the two bits there,
+        // which leaves its physical position (what the queued gates will act on) unchanged
+        if (la >= 0 && lb >= 0)
+            for (Column &c : cols_)
+                if (c.basis && c.basis_idx != UINT64_MAX && (((c.basis_idx >> la) ^ (c.basis_idx >> lb)) & 1ull))
+                    c.basis_idx ^= (1ull << la) | (1ull << lb);
         return Q1T_OK;
     }
     queue_.push_back(lg);
@@ -424,17 +432,56 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
         if (generate) sweeps.front().prog.gen_scale = total;
         else sweeps.back().prog.scale = total;
     }
-    for (size_t si = 0; si < sweeps.size(); ++si) {
-        PlannedSweep &ps = sweeps[si];
-        if (!ps.ptabs.empty())
-            CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
-        ps.prog.generate = (generate && si == 0) ? 1 : 0;
+    for (PlannedSweep &ps : sweeps) {
         ps.prog.prefetch_ahead = (int)prefetch_ahead_;
         ps.prog.dbg_skip = (int)dbg_skip_;
         if (!direct_) {                       // A/B switch: always stage through shared memory, CTA-wide barriers
             ps.prog.direct_load = ps.prog.direct_store = 0;
             for (int r = 0; r < ps.prog.nrounds; ++r) ps.prog.rounds[r].sync_before = 2;
         }
+    }
+    // Support tracking.  A batch that starts from basis states |idx> (every circuit does: VectorState::new,
+    // vectorstate.rs:41-53) knows that an amplitude is zero unless its index agrees with idx in every bit
+    // no non-diagonal gate has touched yet.  Sweeps read, compute and write only what lies inside that
+    // support; the last sweep of the batch writes the remaining tiles as zeros, so the columns leave dense.
+    bool track = generate && track_support_;
+    for (unsigned long long g : gen) track = track && g != ~0ull;
+    for (const PlannedSweep &ps : sweeps) track = track && sweep_uses_ladder_kernel(ps.prog);
+    uint64_t pinned = n_ >= 64 ? ~0ull : ((1ull << n_) - 1ull);
+    std::vector<uint64_t> bytes_moved(sweeps.size());
+    for (size_t si = 0; si < sweeps.size(); ++si) {
+        SweepProgram &P = sweeps[si].prog;
+        const bool last = si + 1 == sweeps.size();
+        const bool gen_here = generate && si == 0;
+        P.sup_mask = 0;
+        P.sup_mode = 0;
+        for (int r = 0; r < P.nrounds; ++r) P.rounds[r].zmask = 0;
+        bytes_moved[si] = (gen_here ? 16ull : 32ull) << n_;
+        if (!track || pinned == 0) continue;
+        P.sup_mask = pinned;
+        P.sup_mode = last ? 2 : 1;
+        uint32_t pinned_tl = 0;                         // pinned tile bits, tile-local
+        for (int i = 0; i < P.T; ++i)
+            if ((pinned >> P.tsrc[i]) & 1ull) pinned_tl |= 1u << i;
+        for (int r = 0; r < P.nrounds; ++r) {
+            RoundDesc &R = P.rounds[r];
+            uint32_t regs = 0;
+            for (int j = 0; j < kRegBits; ++j) regs |= 1u << R.reg_tb[j];
+            R.zmask = pinned_tl & ~regs;
+            for (int j = kRegBits - R.nsteps; j < kRegBits; ++j) pinned_tl &= ~(1u << R.reg_tb[j]);   // this round's targets
+        }
+        int pinned_outer = 0, pinned_all = 0;
+        for (int i = 0; i < P.n_outer; ++i) pinned_outer += (int)((pinned >> P.osrc[i]) & 1ull);
+        for (int b = 0; b < n_; ++b) pinned_all += (int)((pinned >> b) & 1ull);
+        const uint64_t tiles_written = last ? (1ull << P.n_outer) : (1ull << (P.n_outer - pinned_outer));
+        bytes_moved[si] = ((tiles_written << P.T) + (gen_here ? 0ull : (1ull << (n_ - pinned_all)))) * 16ull;
+        pinned &= ~sweeps[si].touched;
+    }
+    for (size_t si = 0; si < sweeps.size(); ++si) {
+        PlannedSweep &ps = sweeps[si];
+        if (!ps.ptabs.empty())
+            CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
+        ps.prog.generate = (generate && si == 0) ? 1 : 0;
         const bool last = si + 1 == sweeps.size();
         bool relabel = false;
         if (last && final_relabel && !ident && which.size() == cols_.size()) {
@@ -452,7 +499,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             stats.kernel_launches++;
             stats.sweeps++;
             stats.sweep_column_passes += which.size();
-            stats.sweep_bytes += (uint64_t)which.size() * ((ps.prog.generate ? 16ull : 32ull) << n_);
+            stats.sweep_bytes += (uint64_t)which.size() * bytes_moved[si];
             continue;
         }
         // out-of-place: one column at a time through a scratch buffer
@@ -474,7 +521,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
         stats.sweeps++;
         stats.fused_relabels++;
         stats.sweep_column_passes += which.size();
-        stats.sweep_bytes += (uint64_t)which.size() * ((ps.prog.generate ? 16ull : 32ull) << n_);
+        stats.sweep_bytes += (uint64_t)which.size() * bytes_moved[si];
         for (int l = 0; l < n_; ++l) perm_[l] = l;
     }
     sweeps.clear();
@@ -690,9 +737,11 @@ int DeviceVectorState::apply_conditional_gate(const uint8_t *control, size_t nco
         if (c.buf) release_column(c.buf);     // columns that had no shots
     cols_.swap(nc);
     if (flagged.empty()) return Q1T_OK;
+    no_relabel_ = true;                       // a Swap on a subset of the columns cannot be a (global) relabel
     rc = lower_and_queue(mat, dim, bits, k, desc);
+    no_relabel_ = false;
     if (rc) return rc;
-    if (queue_.empty()) return Q1T_OK;        // identity or relabel-only
+    if (queue_.empty()) return Q1T_OK;        // identity
     queue_cols_ = flagged;
     return run_queue();
 }
@@ -1256,6 +1305,10 @@ int DeviceVectorState::set_option(const char *key, long value)
         int rc = run_queue();
         if (rc) return rc;
         balance_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "track_support")) {
+        track_support_ = value != 0;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "dbg_skip")) {

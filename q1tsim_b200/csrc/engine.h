@@ -79,11 +79,13 @@ private:
     std::string err_;
     long tile_bits_ = 12;
     long coalesce_bits_ = 3;                 // low index bits kept contiguous per tile (3 = 128 B, 2 = 64 B)
+    bool track_support_ = true;              // skip what is known to be zero while a batch starts from basis states
     long balance_ = -1;                      // sweep packing: -1 try both, 0 greedy, 1 balanced
     long prefetch_ahead_ = 0;
     bool direct_ = true;
     long dbg_skip_ = 0;
     bool fuse_ = true;
+    bool no_relabel_ = false;                // conditional gates: Swap must move data, not relabel
 
     // device scratch
     double2 **d_colptrs_ = nullptr; size_t colptrs_cap_ = 0;

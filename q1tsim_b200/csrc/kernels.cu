@@ -608,16 +608,60 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     } else {
         for (int k = 0; k < P.ds_nruns; ++k) doff_t |= run_bits(tid, P.ds_runs[k]);
     }
-    const unsigned long long gen_g = generate ? gen_idx[col] : 0ull;
+    // support tracking: amplitudes that differ from the basis index in a bit of sup_mask are zero
+    const int sup_mode = P.sup_mode;
+    const unsigned long long sup_g = (generate || sup_mode) ? gen_idx[col] : 0ull;
+    const unsigned long long gen_g = sup_g;
+    const unsigned long long sup_mo = sup_mode ? (P.sup_mask & ~P.tile_mask_src) : 0ull;   // pinned outer bits
+    unsigned sup_mt = 0, sup_vt = 0;                                                     // pinned tile bits (tile-local)
+    if (sup_mode) {
+        for (int i = 0; i < T; ++i) {
+            sup_mt |= (unsigned)((P.sup_mask >> P.tsrc[i]) & 1ull) << i;
+            sup_vt |= (unsigned)((sup_g >> P.tsrc[i]) & 1ull) << i;
+        }
+        sup_vt &= sup_mt;
+    }
     s_off[2 * tid] = soff_t;            // only ever read back by the same thread
     s_off[2 * tid + 1] = doff_t;
+    auto in_support = [&](unsigned long long o) {
+        return ((outer_base(P.o_src, o, P.n_outer) ^ sup_g) & sup_mo) == 0ull;
+    };
+    auto write_zero_tile = [&](unsigned long long o) {
+        double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
+        const double2 z = make_double2(0.0, 0.0);
+        if (staged_store) {
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) st_global_cs(q + P.st_off_hi[i], z);
+        } else {
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) st_global_cs(q + P.ds_slot[s], z);
+        }
+    };
+    // next tile of this CTA that holds data; tiles passed on the way are zero-filled in mode 2
+    auto advance = [&](unsigned long long o) {
+        for (o += gridDim.x; o < ntiles; o += gridDim.x) {
+            if (!sup_mo || in_support(o)) break;
+            if (sup_mode == 2) write_zero_tile(o);
+        }
+        return o;
+    };
 
     auto issue_loads = [&](unsigned long long o) {
         const double2 *__restrict__ p = src + (outer_base(P.o_src, o, P.n_outer) | s_off[2 * tid]);
         unsigned sw = sw_tid;
         asm volatile("" : "+r"(sw));      // keeps the 32 destination addresses from being hoisted out of the tile loop (and spilled)
+        if (sup_mt == 0u) {
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+            for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+        } else {
+            // only the elements inside the support exist in memory; the rest of the tile is zero
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                const unsigned e = tid | ((unsigned)i << TB);
+                if (((e ^ sup_vt) & sup_mt) == 0u) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+                else *reinterpret_cast<double2 *>(tile_b + (sw ^ P.ld_sw_hi[i])) = make_double2(0.0, 0.0);
+            }
+        }
         asm volatile("cp.async.commit_group;\n" ::);
     };
     // phase 1: angle of every phase op for tile o.  One warp per op, lanes over the outer bits,
@@ -658,6 +702,11 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
 
     unsigned long long o = blockIdx.x;
     if (o >= ntiles) return;
+    if (sup_mo && !in_support(o)) {
+        if (sup_mode == 2) write_zero_tile(o);
+        o = advance(o);
+        if (o >= ntiles) return;
+    }
     if (!generate) issue_loads(o);
     for (int e = tid; e < (P.nphase << kThrLoBits); e += blockDim.x)
         s_lo[e] = __ldg(reinterpret_cast<const double2 *>(ptabs[e >> kThrLoBits].lo) + (e & ((1 << kThrLoBits) - 1)));
@@ -672,8 +721,9 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     __syncthreads();
     tables_phase2(0);
     int buf = 0;
-    for (; o < ntiles; o += gridDim.x, buf ^= 1) {
-        const unsigned long long o_next = o + gridDim.x;
+    unsigned long long o_next = 0;
+    for (; o < ntiles; o = o_next, buf ^= 1) {
+        o_next = advance(o);
         const bool has_next = o_next < ntiles;
         if (!generate) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();                       // tile o and its tables are visible to the whole CTA
@@ -716,6 +766,9 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 }
             }
             const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
+            // a thread that differs from the basis index in a still-pinned thread bit holds only zeros
+            const bool all_zero = ((thrL ^ sup_vt) & R.zmask) != 0u;
+            if (!all_zero)
             switch (R.nsteps) {
             case 1: LadderSteps<1, kRegBits - 1, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
             case 2: LadderSteps<2, kRegBits - 2, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
@@ -781,6 +834,15 @@ constexpr int kMaxThreads = 1 << kMaxThrBits;
 #define Q1T_LADDER_MIN_CTAS (Q1T_REG_BITS >= 5 ? 3 : 2)
 #endif
 
+bool sweep_uses_ladder_kernel(const SweepProgram &prog)
+{
+    static const bool pipe = !(std::getenv("Q1T_LADDER_PIPE") && std::atoi(std::getenv("Q1T_LADDER_PIPE")) == 0);
+    if (!pipe || prog.nrounds <= 0 || (1 << prog.TB) > kSmallThreads || prog.dbg_skip) return false;
+    for (int r = 0; r < prog.nrounds; ++r)
+        if (prog.rounds[r].kind != ROUND_PH) return false;
+    return true;
+}
+
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream)
 {
@@ -807,8 +869,7 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
     for (int r = 0; r < prog.nrounds; ++r) ladders_only = ladders_only && prog.rounds[r].kind == ROUND_PH;
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
-    static const bool pipe = !(std::getenv("Q1T_LADDER_PIPE") && std::atoi(std::getenv("Q1T_LADDER_PIPE")) == 0);
-    if (pipe && ladders_only && prog.nrounds > 0 && (int)block.x <= kSmallThreads && !prog.dbg_skip) {
+    if (sweep_uses_ladder_kernel(prog)) {
         static int ctas_per_sm = 0;
         if (!ctas_per_sm) {
             e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -19,6 +19,9 @@ struct GenericGateArgs {
 
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream);
+// true if launch_sweep() runs this program in the persistent ladder kernel (the one that honours
+// SweepProgram::sup_mask / sup_mode)
+bool sweep_uses_ladder_kernel(const SweepProgram &prog);
 cudaError_t launch_generic_gate(double2 *const *d_cols, int ncols, int n, int k, const GenericGateArgs &g,
                                 const double2 *d_mat, cudaStream_t stream);
 cudaError_t launch_leaf_totals(const double2 *const *d_cols, int ncols, double *d_leaf, int n,

@@ -557,6 +557,7 @@ void Planner::close_sweep()
             std::memset(&op, 0, sizeof op);
             const int j = slot_of_tb[tile_index[ob.target]];
             op.j = (uint8_t)j;
+            if (!ob.is_phase) ps.touched |= 1ull << ob.target;
             const bool plain_h = !ob.is_phase && ob.kind == OP_G1_HADAMARD && ob.cmask == 0;
             if (plain_h) {
                 // uncontrolled Hadamard: butterfly only, c = 1/sqrt(2) deferred to the store
@@ -610,6 +611,7 @@ void Planner::close_sweep()
                     if (!nx.is_phase && nx.kind == OP_G1_HADAMARD && nx.cmask == 0 && nx.target == ob.target) {
                         op.kind = OP_PHASE_H;       // phase then butterfly on the same bit, fused
                         P.scale *= nx.m[0];
+                        ps.touched |= 1ull << nx.target;
                         ++oi;
                     }
                 }

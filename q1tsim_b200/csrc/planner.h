@@ -40,6 +40,7 @@ struct PlannedSweep {
     SweepProgram prog;
     std::vector<PhaseTab> ptabs;
     bool is_permute = false;
+    uint64_t touched = 0;        // physical bits acted on by non-diagonal gates (these lose a pinned basis value)
 };
 
 struct PlanStats {

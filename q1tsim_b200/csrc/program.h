@@ -70,6 +70,9 @@ struct RoundDesc {
     uint8_t nsteps;                 // ROUND_PH: ops op_begin..op_begin+nsteps-1 act on slot bits 0..nsteps-1
     uint8_t sync_before;            // 0 none, 1 __syncwarp (data only moves inside warps), 2 __syncthreads
     uint8_t pad1[3];
+    uint32_t zmask;                 // support tracking: tile-local bits that are thread bits of this round and still
+                                    // pinned to the basis value -> a thread that differs there holds only zeros
+    uint32_t pad2;
     BitRun runs[kMaxRuns];          // tid -> tile-local index of the thread
     uint32_t sw_slot[kSlots];       // byte offset (swizzled index * 16) contributed by slot s
     uint16_t op_begin, op_end;
@@ -92,6 +95,13 @@ struct SweepProgram {
     int32_t dbg_skip;         // timing experiments only: bit0 = skip loads, bit1 = skip stores (results are wrong)
     int32_t coalesce;         // low index bits kept contiguous in every tile (3 = 128 B, 2 = 64 B)
     double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
+    // Support tracking (ladder kernel): every amplitude whose index differs from the column's basis
+    // index gen_idx[col] in a bit of sup_mask (source positions) is zero and NOT read.  sup_mode 1:
+    // tiles outside the support are skipped altogether; 2: they are written as zeros (last sweep of
+    // a batch: the column leaves dense); 0: no tracking.
+    uint64_t sup_mask;
+    int32_t sup_mode;
+    int32_t pad_sup;
     double gen_scale;     // value of the basis element of a generated input (1, or the normalisation of the whole batch of sweeps)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];

@@ -361,3 +361,92 @@ def test_tile_sizes(tile_bits):
         m = O.gate_matrix(op[1], op[2])
         e.apply_gate(m, op[3], op[1]); o.apply_gate(m, op[3])
     assert rel_l2(e.column(0), o.column(0)) < TOL
+
+
+def _ladder_ops(n, targets, partners_per_target=None):
+    """H on `targets` (in order), each preceded by controlled phases from every earlier-touched or
+    arbitrary other qubit: a QFT-like ladder restricted to a subset of the qubits."""
+    ops = []
+    done = []
+    for t in targets:
+        for d, c in enumerate(done[::-1][:6]):
+            ops.append(("gate", "cu1", (math.pi / (1 << (d + 1)),), [c, t]))
+        for c in (partners_per_target or {}).get(t, []):
+            ops.append(("gate", "cu1", (0.37 * (c + 1),), [c, t]))
+        ops.append(("gate", "h", (), [t]))
+        done.append(t)
+    return ops
+
+
+@pytest.mark.parametrize("n", [10, 12, 13, 15, 17])
+@pytest.mark.parametrize("case", ["qft", "qft_noswap", "low_half", "high_half", "scattered", "one"])
+def test_support_tracking_from_basis_states(n, case):
+    """Circuits that start from |0..0> and consist of (phase, Hadamard) ladders run with support
+    tracking: only what can be non-zero is read, computed and written.  Same result
+    as with tracking off and as the oracle, including the tiles that are written as zeros."""
+    if case == "qft":
+        ops = W.qft_ops(n, measure=False)
+    elif case == "qft_noswap":
+        ops = W.qft_ops(n, measure=False, swaps=False)
+    elif case == "low_half":
+        ops = _ladder_ops(n, list(range(n - 1, n // 2, -1)))
+    elif case == "high_half":
+        ops = _ladder_ops(n, list(range(n // 2, -1, -1)), {0: [n - 1], 1: [n - 2]})
+    elif case == "scattered":
+        ops = _ladder_ops(n, [n - 1, 0, n // 2, 3, n - 4, 1], {3: [2, n - 2]})
+    else:
+        ops = _ladder_ops(n, [n // 2])
+    outs = []
+    for track in (1, 0):
+        e = E.VectorState(n, 1)
+        e.set_option("track_support", track)
+        for op in ops:
+            e.apply_gate(O.gate_matrix(op[1], op[2]), op[3], op[1])
+        outs.append(e.column(0))
+        assert e.stats()["fallback_sweeps"] == 0
+        e.close()
+    o = O.OracleState(n, 1, mode=1, order=1)
+    for op in ops:
+        o.apply_gate(O.gate_matrix(op[1], op[2]), op[3])
+    assert rel_l2(outs[0], o.column(0)) < TOL
+    assert rel_l2(outs[1], o.column(0)) < TOL
+    assert rel_l2(outs[0], outs[1]) < 1e-14
+
+
+@pytest.mark.parametrize("n,shots", [(10, 16), (13, 40)])
+def test_support_tracking_collapsed_columns(n, shots):
+    """measure_all leaves one lazy basis column per distinct outcome (vectorstate.rs:150-158): a ladder
+    applied afterwards starts from a different basis index in every column."""
+    e, o = E.VectorState(n, shots), O.OracleState(n, shots, mode=1, order=1)
+    for q in range(n):
+        m = O.gate_matrix("h")
+        e.apply_gate(m, [q], "H"); o.apply_gate(m, [q])
+    words = O.splitmix64_words(11, shots)
+    re_, ro = np.zeros(shots, dtype=np.uint64), np.zeros(shots, dtype=np.uint64)
+    e.measure_all_into(list(range(n)), re_, E.Rng(words=words))
+    o.measure_all_into(list(range(n)), ro, O.Rng(words=words))
+    assert np.array_equal(re_, ro)
+    for op in W.qft_ops(n, measure=False):
+        m = O.gate_matrix(op[1], op[2])
+        e.apply_gate(m, op[3], op[1]); o.apply_gate(m, op[3])
+    assert e.counts == o.counts
+    for c in range(len(o.counts)):
+        assert rel_l2(e.column(c), o.column(c)) < TOL
+
+
+def test_conditional_swap_moves_only_flagged_columns():
+    """A conditional Swap (vectorstate.rs:193-227 with swap.rs) must not relabel the unflagged columns."""
+    n, shots = 6, 8
+    e, o = pair(n, shots, seed=3)
+    words = O.splitmix64_words(5, 64)
+    re_, ro = np.zeros(shots, dtype=np.uint64), np.zeros(shots, dtype=np.uint64)
+    e.measure_into(2, 0, re_, E.Rng(words=words)); o.measure_into(2, 0, ro, O.Rng(words=words))
+    assert np.array_equal(re_, ro)
+    ctrl = [bool(v & 1) for v in re_]
+    m = O.gate_matrix("swap")
+    e.apply_conditional_gate(ctrl, m, [0, 5], "Swap"); o.apply_conditional_gate(ctrl, m, [0, 5])
+    mh = O.gate_matrix("h")
+    e.apply_gate(mh, [0], "H"); o.apply_gate(mh, [0])
+    assert e.counts == o.counts
+    for c in range(len(o.counts)):
+        assert rel_l2(e.column(c), o.column(c)) < TOL

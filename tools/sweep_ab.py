@@ -24,8 +24,10 @@ for (coal, bal, tile) in combos:
             st.apply_gate(m, b)
         st.flush()
     s = st.stats()
-    probe = st.column(0, (1 << n) - 4096, 4096)
-    err = float(np.max(np.abs(probe - 2.0 ** (-n / 2))))
+    err = 0.0
+    for off in (0, (1 << n) - 4096, (1 << (n - 1)) + 12345 * 64, 3 << (n - 3)):
+        err = max(err, float(np.max(np.abs(st.column(0, off, 4096) - 2.0 ** (-n / 2)))))
+    err = max(err, abs(st.column_totals()[0] - 1.0))
     print(json.dumps({"lib": os.path.basename(E.LIB_PATH), "n": n, "coalesce": coal, "balance": bal, "tile": tile,
                       "sweeps_per_circuit": s["sweeps"] / 3, "avg_sweep_ms": s["sweep_ms"] / s["sweeps"],
                       "circuit_sweep_ms": s["sweep_ms"] / 3, "max_abs_err_probe": err}), flush=True)
