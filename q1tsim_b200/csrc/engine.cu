@@ -54,8 +54,13 @@ bool pool_give(int device, size_t bytes, void *ptr)
     for (const PoolEntry &e : g_pool)
         if (e.device == device) { cached += e.bytes; if (e.bytes == bytes) ++same; }
     if (same >= kPoolMaxPerClass) return false;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+    static size_t total_of[64] = { 0 };      // cudaMemGetInfo costs up to a millisecond: ask once per device
+    size_t total_b = (device >= 0 && device < 64) ? total_of[device] : 0;
+    if (!total_b) {
+        size_t free_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+        if (device >= 0 && device < 64) total_of[device] = total_b;
+    }
     if (total_b && cached + bytes > total_b / 100 * 72) return false;
     g_pool.push_back({ device, bytes, ptr });
     return true;
@@ -179,8 +184,13 @@ void DeviceVectorState::release_column(double2 *p)
     for (const Column &c : cols_)
         if (c.buf) ++live;
     const size_t bytes = sizeof(double2) << n_;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+    static size_t total_of[64] = { 0 };      // cudaMemGetInfo costs up to a millisecond: ask once per device
+    size_t total_b = (device_ >= 0 && device_ < 64) ? total_of[device_] : 0;
+    if (!total_b) {
+        size_t free_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+        if (device_ >= 0 && device_ < 64) total_of[device_] = total_b;
+    }
     const bool fits = total_b == 0 || (live + free_bufs_.size() + 1) * bytes <= total_b / 100 * 80;
     if (free_bufs_.size() < 2 && fits) free_bufs_.push_back(p);
     else { cudaStreamSynchronize(stream_); cudaFree(p); }
@@ -455,7 +465,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
         const bool gen_here = generate && si == 0;
         P.sup_mask = 0;
         P.sup_mode = 0;
-        for (int r = 0; r < P.nrounds; ++r) P.rounds[r].zmask = 0;
+        for (int r = 0; r < P.nrounds; ++r) P.rounds[r].zmask = P.rounds[r].smask = 0;
         bytes_moved[si] = (gen_here ? 16ull : 32ull) << n_;
         if (!track || pinned == 0) continue;
         P.sup_mask = pinned;
@@ -468,6 +478,8 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             uint32_t regs = 0;
             for (int j = 0; j < kRegBits; ++j) regs |= 1u << R.reg_tb[j];
             R.zmask = pinned_tl & ~regs;
+            R.smask = 0;
+            for (int j = 0; j < kRegBits; ++j) R.smask |= ((pinned_tl >> R.reg_tb[j]) & 1u) << j;
             for (int j = kRegBits - R.nsteps; j < kRegBits; ++j) pinned_tl &= ~(1u << R.reg_tb[j]);   // this round's targets
         }
         int pinned_outer = 0, pinned_all = 0;
@@ -564,6 +576,7 @@ int DeviceVectorState::run_queue(bool final_relabel)
         bool fusable = true;
         for (const LoweredGate &g : q) fusable = fusable && (g.kind == LoweredGate::POLY || g.kind == LoweredGate::G1);
         if (fusable) {
+            std::vector<PlannedSweep> plan[2];
             uint64_t cost[2][2];
             for (int b = 0; b < 2; ++b) {
                 Planner trial(n_, (int)tile_bits_, (int)coalesce_bits_, b != 0);
@@ -571,8 +584,10 @@ int DeviceVectorState::run_queue(bool final_relabel)
                 trial.finish();
                 cost[b][0] = trial.stats.sweeps;
                 cost[b][1] = trial.stats.rounds;
+                plan[b] = trial.take();
             }
-            balance = cost[1][0] < cost[0][0] || (cost[1][0] == cost[0][0] && cost[1][1] < cost[0][1]);
+            const int pick = (cost[1][0] < cost[0][0] || (cost[1][0] == cost[0][0] && cost[1][1] < cost[0][1])) ? 1 : 0;
+            return run_sweeps(plan[pick], which, final_relabel);
         }
     }
     Planner pl(n_, (int)tile_bits_, (int)coalesce_bits_, balance);

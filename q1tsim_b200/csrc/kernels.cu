@@ -577,9 +577,8 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     const int ntab = P.nphase << he_bits;
     double2 *const s_hiF = tile + (1u << T);             // [2][ntab]: hi[ih] * exp(i*pi*angle(outer bits)), double-buffered
     double2 *const s_tileF = s_hiF + 2 * ntab;           // [nphase]
-    double2 *const s_lo = s_tileF + P.nphase;            // [nphase][16]  copies of the PhaseTab rows: the CTA is
-    double2 *const s_hi = s_lo + (P.nphase << kThrLoBits);   // [ntab]    persistent, global memory is read once
-    double *const s_coef = reinterpret_cast<double *>(s_hi + ntab);   // [nphase][n_outer + 1], last = base
+    double2 *const s_lo = s_tileF + P.nphase;            // [nphase][16]  copies of the PhaseTab rows (the CTA is persistent)
+    double *const s_coef = reinterpret_cast<double *>(s_lo + (P.nphase << kThrLoBits));   // [nphase][n_outer + 1], last = base
     const int ncoef = P.n_outer + 1;
     // per-thread source / destination offsets: kept in shared memory, not in registers -- with 32
     // amplitudes per thread the compiler spilled them, and a local-memory reload is an L2 round trip
@@ -654,12 +653,12 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
 #pragma unroll
             for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
         } else {
-            // only the elements inside the support exist in memory; the rest of the tile is zero
+            // only the elements inside the support exist in memory; the others are zeros that no round
+            // reads (its loads are masked by zmask / smask), so they are not even written to the tile
 #pragma unroll
             for (int i = 0; i < kSlots; ++i) {
                 const unsigned e = tid | ((unsigned)i << TB);
                 if (((e ^ sup_vt) & sup_mt) == 0u) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
-                else *reinterpret_cast<double2 *>(tile_b + (sw ^ P.ld_sw_hi[i])) = make_double2(0.0, 0.0);
             }
         }
         asm volatile("cp.async.commit_group;\n" ::);
@@ -697,7 +696,12 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         }
     };
     auto tables_phase2 = [&](int buf) {
-        for (int e = tid; e < ntab; e += blockDim.x) s_hiF[buf * ntab + e] = cmul(s_hi[e], s_tileF[e >> he_bits]);
+        // (hi[] stays in global memory: this runs in the shadow of the next tile's loads, and the 1.5 KiB
+        //  it would take decide whether three CTAs fit on an SM for a 12-step sweep)
+        for (int e = tid; e < ntab; e += blockDim.x) {
+            const double2 hi = __ldg(reinterpret_cast<const double2 *>(ptabs[e >> he_bits].hi) + (e & ((1 << he_bits) - 1)));
+            s_hiF[buf * ntab + e] = cmul(hi, s_tileF[e >> he_bits]);
+        }
     };
 
     unsigned long long o = blockIdx.x;
@@ -710,8 +714,6 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     if (!generate) issue_loads(o);
     for (int e = tid; e < (P.nphase << kThrLoBits); e += blockDim.x)
         s_lo[e] = __ldg(reinterpret_cast<const double2 *>(ptabs[e >> kThrLoBits].lo) + (e & ((1 << kThrLoBits) - 1)));
-    for (int e = tid; e < ntab; e += blockDim.x)
-        s_hi[e] = __ldg(reinterpret_cast<const double2 *>(ptabs[e >> he_bits].hi) + (e & ((1 << he_bits) - 1)));
     for (int e = tid; e < P.nphase * ncoef; e += blockDim.x) {
         const int pid = e / ncoef, i = e - pid * ncoef;
         s_coef[e] = i < P.n_outer ? ptabs[pid].outer_coef[i] : ptabs[pid].base;
@@ -738,6 +740,8 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 if (R.sync_before == 2) __syncthreads();
                 else __syncwarp();
             }
+            // a thread that differs from the basis index in a still-pinned thread bit holds only zeros
+            const bool all_zero = ((thrL ^ sup_vt) & R.zmask) != 0u;
             double2 a[kSlots];
             if (r == 0 && generate) {
                 // the basis element lives in exactly one tile of the grid and one slot of one thread
@@ -753,9 +757,19 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 }
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)gen_slot ? P.gen_scale : 0.0, 0.0);
-            } else {
+            } else if (R.zmask == 0u && R.smask == 0u) {
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
+            } else {
+                // support tracking: read only what can be non-zero
+                unsigned vs = 0;
+                for (int j = 0; j < kRegBits; ++j) vs |= ((sup_vt >> R.reg_tb[j]) & 1u) << j;
+                vs &= R.smask;
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) {
+                    if (!all_zero && (((unsigned)s ^ vs) & R.smask) == 0u) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
+                    else a[s] = make_double2(0.0, 0.0);
+                }
             }
             if (last && !staged_store) {
                 if (has_next) tables_phase1(o_next);
@@ -766,8 +780,6 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 }
             }
             const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
-            // a thread that differs from the basis index in a still-pinned thread bit holds only zeros
-            const bool all_zero = ((thrL ^ sup_vt) & R.zmask) != 0u;
             if (!all_zero)
             switch (R.nsteps) {
             case 1: LadderSteps<1, kRegBits - 1, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
@@ -788,7 +800,9 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 }
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) st_global_cs(q + P.ds_slot[s], a[s]);
-            } else {
+            } else if (!all_zero || last) {
+                // (zeros of an all-zero thread are never read by a later round; the store pass after
+                //  the last round reads everything)
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
             }
@@ -881,7 +895,7 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
             ctas_per_sm = Q1T_LADDER_MIN_CTAS;
         }
         const size_t lsmem = (sizeof(double2) << prog.T) +
-                             sizeof(double2) * (((size_t)prog.nphase << he_bits) * 3 + prog.nphase + ((size_t)prog.nphase << kThrLoBits)) +
+                             sizeof(double2) * (((size_t)prog.nphase << he_bits) * 2 + prog.nphase + ((size_t)prog.nphase << kThrLoBits)) +
                              sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x;
         int dev = 0, nsm = 148, occ = 0;
         cudaGetDevice(&dev);

@@ -72,7 +72,8 @@ struct RoundDesc {
     uint8_t pad1[3];
     uint32_t zmask;                 // support tracking: tile-local bits that are thread bits of this round and still
                                     // pinned to the basis value -> a thread that differs there holds only zeros
-    uint32_t pad2;
+    uint32_t smask;                 // same for the register bits: slot bits still pinned when the round starts -> a slot
+                                    // that differs from the basis value there is zero and is not read
     BitRun runs[kMaxRuns];          // tid -> tile-local index of the thread
     uint32_t sw_slot[kSlots];       // byte offset (swizzled index * 16) contributed by slot s
     uint16_t op_begin, op_end;
