@@ -19,6 +19,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cstdio>
 #include <cstdlib>
 
 namespace q1t {
@@ -561,6 +562,15 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
 // dead, and the cp.async loads and phase tables of the NEXT tile are issued into
 // it before the last round's arithmetic and global stores.
 // ---------------------------------------------------------------------------
+#ifdef Q1T_PHASE_CLOCKS
+// debug build: cycles per phase of the tile loop, per warp of one CTA, printed at exit
+#define PCLK_DECL long long pclk[16] = { 0 }; long long pclk_t = clock64();
+#define PCLK(i) do { const long long now__ = clock64(); pclk[i] += now__ - pclk_t; pclk_t = now__; } while (0)
+#else
+#define PCLK_DECL
+#define PCLK(i) do { } while (0)
+#endif
+
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
@@ -724,11 +734,15 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     tables_phase2(0);
     int buf = 0;
     unsigned long long o_next = 0;
+    PCLK_DECL
     for (; o < ntiles; o = o_next, buf ^= 1) {
         o_next = advance(o);
         const bool has_next = o_next < ntiles;
+        PCLK(0);
         if (!generate) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        PCLK(1);
         __syncthreads();                       // tile o and its tables are visible to the whole CTA
+        PCLK(2);
         const double2 *const hiF = s_hiF + buf * ntab;
         for (int r = 0; r < P.nrounds; ++r) {
             const RoundDesc &R = P.rounds[r];
@@ -736,10 +750,12 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             unsigned thrL = 0;
             for (int k = 0; k < R.nruns; ++k) thrL |= (unsigned)run_bits(tid, R.runs[k]);
             const unsigned swT = tile_swizzle(thrL) * 16u;
+            PCLK(3);
             if (r > 0) {
                 if (R.sync_before == 2) __syncthreads();
                 else __syncwarp();
             }
+            PCLK(4);
             // a thread that differs from the basis index in a still-pinned thread bit holds only zeros
             const bool all_zero = ((thrL ^ sup_vt) & R.zmask) != 0u;
             double2 a[kSlots];
@@ -771,6 +787,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                     else a[s] = make_double2(0.0, 0.0);
                 }
             }
+            PCLK(5);
             if (last && !staged_store) {
                 if (has_next) tables_phase1(o_next);
                 __syncthreads();               // all amplitudes of the tile are in registers: the buffer is dead
@@ -779,6 +796,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                     tables_phase2(buf ^ 1);
                 }
             }
+            PCLK(6);
             const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
             if (!all_zero)
             switch (R.nsteps) {
@@ -792,6 +810,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             default: LadderSteps<4, kRegBits - 4, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
 #endif
             }
+            PCLK(7);
             if (last && !staged_store) {
                 double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
                 if (scale != 1.0) {
@@ -807,10 +826,12 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
             }
         }
+        PCLK(8);
         if (staged_store) {
             // the destination layout differs from the last round's thread layout (fused relabel):
             // one more trip through shared memory, stores coalesced in destination order
             __syncthreads();
+            PCLK(10);
             double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
             unsigned swl = sw_lo;
             asm volatile("" : "+r"(swl));     // as in issue_loads: no hoisting of the 32 addresses
@@ -822,22 +843,33 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 for (int i = 0; i < kSlots / 2; ++i)
                     st_global_cs(q + P.st_off_hi[i], scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i]);
             }
+            PCLK(11);
             {   // second half: once it is in registers the tile is dead -> prefetch, then store
                 double2 v[kSlots / 2];
 #pragma unroll
                 for (int i = 0; i < kSlots / 2; ++i) v[i] = *reinterpret_cast<const double2 *>(tile_b + (swl ^ P.st_l_hi[kSlots / 2 + i]));
                 if (has_next) tables_phase1(o_next);
+                PCLK(12);
                 __syncthreads();
+                PCLK(13);
                 if (has_next) {
                     if (!generate) issue_loads(o_next);
                     tables_phase2(buf ^ 1);
                 }
+                PCLK(14);
 #pragma unroll
                 for (int i = 0; i < kSlots / 2; ++i)
                     st_global_cs(q + P.st_off_hi[kSlots / 2 + i], scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i]);
             }
         }
+        PCLK(9);
     }
+#ifdef Q1T_PHASE_CLOCKS
+    if (blockIdx.x == 7 && (tid & 31) == 0)
+        printf("PCLK warp %d: adv %lld ldwait %lld topbar %lld | roundhdr %lld sync %lld lds %lld dead+pref %lld compute %lld | store/sts %lld staged %lld"
+               " [bar %lld half1 %lld lds2+ph1 %lld bar %lld pref %lld stg2->9]\n",
+               tid >> 5, pclk[0], pclk[1], pclk[2], pclk[3], pclk[4], pclk[5], pclk[6], pclk[7], pclk[8], pclk[9], pclk[10], pclk[11], pclk[12], pclk[13], pclk[14]);
+#endif
 }
 
 // threads per CTA: 2^(T - kRegBits).  The ladder-only kernel for tiles up to 2^12 runs with several

@@ -88,7 +88,7 @@ struct SweepProgram {
     int32_t relabel;      // 1 if dst positions differ from src positions (out-of-place only)
     int32_t generate;     // 1: the source column is a basis state |gen_idx[col]>, nothing is read
     int32_t ld_nruns, st_nruns;
-    int32_t prefetch_ahead;   // >0: prefetch the tile this many outer indices ahead into L2
+    int32_t prefetch_ahead;   // >0: prefetch the tile this many outer indices ahead into L2 (old experiment, unused)
     int32_t direct_load;      // round 0 reads its amplitudes straight from global memory (no staging pass)
     int32_t direct_store;     // the last round writes its amplitudes straight to global memory
     int32_t dl_nruns, ds_nruns;
