@@ -6,10 +6,10 @@ CPU oracle timed beside it).
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--qubits n]
 
 One "step" = one full execution of the circuit: |0..0> state, every gate,
-measure_all of all shots.  `value` times the steps with the state buffer already
-resident in HBM (reset + gates + measurement); `e2e` times the public call a user
-makes (state allocation and initialisation, gate lowering/planning on the host,
-all host<->device copies, results returned in host memory).
+measure_all of all shots.  `value` times circuit.execute(shots) on a circuit that
+was built once (state buffers HBM-resident through the buffer cache); `e2e` times
+what a user of the reference's FFI does from scratch every step (build the circuit
+from host data, execute, read the classical register back to host memory).
 """
 import argparse
 import json
@@ -177,19 +177,24 @@ def run_ours(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: state buffer resident in HBM ----
-    st = E.VectorState(n, shots, dev)
+    # ---- value: the reference-shaped call on a circuit built once: circuit.execute(nr_shots)
+    # (circuit.rs:562-600: fresh |0..0> state, every gate, measure_all).  The op list lives in host
+    # memory and is lowered, planned (plan cache) and launched by the C++ host layer; the state buffers
+    # are HBM-resident (process-wide buffer cache) ----
+    from q1tsim_b200 import circuit as QC
+    circ = QC.Circuit(n, n, dev)
+    W.load_ops(circ, ops)
+    st = E.VectorState(n, shots, dev)          # direct QuState-level handle: used for the per-kernel timing below
     if args.tile_bits:
         st.set_option("tile_bits", args.tile_bits)
-    if args.prefetch_ahead >= 0:
-        st.set_option("prefetch_ahead", args.prefetch_ahead)
-    if args.direct >= 0:
-        st.set_option("direct", args.direct)
     res = np.zeros(shots, dtype=np.uint64)
     rng = E.Rng(seed=2)
 
     def step():
-        # reset to |0..0> (lazy), queue the 480 gates, measure all shots
+        circ.execute(shots, rng)
+
+    def qustate_step():
+        # the same work through the inner (QuState) ABI: reset to |0..0> (lazy), queue the gates, measure all shots
         st.reset_all()
         for m, b, name in gates:
             st.apply_gate(m, b, name)
@@ -197,7 +202,6 @@ def run_ours(args, rank, world, local):
 
     for _ in range(args.warmup):
         step()
-    st.reset_stats()
     sampler = ClockSampler(dev)
     barrier()
     sampler.start()
@@ -207,7 +211,7 @@ def run_ours(args, rank, world, local):
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
-    stats = st.stats()
+    stats = circ.engine_stats()                # statistics of the last execute()
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -219,10 +223,11 @@ def run_ours(args, rank, world, local):
     #     bytes a launch has to move are fewer than 32 B/amplitude -- sweep_bytes counts what is needed)
     # (b) the same circuit on a DENSE input (seeded product state, SURVEY 8(d) cfg3 input B): every
     #     sweep reads and writes all 2^n amplitudes, 32 B each -- the figure the kernel is judged by
+    qustate_step()
     st.set_timing(True)
     st.reset_stats()
     for _ in range(2):
-        step()
+        qustate_step()
     ts = st.stats()
     st.set_timing(False)
     st.close()
@@ -271,8 +276,6 @@ def run_ours(args, rank, world, local):
     # ---- e2e: the call a user makes, host buffers in, host buffers out ----
     e2e_steps = max(3, min(args.steps, 5))
 
-    from q1tsim_b200 import circuit as QC
-
     def e2e_step():
         # the reference-facing call: build the circuit through the ffi.rs-compatible C ABI,
         # execute(nr_shots) (fresh state, gate lowering + planning, every H2D/D2H copy), read c_state
@@ -310,9 +313,10 @@ def run_ours(args, rank, world, local):
                    "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
         "circuit_ms": 1e3 * dt / args.steps,
         "e2e": {"value": e2e_val, "unit": "gate_amp_updates/s", "ms_per_step": 1e3 * dte / e2e_steps,
-                "h2d_bytes_per_step": int(stats["sweeps"] / args.steps * 16384 + shots * 8),
-                "d2h_bytes_per_step": int(shots * 8 + 8), "steps": e2e_steps},
-        "gpu_launches": int(stats["kernel_launches"]),
+                "h2d_bytes_per_step": int(stats["sweeps"] * 28000 + shots * 8),
+                "d2h_bytes_per_step": int(shots * 8 + 8), "steps": e2e_steps,
+                "call": "Circuit built through the ffi.rs-compatible C ABI from host data, execute(shots), c_state read back to host, every step"},
+        "gpu_launches": int(stats["kernel_launches"]) * args.steps,
         "engine_stats": stats,
         "roofline": roofline,
         "clocks": clocks,

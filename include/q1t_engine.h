@@ -154,17 +154,19 @@ typedef struct {
     uint64_t permute_sweeps;      /* sweeps spent only on qubit relabelling */
     uint64_t fallback_sweeps;     /* gates executed by the unfused generic kernel */
     uint64_t fused_relabels;      /* relabellings absorbed into the last gate sweep (no extra pass) */
-    uint64_t sweep_bytes;         /* algorithmic bytes of the sweep launches: 32 B per amplitude, 16 B when the input is generated */
+    uint64_t sweep_bytes;         /* bytes the sweep launches had to move: 32 B per amplitude, less when the input is a basis state (support tracking) */
     double   sweep_ms;            /* device time of sweep kernels (CUDA events), if timing enabled */
     double   read_ms;             /* device time of read passes */
     double   peer_swap_ms;        /* device time of q1t_peer_swap kernels (always measured) */
     uint64_t peer_swap_bytes;     /* bytes this rank moved over NVLink in q1t_peer_swap (remote reads + remote writes) */
+    uint64_t plan_cache_hits;     /* gate batches whose sweep plan came from the process-wide plan cache */
 } q1t_stats;
 int q1t_get_stats(q1t_state *st, q1t_stats *out);
 int q1t_reset_stats(q1t_state *st);
 /* enable per-kernel CUDA-event timing (bench only; serialises the stream) */
 int q1t_set_timing(q1t_state *st, int enabled);
-/* engine knobs: "tile_bits" (8..13), "fuse" (0/1).  Returns Q1T_ERR_INVALID_ARGUMENT for unknown keys. */
+/* engine knobs: "tile_bits" (8..13), "fuse" (0/1), "coalesce_bits" (2/3), "balance" (-1/0/1), "track_support" (0/1).
+ * Returns Q1T_ERR_INVALID_ARGUMENT for unknown keys. */
 int q1t_set_option(q1t_state *st, const char *key, long value);
 
 /* ---- host-only helpers (no device needed) ---- */

@@ -87,6 +87,14 @@ void scratch_free(int device, void *p, size_t bytes)
 }
 }  // namespace
 
+namespace {
+struct PlanCacheEntry { uint64_t key; size_t ngates; uint64_t stamp; std::vector<PlannedSweep> sweeps; };
+std::mutex g_plan_mu;
+std::vector<PlanCacheEntry> g_plan_cache;
+uint64_t g_plan_clock = 0;
+const size_t kPlanCacheMax = 16;
+}  // namespace
+
 int DeviceVectorState::cuda_fail(cudaError_t e, const char *what)
 {
     char buf[512];
@@ -576,6 +584,32 @@ int DeviceVectorState::run_queue(bool final_relabel)
         bool fusable = true;
         for (const LoweredGate &g : q) fusable = fusable && (g.kind == LoweredGate::POLY || g.kind == LoweredGate::G1);
         if (fusable) {
+            // plan cache: execute() of the same circuit lowers to the same gate list every time
+            // (circuit.rs:594-600 builds a fresh state per call); planning it again is pure host time
+            uint64_t key = 1469598103934665603ull;
+            auto mix = [&](const void *p, size_t nbytes) {
+                const unsigned char *b = static_cast<const unsigned char *>(p);
+                for (size_t i = 0; i < nbytes; ++i) { key ^= b[i]; key *= 1099511628211ull; }
+            };
+            const long cfg[4] = { (long)n_, tile_bits_, coalesce_bits_, (long)kRegBits };
+            mix(cfg, sizeof cfg);
+            for (const LoweredGate &g : q) {
+                const int hdr[5] = { (int)g.kind, g.nb, g.b[0], g.b[1], g.target };
+                mix(hdr, sizeof hdr);
+                mix(&g.cmask, sizeof g.cmask);
+                if (g.kind == LoweredGate::POLY) { mix(&g.c0, sizeof g.c0); mix(g.lin, sizeof g.lin); mix(&g.quad, sizeof g.quad); }
+                else mix(g.m, sizeof g.m);
+            }
+            {
+                std::lock_guard<std::mutex> lk(g_plan_mu);
+                for (PlanCacheEntry &pc : g_plan_cache)
+                    if (pc.key == key && pc.ngates == q.size()) {
+                        std::vector<PlannedSweep> plan = pc.sweeps;
+                        pc.stamp = ++g_plan_clock;
+                        stats.plan_cache_hits++;
+                        return run_sweeps(plan, which, final_relabel);
+                    }
+            }
             std::vector<PlannedSweep> plan[2];
             uint64_t cost[2][2];
             for (int b = 0; b < 2; ++b) {
@@ -587,6 +621,16 @@ int DeviceVectorState::run_queue(bool final_relabel)
                 plan[b] = trial.take();
             }
             const int pick = (cost[1][0] < cost[0][0] || (cost[1][0] == cost[0][0] && cost[1][1] < cost[0][1])) ? 1 : 0;
+            if (q.size() >= 16) {
+                std::lock_guard<std::mutex> lk(g_plan_mu);
+                if (g_plan_cache.size() >= kPlanCacheMax) {       // evict the least recently used plan
+                    size_t lru = 0;
+                    for (size_t i = 1; i < g_plan_cache.size(); ++i)
+                        if (g_plan_cache[i].stamp < g_plan_cache[lru].stamp) lru = i;
+                    g_plan_cache.erase(g_plan_cache.begin() + lru);
+                }
+                g_plan_cache.push_back({ key, q.size(), ++g_plan_clock, plan[pick] });
+            }
             return run_sweeps(plan[pick], which, final_relabel);
         }
     }

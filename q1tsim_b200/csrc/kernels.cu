@@ -688,27 +688,33 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             }
             return;
         }
+        // four ops per warp and pass: lane = (op slot p, bit group g); every lane adds the coefficients of
+        // outer bits g, g+8, g+16, ..., three butterfly stages finish the sums, then one sincospi per op
         const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-        double mine = 0.0;
-        int k = 0;
-        for (int pid = warp; pid < P.nphase; pid += nwarps, ++k) {
-            double part = lane == 0 ? s_coef[pid * ncoef + P.n_outer] : 0.0;
-            for (int i = lane; i < P.n_outer; i += 32)
-                if ((o >> i) & 1ull) part += s_coef[pid * ncoef + i];
+        const int p = lane >> 3, g = lane & 7;
+        for (int base = 0; base < P.nphase; base += 4 * nwarps) {
+            const int pid = base + warp * 4 + p;
+            double part = 0.0;
+            if (pid < P.nphase) {
+                if (g == 0) part = s_coef[pid * ncoef + P.n_outer];
+                for (int i = g; i < P.n_outer; i += 8)
+                    if ((o >> i) & 1ull) part += s_coef[pid * ncoef + i];
+            }
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-            if (lane == k) mine = part;
-        }
-        if (lane < k) {
-            double sn, cs;
-            sincospi(mine, &sn, &cs);
-            s_tileF[warp + lane * nwarps] = make_double2(cs, sn);
+            for (int off = 4; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (g == 0 && pid < P.nphase) {
+                double sn, cs;
+                sincospi(part, &sn, &cs);
+                s_tileF[pid] = make_double2(cs, sn);
+            }
         }
     };
+    // phase 2: s_hiF[e] = hi[e] * tile factor.  Entry tid of hi[] never changes: it stays in registers
+    const double2 my_hi = (int)tid < ntab ? __ldg(reinterpret_cast<const double2 *>(ptabs[tid >> he_bits].hi) + (tid & ((1 << he_bits) - 1)))
+                                          : make_double2(0.0, 0.0);
     auto tables_phase2 = [&](int buf) {
-        // (hi[] stays in global memory: this runs in the shadow of the next tile's loads, and the 1.5 KiB
-        //  it would take decide whether three CTAs fit on an SM for a 12-step sweep)
-        for (int e = tid; e < ntab; e += blockDim.x) {
+        if ((int)tid < ntab) s_hiF[buf * ntab + tid] = cmul(my_hi, s_tileF[tid >> he_bits]);
+        for (int e = tid + blockDim.x; e < ntab; e += blockDim.x) {
             const double2 hi = __ldg(reinterpret_cast<const double2 *>(ptabs[e >> he_bits].hi) + (e & ((1 << he_bits) - 1)));
             s_hiF[buf * ntab + e] = cmul(hi, s_tileF[e >> he_bits]);
         }
