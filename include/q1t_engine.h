@@ -182,6 +182,13 @@ q1t_rng        q1t_rng_handle(q1t_rng_state *r);
 uint64_t q1t_binomial(q1t_rng rng, uint64_t n, double p);
 /* `matrix()` of a built-in gate by name (composite.rs:287-445 table); returns #qubits or <0 */
 int q1t_gate_matrix(const char *name, const double *params, size_t nr_params, double *out_re_im /* 2*64 */);
+/* Composite::from_string(..).matrix() (composite.rs:273-450, :480-485): parses the description and
+ * writes the row-major 2^k x 2^k matrix (re,im).  Returns k (<= 10), or Q1T_ERR_PARSE with the
+ * reference's ParseError text in err_out, or Q1T_ERR_NOT_ENOUGH_SPACE if out_capacity_doubles < 2*4^k. */
+int q1t_composite_matrix(const char *description, double *out_re_im, size_t out_capacity_doubles, char *err_out, size_t err_capacity);
+/* Expression::parse(text).eval() (expression.rs:86-392): arithmetic with pi, + - * / ^, sin cos tan exp ln sqrt.
+ * Returns 0 and the value, or Q1T_ERR_PARSE; *consumed = characters parsed. */
+int q1t_eval_expression(const char *text, double *value_out, size_t *consumed, char *err_out, size_t err_capacity);
 /* fusion planner dry run (no device): how many sweeps / rounds a gate list takes on nr_bits qubits.
  * gates: concatenated matrices, bits; returns Q1T_OK and fills out[0]=sweeps out[1]=rounds out[2]=ops
  * out[3]=fallback gates out[4]=permute sweeps needed to restore canonical order */

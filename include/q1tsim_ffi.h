@@ -11,7 +11,7 @@
  *     circuit.rs:576-583, which is out of scope here);
  *   - circuit_latex / circuit_open_qasm / circuit_c_qasm return an error result
  *     (text exporters are out of scope);
- *   - extra entry points: circuit_add_matrix_gate, circuit_execute_with_rng,
+ *   - extra entry points: circuit_add_matrix_gate, circuit_add_composite_gate, circuit_execute_with_rng,
  *     circuit_reexecute_with_rng, circuit_histogram_u64, circuit_engine_stats,
  *     circuit_set_device, circuit_state.
  * Ownership (ffi.rs:139-169): every result_t is returned by value and owns
@@ -70,6 +70,13 @@ result_t   circuit_add_conditional_matrix_gate(circuit_t *ptr, const size_t *con
                                                uint64_t target, const char *description, const double *matrix_re_im,
                                                size_t matrix_dim, const size_t *qbits, size_t nr_qbits);
 result_t   circuit_barrier(circuit_t *ptr, const size_t *qbits, size_t nr_qbits);           /* circuit.rs:541-552 */
+/* Composite::from_string(name, desc) (composite.rs:273-450) added on `qbits`, its body `nr_iterations`
+ * times (Loop, staticloop.rs:71-92; 1 for a plain composite).  The sub-gates are flattened into the
+ * circuit rather than multiplied into one 2^k x 2^k matrix.  Errors: the reference's
+ * ParseError texts (error.rs:93-127) and "Expected {} bits for \"{}\", got {}". */
+result_t   circuit_add_composite_gate(circuit_t *ptr, const char *name, const char *description,
+                                      const size_t *qbits, size_t nr_qbits, size_t nr_iterations);
+size_t     circuit_nr_ops(const circuit_t *ptr);
 /* execute_with_rng / reexecute_with_rng (circuit.rs:573-641) with a caller-owned generator */
 result_t   circuit_execute_with_rng(circuit_t *ptr, size_t nr_shots, q1t_rng rng);
 result_t   circuit_reexecute_with_rng(circuit_t *ptr, q1t_rng rng);

@@ -39,7 +39,8 @@ OUTER_ABI_SYMBOLS = [
     # additive
     "circuit_add_matrix_gate", "circuit_add_conditional_matrix_gate", "circuit_barrier", "circuit_execute_with_rng",
     "circuit_reexecute_with_rng", "circuit_execute_with_qubit_coefs", "circuit_histogram_u64", "circuit_cstate_into",
-    "circuit_set_cstate", "circuit_set_device", "circuit_state", "circuit_engine_stats",
+    "circuit_set_cstate", "circuit_set_device", "circuit_state", "circuit_engine_stats", "circuit_add_composite_gate",
+    "circuit_nr_ops",
 ]
 
 _bound = False
@@ -67,6 +68,8 @@ def _lib():
         "circuit_add_matrix_gate": (R, [vp, C.c_char_p, dp, sz, szp, sz]),
         "circuit_add_conditional_matrix_gate": (R, [vp, szp, sz, C.c_uint64, C.c_char_p, dp, sz, szp, sz]),
         "circuit_barrier": (R, [vp, szp, sz]),
+        "circuit_add_composite_gate": (R, [vp, C.c_char_p, C.c_char_p, szp, sz, sz]),
+        "circuit_nr_ops": (sz, [vp]),
         "circuit_execute_with_rng": (R, [vp, sz, RNG]), "circuit_reexecute_with_rng": (R, [vp, RNG]),
         "circuit_execute_with_qubit_coefs": (R, [vp, sz, RNG, dp]),
         "circuit_histogram_u64": (R, [vp]),
@@ -180,6 +183,15 @@ class Circuit:
         self._keep.extend(p for p in params if isinstance(p, RefParam))
         q, nq = _sz(qbits)
         return _unpack(self._L.circuit_add_gate(self._p, name.encode(), q, nq, _params(params) if params else None, len(params)))
+
+    def add_composite_gate(self, name, description, qbits, nr_iterations=1):
+        """`Composite::from_string(name, description)` on `qbits` (composite.rs:273-450), body repeated
+        `nr_iterations` times (`Loop`, staticloop.rs:71-92); flattened into the circuit's gate list."""
+        q, nq = _sz(qbits)
+        return _unpack(self._L.circuit_add_composite_gate(self._p, name.encode(), description.encode(), q, nq, int(nr_iterations)))
+
+    def nr_ops(self):
+        return int(self._L.circuit_nr_ops(self._p))
 
     def add_matrix_gate(self, matrix, qbits, description="user gate"):
         m = np.ascontiguousarray(np.asarray(matrix, dtype=np.complex128))

@@ -4,6 +4,7 @@
 #include <string>
 
 #include "engine.h"
+#include "circuit.h"
 
 using q1t::DeviceVectorState;
 
@@ -176,6 +177,34 @@ int q1t_gate_matrix(const char *name, const double *params, size_t nparams, doub
 {
     if (!name || !out) return Q1T_ERR_INVALID_ARGUMENT;
     return q1t::builtin_gate_matrix(name, params, nparams, reinterpret_cast<std::complex<double> *>(out));
+}
+
+int q1t_composite_matrix(const char *description, double *out, size_t cap, char *err_out, size_t err_cap)
+{
+    if (!description || !out) return Q1T_ERR_INVALID_ARGUMENT;
+    std::vector<std::complex<double>> m;
+    std::string err;
+    const int k = q1t::composite_matrix(description, m, err);
+    if (k < 0) {
+        if (err_out && err_cap) std::snprintf(err_out, err_cap, "%s", err.c_str());
+        return Q1T_ERR_PARSE;
+    }
+    if (cap < 2 * m.size()) return Q1T_ERR_NOT_ENOUGH_SPACE;
+    std::memcpy(out, m.data(), sizeof(double) * 2 * m.size());
+    return k;
+}
+
+int q1t_eval_expression(const char *text, double *value_out, size_t *consumed, char *err_out, size_t err_cap)
+{
+    if (!text || !value_out) return Q1T_ERR_INVALID_ARGUMENT;
+    std::string err;
+    const char *rest = text;
+    if (!q1t::parse_expression(text, *value_out, &rest, err)) {
+        if (err_out && err_cap) std::snprintf(err_out, err_cap, "%s", err.c_str());
+        return Q1T_ERR_PARSE;
+    }
+    if (consumed) *consumed = (size_t)(rest - text);
+    return Q1T_OK;
 }
 
 int q1t_plan_dry_run(size_t nr_bits, size_t nr_gates, const double *matrices, const size_t *dims, const size_t *bits,

@@ -64,6 +64,10 @@ public:
     CircuitError reset(size_t qbit);
     void reset_all();
     CircuitError barrier(const std::vector<size_t> &qbits);
+    // Composite::from_string (composite.rs:273-450) / Loop (staticloop.rs:71-92): the sub-gates of the
+    // description are flattened into the op list on `bits`, the body `repeat` times
+    CircuitError add_composite(const std::string &name, const std::string &desc, const std::vector<size_t> &bits, size_t repeat = 1);
+    size_t nr_ops() const { return ops_.size(); }
 
     CircuitError execute(size_t nr_shots, q1t_rng rng, const double *qubit_coefs = nullptr);
     CircuitError reexecute(q1t_rng rng);
@@ -87,5 +91,11 @@ private:
 };
 
 int gate_spec_from_name(const char *name, const Param *params, size_t nparams, GateSpec &out, std::string &err);
+
+// composite.cpp: text front-end (composite.rs:92-450, expression.rs:86-300)
+struct SubGateDesc { std::string name; std::vector<double> args; std::vector<size_t> bits; };
+bool parse_expression(const char *text, double &out, const char **rest, std::string &err);
+bool parse_composite(const std::string &desc, std::vector<SubGateDesc> &out, size_t &nr_bits, std::string &err);
+int composite_matrix(const std::string &desc, std::vector<std::complex<double>> &out, std::string &err);
 
 }  // namespace q1t

@@ -167,6 +167,18 @@ result_t circuit_add_conditional_matrix_gate(circuit_t *ptr, const size_t *contr
                                                    std::vector<size_t>(qbits, qbits + nr_qbits)));
 }
 
+result_t circuit_add_composite_gate(circuit_t *ptr, const char *name, const char *description,
+                                    const size_t *qbits, size_t nr_qbits, size_t nr_iterations)
+{
+    if (!ptr) return res_error("Pointer to circuit is NULL");
+    if (!qbits && nr_qbits) return res_error("Pointer to bit indices is NULL");
+    if (!description) return res_error("Invalid gate description");
+    return res_from(ptr->impl.add_composite(name ? name : "composite", description,
+                                            std::vector<size_t>(qbits, qbits + nr_qbits), nr_iterations));
+}
+
+size_t circuit_nr_ops(const circuit_t *ptr) { return ptr ? ptr->impl.nr_ops() : 0; }
+
 result_t circuit_barrier(circuit_t *ptr, const size_t *qbits, size_t nr_qbits)
 {
     if (!ptr) return res_error("Pointer to circuit is NULL");

@@ -95,6 +95,8 @@ def lib():
         "q1t_binomial": (C.c_uint64, [R, C.c_uint64, C.c_double]),
         "q1t_gate_matrix": (C.c_int, [C.c_char_p, dp, sz, dp]),
         "q1t_plan_dry_run": (C.c_int, [sz, sz, dp, szp, szp, szp, C.c_long, u64p]),
+        "q1t_composite_matrix": (C.c_int, [C.c_char_p, dp, sz, C.c_char_p, sz]),
+        "q1t_eval_expression": (C.c_int, [C.c_char_p, dp, szp, C.c_char_p, sz]),
         "q1t_device_count": (C.c_int, []),
         "q1t_version": (C.c_char_p, []),
     }
@@ -113,7 +115,7 @@ INNER_ABI_SYMBOLS = [
     "q1t_counts", "q1t_read_amplitudes", "q1t_write_amplitudes", "q1t_marginal0", "q1t_column_totals", "q1t_flush",
     "q1t_last_error", "q1t_get_stats", "q1t_reset_stats", "q1t_set_timing", "q1t_set_option", "q1t_rng_splitmix64",
     "q1t_rng_from_words", "q1t_rng_entropy", "q1t_rng_consumed", "q1t_rng_free", "q1t_rng_handle", "q1t_binomial",
-    "q1t_gate_matrix", "q1t_plan_dry_run", "q1t_device_count", "q1t_version",
+    "q1t_gate_matrix", "q1t_plan_dry_run", "q1t_composite_matrix", "q1t_eval_expression", "q1t_device_count", "q1t_version",
 ]
 
 
@@ -165,6 +167,32 @@ def gate_matrix(name, params=()):
         raise ValueError("Invalid number of arguments for gate %s" % name)
     g = 1 << nb
     return out[:2 * g * g].view(np.complex128).reshape(g, g).copy()
+
+
+class ParseError(ValueError):
+    """error.rs:71-127 (ParseError), message = its Display text"""
+
+
+def composite_matrix(description):
+    """`Composite::from_string(name, description).matrix()` (composite.rs:273-450, :480-485)."""
+    out = np.zeros(2 << 20, dtype=np.float64)
+    err = C.create_string_buffer(512)
+    k = lib().q1t_composite_matrix(description.encode(), _dptr(out), out.size, err, 512)
+    if k < 0:
+        raise ParseError(err.value.decode())
+    g = 1 << k
+    return out[:2 * g * g].view(np.complex128).reshape(g, g).copy()
+
+
+def eval_expression(text):
+    """`Expression::parse(text)` + `eval()` (expression.rs:304-392): returns (value, unparsed rest)."""
+    v = C.c_double()
+    used = C.c_size_t()
+    err = C.create_string_buffer(512)
+    rc = lib().q1t_eval_expression(text.encode(), C.byref(v), C.byref(used), err, 512)
+    if rc:
+        raise ParseError(err.value.decode())
+    return v.value, text.encode()[used.value:].decode()
 
 
 def plan_dry_run(nr_bits, gates, tile_bits=12):

@@ -177,3 +177,60 @@ def test_execute_errors_surface_like_the_reference():
     with pytest.raises(QC.CircuitError) as ei:
         c.execute(4)
     assert str(ei.value) == "Expected 2 measurement bits, but got 1"
+
+
+def test_composite_and_loop_gates_flattened():
+    """SURVEY 8(f)2-3: a circuit that uses `Composite::from_string` descriptions and a `Loop`
+    (composite.rs:273-450, staticloop.rs:71-92) against the oracle fed with the same sub-gates one by one
+    (the reference applies a composite as the product of its sub-gates, composite.rs:487-501) and against
+    the composite's own matrix() used as one dense user gate."""
+    nq, shots = 9, 256
+    inc3 = "CCX 2 1 0; CX 2 1; X 2"
+    rot = "RY(pi/3) 0; CU1(pi/4) 0 1; H 1; CRZ(0.5*(1.0-0.26)) 1 0"
+    c = QC.Circuit(nq, nq)
+    for q in range(nq):
+        c.add_gate("h", [q])
+    c.add_composite_gate("Inc3", inc3, [6, 2, 4])
+    c.add_composite_gate("Rot", rot, [8, 0], nr_iterations=3)
+    c.add_composite_gate("Inc3", inc3, [0, 1, 2])
+    c.measure_all(list(range(nq)))
+    words = O.splitmix64_words(3, 4 * shots + 64)
+    c.execute(shots, E.Rng(words=words))
+
+    def sub(desc, bits, reps=1):
+        out = []
+        for _ in range(reps):
+            for part in desc.split(";"):
+                name = part.split("(")[0].split()[0]
+                args = ()
+                if "(" in part:
+                    inner = part[part.index("(") + 1:part.rindex(")")]
+                    depth, cur, args = 0, "", []
+                    for ch in inner:                      # split on top-level commas
+                        if ch == "," and depth == 0:
+                            args.append(cur); cur = ""
+                        else:
+                            depth += ch == "("; depth -= ch == ")"; cur += ch
+                    args = tuple(E.eval_expression(a)[0] for a in args + [cur])
+                    tail = part[part.rindex(")") + 1:]
+                else:
+                    tail = part.strip()[len(name):]
+                out.append(("gate", name.lower(), args, [bits[int(b)] for b in tail.split()]))
+        return out
+    ops = [("gate", "h", (), [q]) for q in range(nq)] + sub(inc3, [6, 2, 4]) + sub(rot, [8, 0], 3) + sub(inc3, [0, 1, 2])
+    o = O.OracleCircuit(nq, nq, mode=1, order=1)
+    W.load_ops(o, ops + [("measure_all", list(range(nq)), "Z")])
+    o.execute(shots, O.Rng(words=words))
+    assert np.array_equal(c.cstate(), o.cstate())
+    # the same circuit with each composite as ONE dense matrix gate
+    e = E.VectorState(nq, 1)
+    o2 = O.OracleState(nq, 1, mode=1, order=1)
+    for q in range(nq):
+        e.apply_gate(O.gate_matrix("h"), [q], "H")
+    e.apply_gate(E.composite_matrix(inc3), [6, 2, 4], "Inc3")
+    for _ in range(3):
+        e.apply_gate(E.composite_matrix(rot), [8, 0], "Rot")
+    e.apply_gate(E.composite_matrix(inc3), [0, 1, 2], "Inc3")
+    for op in ops:
+        o2.apply_gate(O.gate_matrix(op[1], op[2]), op[3])
+    assert rel_l2(e.column(0), o2.column(0)) < 1e-10
