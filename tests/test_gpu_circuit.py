@@ -221,7 +221,7 @@ def test_composite_and_loop_gates_flattened():
     o = O.OracleCircuit(nq, nq, mode=1, order=1)
     W.load_ops(o, ops + [("measure_all", list(range(nq)), "Z")])
     o.execute(shots, O.Rng(words=words))
-    assert np.array_equal(c.cstate(), o.cstate())
+    assert np.array_equal(c.cstate(), o.c_state)
     # the same circuit with each composite as ONE dense matrix gate
     e = E.VectorState(nq, 1)
     o2 = O.OracleState(nq, 1, mode=1, order=1)
