@@ -580,12 +580,47 @@ class ShardedState:
         self.apply_conditional_gate((m != 0).astype(np.uint8), x, [bit], "X")
 
     # ---- whole op lists with look-ahead ------------------------------------------------
+    _expand_cache = {}
+
+    def _expanded_ops(self, ops):
+        """circuit.rs:667-735: X- and Y-basis measurements / peeks are sandwiches of one-qubit gates
+        around the Z-basis operation (H ... H, resp. Sdg H ... H S); `measure_all` / `peek_all` apply
+        them to every qubit (`apply_unary_gate_all`).  Expanding them here lets the look-ahead
+        planner see those gates like any others."""
+        key = (id(ops), len(ops), self.n)
+        hit = ShardedState._expand_cache.get(key)
+        if hit is not None and hit[0] is ops:
+            return hit[1]
+        out = []
+        for op in ops:
+            k = op[0]
+            if k in ("measure", "peek") and op[3] in ("X", "Y"):
+                q = op[1]
+                pre = [("gate", "h", (), [q])] if op[3] == "X" else [("gate", "sdg", (), [q]), ("gate", "h", (), [q])]
+                post = [("gate", "h", (), [q])] if op[3] == "X" else [("gate", "h", (), [q]), ("gate", "s", (), [q])]
+                out += pre + [(k, op[1], op[2], "Z")] + post
+            elif k in ("measure_all", "peek_all") and op[2] in ("X", "Y"):
+                names_pre = ["h"] if op[2] == "X" else ["sdg", "h"]
+                names_post = ["h"] if op[2] == "X" else ["h", "s"]
+                for nm in names_pre:
+                    out += [("gate", nm, (), [q]) for q in range(self.n)]
+                out.append((k, op[1], "Z"))
+                for nm in names_post:
+                    out += [("gate", nm, (), [q]) for q in range(self.n)]
+            else:
+                out.append(op)
+        if len(ShardedState._expand_cache) > 32:
+            ShardedState._expand_cache.clear()
+        ShardedState._expand_cache[key] = (ops, out)
+        return out
+
     def run_ops(self, ops, gate_matrix, res=None, rng=None):
         """Apply an op list (q1tsim_b200.workloads format).  Knowing the future lets every
         remap evict the local qubit whose data is destined for that rank bit (following the
         remaining `Swap` relabels) and that no later gate touches non-diagonally, so the
         final canonicalisation usually needs no further exchange."""
         key = (id(ops), len(ops))
+        ops = self._expanded_ops(ops)
         cached = getattr(ShardedState, "_plan_cache", {}).get(key)
         if cached is not None and cached[0] == (self.n, self.g):
             _, mats, dest, busy, nxt = cached
@@ -620,6 +655,9 @@ class ShardedState:
                 for q in op[5]:
                     b[q] = True
                     x[q] = t
+            elif op[0] == "reset":
+                b[op[1]] = True
+                x[op[1]] = t
             dest[t], busy[t], nxt[t] = d, b, x
         if not hasattr(ShardedState, "_plan_cache"):
             ShardedState._plan_cache = {}
@@ -658,10 +696,14 @@ class ShardedState:
                     (self.measure_into if k == "measure" else self.peek_into)(op[1], op[2], res, rng)
                 elif k in ("measure_all", "peek_all") and op[2] == "Z":
                     (self.measure_all_into if k == "measure_all" else self.peek_all_into)(op[1], res, rng)
+                elif k == "reset":
+                    self.reset(op[1], rng)                 # vectorstate.rs:402-408
+                elif k == "reset_all":
+                    raise NotImplementedError("run_ops: reset_all in the middle of a sharded op list (start a new ShardedState)")
                 elif k == "barrier":
                     pass
                 else:
-                    raise NotImplementedError("run_ops: %r (basis-change sandwiches: use the single-GPU Circuit)" % (op,))
+                    raise NotImplementedError("run_ops: %r" % (op,))
         finally:
             self.lookahead = old
 

@@ -102,6 +102,18 @@ def _worker(rank, world, port, n, case, q):
             out["counts_equal"] = st.counts == ref.counts
             out["consumed"] = (rng_s.consumed, rng_o.consumed)
             out["col_err"] = float(max(np.linalg.norm(st.gather_column(c) - ref.column(c)) for c in range(ref.ncols)))
+        elif case == "run_ops_basis":
+            # cfg4-shaped op list through run_ops: X/Y/Z-basis mid-circuit measurements (circuit.rs:667-703),
+            # conditional gates on the classical word, a reset, X-basis measure_all at the end
+            ops = W.ghz_branching_ops(n)[:-1] + [("reset", 1), ("gate", "ry", (0.4,), [1]), ("peek", n - 1, 5, "Y"),
+                                                  ("measure_all", list(range(n)), "X")]
+            cs = np.zeros(shots, dtype=np.uint64)
+            st.run_ops(ops, G, cs, rng_s)
+            oc = O.OracleCircuit(n, n, mode=1, order=1)
+            W.load_ops(oc, ops)
+            oc.execute(shots, rng_o)
+            out["cstate_equal"] = bool(np.array_equal(cs, oc.c_state))
+            out["consumed"] = (rng_s.consumed, rng_o.consumed)
         q.put(out)
     finally:
         dist.destroy_process_group()
@@ -148,3 +160,10 @@ def test_sharded_branching(world, n):
         assert o["cstate_equal"] and o["counts_equal"]
         assert o["consumed"][0] == o["consumed"][1]
         assert o["col_err"] < 1e-12
+
+
+@pytest.mark.parametrize("world,n", [(2, 12), (4, 13)])
+def test_sharded_run_ops_basis_changes_and_reset(world, n):
+    for o in _run(world, n, "run_ops_basis"):
+        assert o["cstate_equal"]
+        assert o["consumed"][0] == o["consumed"][1]
