@@ -112,6 +112,8 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
     if (const char *e = std::getenv("Q1T_COALESCE_BITS")) { const long v = std::atol(e); if (v == 2 || v == 3) coalesce_bits_ = v; }
     if (const char *e = std::getenv("Q1T_BALANCE")) balance_ = std::atol(e);
     if (const char *e = std::getenv("Q1T_TRACK_SUPPORT")) track_support_ = std::atol(e) != 0;
+    if (const char *e = std::getenv("Q1T_SPARSE_C2")) sparse_c2_ = std::atol(e) != 0;
+    if (const char *e = std::getenv("Q1T_FUSE_LEAF")) fuse_leaf_totals_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
 }
 
@@ -508,8 +510,12 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             std::vector<int> dstpos(n_);
             for (int l = 0; l < n_; ++l) dstpos[perm_[l]] = l;
             if (can_fuse_relabel(ps.prog, dstpos)) {
-                set_relabel(ps.prog, dstpos);
+                const bool try_leaf = want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(ps.prog);
+                set_relabel(ps.prog, dstpos, try_leaf);
                 relabel = true;
+                if (ps.prog.leaf_fuse) {
+                    if (ps.prog.direct_store || ensure_scratch(which.size())) ps.prog.leaf_fuse = 0;   // needs the staged store pass
+                }
             }
         }
         if (!relabel) {
@@ -531,7 +537,8 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             double2 *h[2] = { col.buf, scratch };
             CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
             time_begin();
-            CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, d_gen_ ? d_gen_ + i : nullptr, stream_));
+            CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, d_gen_ ? d_gen_ + i : nullptr, stream_,
+                            ps.prog.leaf_fuse ? d_leaf_ + (i << (n_ - kCanonLeafBits)) : nullptr));
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
             double2 *old = col.buf;
@@ -540,6 +547,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
         }
         stats.sweeps++;
         stats.fused_relabels++;
+        if (ps.prog.leaf_fuse) leaf_fused_ = true;
         stats.sweep_column_passes += which.size();
         stats.sweep_bytes += (uint64_t)which.size() * bytes_moved[si];
         for (int l = 0; l < n_; ++l) perm_[l] = l;
@@ -591,7 +599,12 @@ int DeviceVectorState::run_queue(bool final_relabel)
                 const unsigned char *b = static_cast<const unsigned char *>(p);
                 for (size_t i = 0; i < nbytes; ++i) { key ^= b[i]; key *= 1099511628211ull; }
             };
-            const long cfg[4] = { (long)n_, tile_bits_, coalesce_bits_, (long)kRegBits };
+            // batches that start from basis states run with support tracking: their loads are negligible,
+            // so 64-byte tiles cost nothing and leave 10 (not 9) free bits per sweep -- provided every sweep
+            // of the plan qualifies for the ladder kernel (otherwise the dense default is planned)
+            bool sparse_start = sparse_c2_ && track_support_ && coalesce_bits_ == 3 && tile_bits_ == 12;
+            for (int c : which) sparse_start = sparse_start && cols_[c].basis && cols_[c].basis_idx != UINT64_MAX;
+            const long cfg[5] = { (long)n_, tile_bits_, coalesce_bits_, (long)kRegBits, (long)sparse_start };
             mix(cfg, sizeof cfg);
             for (const LoweredGate &g : q) {
                 const int hdr[5] = { (int)g.kind, g.nb, g.b[0], g.b[1], g.target };
@@ -612,15 +625,22 @@ int DeviceVectorState::run_queue(bool final_relabel)
             }
             std::vector<PlannedSweep> plan[2];
             uint64_t cost[2][2];
-            for (int b = 0; b < 2; ++b) {
-                Planner trial(n_, (int)tile_bits_, (int)coalesce_bits_, b != 0);
-                for (const LoweredGate &g : q) trial.add(g);
-                trial.finish();
-                cost[b][0] = trial.stats.sweeps;
-                cost[b][1] = trial.stats.rounds;
-                plan[b] = trial.take();
+            int pick = 0;
+            for (int attempt = sparse_start ? 0 : 1; attempt < 2; ++attempt) {
+                const int cbits = attempt == 0 ? 2 : (int)coalesce_bits_;
+                for (int b = 0; b < 2; ++b) {
+                    Planner trial(n_, (int)tile_bits_, cbits, b != 0);
+                    for (const LoweredGate &g : q) trial.add(g);
+                    trial.finish();
+                    cost[b][0] = trial.stats.sweeps;
+                    cost[b][1] = trial.stats.rounds;
+                    plan[b] = trial.take();
+                }
+                pick = (cost[1][0] < cost[0][0] || (cost[1][0] == cost[0][0] && cost[1][1] < cost[0][1])) ? 1 : 0;
+                bool all_ladder = true;
+                for (const PlannedSweep &ps : plan[pick]) all_ladder = all_ladder && sweep_uses_ladder_kernel(ps.prog);
+                if (attempt == 0 && all_ladder) break;            // the 64-byte plan will be tracked
             }
-            const int pick = (cost[1][0] < cost[0][0] || (cost[1][0] == cost[0][0] && cost[1][1] < cost[0][1])) ? 1 : 0;
             if (q.size() >= 16) {
                 std::lock_guard<std::mutex> lk(g_plan_mu);
                 if (g_plan_cache.size() >= kPlanCacheMax) {       // evict the least recently used plan
@@ -833,7 +853,8 @@ int DeviceVectorState::ensure_scratch(size_t ncols)
 
 // canonical totals of |amp|^2 over amplitudes with (index & mask) == want, for
 // every device-resident column; leaves d_leaf_/d_block_ holding the prefixes
-int DeviceVectorState::reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols)
+int DeviceVectorState::reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols,
+                                      bool leaf_totals_ready)
 {
     dev_cols.clear();
     for (size_t c = 0; c < cols_.size(); ++c)
@@ -845,11 +866,14 @@ int DeviceVectorState::reduce_columns(uint64_t mask, uint64_t want, std::vector<
     rc = upload_colptrs(dev_cols);
     if (rc) return rc;
     time_begin();
-    CK(launch_leaf_totals(d_colptrs_, (int)dev_cols.size(), d_leaf_, n_, mask, want, stream_));
+    if (!leaf_totals_ready) {              // else: the last sweep's store pass has already left them in d_leaf_
+        CK(launch_leaf_totals(d_colptrs_, (int)dev_cols.size(), d_leaf_, n_, mask, want, stream_));
+        stats.kernel_launches += 1;
+        stats.read_passes += dev_cols.size();
+    }
     CK(launch_scan(d_leaf_, d_block_, d_totals_, (int)dev_cols.size(), n_, stream_));
     time_end(stats.read_ms);
-    stats.kernel_launches += 3;
-    stats.read_passes += dev_cols.size();
+    stats.kernel_launches += 2;
     CK(cudaMemcpyAsync(totals.data(), d_totals_, sizeof(double) * dev_cols.size(), cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     return Q1T_OK;
@@ -1200,11 +1224,15 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
     if (!res || !cbits || !rng.next_u64) return fail(Q1T_ERR_INVALID_ARGUMENT, "NULL pointer argument");
     for (size_t j = 0; j < ncbits; ++j)
         if (cbits[j] >= 64) return fail(Q1T_ERR_INVALID_ARGUMENT, "classical bit index must be < 64");
+    want_leaf_fusion_ = fuse_leaf_totals_;
+    leaf_fused_ = false;
     int rc = flush();
+    const bool leaf_ready = leaf_fused_;
+    want_leaf_fusion_ = leaf_fused_ = false;
     if (rc) return rc;
     std::vector<double> totals;
     std::vector<int> dev;
-    rc = reduce_columns(0, 0, totals, dev);
+    rc = reduce_columns(0, 0, totals, dev, leaf_ready);
     if (rc) return rc;
     const int leaf_bits = n_ < kCanonLeafBits ? n_ : kCanonLeafBits;
     const size_t nleaves = (size_t)1 << (n_ - leaf_bits);
@@ -1364,6 +1392,16 @@ int DeviceVectorState::set_option(const char *key, long value)
         int rc = run_queue();
         if (rc) return rc;
         balance_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "fuse_leaf_totals")) {
+        fuse_leaf_totals_ = value != 0;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "sparse_c2")) {
+        int rc = run_queue();
+        if (rc) return rc;
+        sparse_c2_ = value != 0;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "track_support")) {

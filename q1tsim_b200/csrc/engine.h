@@ -79,6 +79,9 @@ private:
     std::string err_;
     long tile_bits_ = 12;
     long coalesce_bits_ = 3;                 // low index bits kept contiguous per tile (3 = 128 B, 2 = 64 B)
+    bool sparse_c2_ = true;                  // batches that start from basis states: 64-byte tiles (10 free bits per sweep)
+    bool fuse_leaf_totals_ = true;           // measure_all: leaf totals produced by the last sweep's store pass
+    bool want_leaf_fusion_ = false, leaf_fused_ = false;   // handshake between measure_all_into and run_sweeps
     bool track_support_ = true;              // skip what is known to be zero while a batch starts from basis states
     long balance_ = -1;                      // sweep packing: -1 try both, 0 greedy, 1 balanced
     long prefetch_ahead_ = 0;
@@ -110,7 +113,8 @@ private:
     int run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel);
     int run_generic(const LoweredGate &g, const std::vector<int> &which);
     int canonicalize();                      // undo swap relabelling (perm_ -> identity)
-    int reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols);
+    int reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols,
+                       bool leaf_totals_ready = false);
     int ensure_scratch(size_t ncols);
     int lower_and_queue(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc);
     void time_begin();

@@ -574,7 +574,7 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
-              const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx)
+              const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx, double *__restrict__ leaf_out)
 {
     extern __shared__ double2 tile[];
     const SweepProgram &P = c_prog;
@@ -596,6 +596,9 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     const bool generate = P.generate != 0;
     const bool staged_store = P.direct_store == 0;
     const double scale = P.scale;
+    // fused canonical leaf totals (one leaf of 1024 amplitudes per warp in the staged store pass)
+    const bool leaf_fuse = P.leaf_fuse != 0 && leaf_out != nullptr && staged_store;
+    double *__restrict__ const leaf_col = leaf_fuse ? leaf_out + ((unsigned long long)col << (P.n - 10)) : nullptr;
     const double2 *__restrict__ const src = src_cols[col];
     double2 *__restrict__ const dst = dst_cols[col];
 
@@ -641,6 +644,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         if (staged_store) {
 #pragma unroll
             for (int i = 0; i < kSlots; ++i) st_global_cs(q + P.st_off_hi[i], z);
+            if (leaf_fuse && (tid & 31) == 0) leaf_col[(outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]) >> 10] = 0.0;
         } else {
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) st_global_cs(q + P.ds_slot[s], z);
@@ -841,13 +845,17 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
             unsigned swl = sw_lo;
             asm volatile("" : "+r"(swl));     // as in issue_loads: no hoisting of the 32 addresses
+            double leaf_acc = 0.0;
             {   // first half: read and store right away
                 double2 v[kSlots / 2];
 #pragma unroll
                 for (int i = 0; i < kSlots / 2; ++i) v[i] = *reinterpret_cast<const double2 *>(tile_b + (swl ^ P.st_l_hi[i]));
 #pragma unroll
-                for (int i = 0; i < kSlots / 2; ++i)
-                    st_global_cs(q + P.st_off_hi[i], scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i]);
+                for (int i = 0; i < kSlots / 2; ++i) {
+                    const double2 x = scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i];
+                    if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
+                    st_global_cs(q + P.st_off_hi[i], x);
+                }
             }
             PCLK(11);
             {   // second half: once it is in registers the tile is dead -> prefetch, then store
@@ -864,8 +872,18 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 }
                 PCLK(14);
 #pragma unroll
-                for (int i = 0; i < kSlots / 2; ++i)
-                    st_global_cs(q + P.st_off_hi[kSlots / 2 + i], scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i]);
+                for (int i = 0; i < kSlots / 2; ++i) {
+                    const double2 x = scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i];
+                    if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
+                    st_global_cs(q + P.st_off_hi[kSlots / 2 + i], x);
+                }
+            }
+            if (leaf_fuse) {
+                // lane l has summed elements l, l+32, ... of its warp's leaf in increasing order: finish
+                // with the canonical 5-stage butterfly (same arithmetic as leaf_totals_kernel)
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) leaf_acc = __dadd_rn(leaf_acc, __shfl_xor_sync(0xffffffffu, leaf_acc, off));
+                if ((tid & 31) == 0) leaf_col[(outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]) >> 10] = leaf_acc;
             }
         }
         PCLK(9);
@@ -896,7 +914,8 @@ bool sweep_uses_ladder_kernel(const SweepProgram &prog)
 }
 
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
-                         int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream)
+                         int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
+                         double *d_leaf_out)
 {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
@@ -946,7 +965,7 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         if (per_col < 1) per_col = 1;
         if (per_col > (1ull << prog.n_outer)) per_col = 1ull << prog.n_outer;
         dim3 pgrid((unsigned)per_col, (unsigned)ncols, 1);
-        ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+        ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out);
         return cudaGetLastError();
     }
     if (ladders_only && (int)block.x <= kSmallThreads)

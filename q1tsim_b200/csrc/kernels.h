@@ -17,8 +17,11 @@ struct GenericGateArgs {
     unsigned long long cmask;                         // control positions that must be 1
 };
 
+// d_leaf_out: when prog.leaf_fuse is set (ladder kernel, staged store), receives the canonical leaf totals
+// of the written column(s), 2^(n-10) doubles per column (what launch_leaf_totals would compute afterwards)
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
-                         int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream);
+                         int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
+                         double *d_leaf_out = nullptr);
 // true if launch_sweep() runs this program in the persistent ladder kernel (the one that honours
 // SweepProgram::sup_mask / sup_mode)
 bool sweep_uses_ladder_kernel(const SweepProgram &prog);

@@ -705,7 +705,7 @@ void Planner::close_sweep()
 // Fill the destination side of a program whose source side (tsrc, osrc, T, TB)
 // is set.  The store is coalesced when the tile contains the sources of the low
 // destination bits.
-void set_relabel(SweepProgram &P, const std::vector<int> &dstpos)
+void set_relabel(SweepProgram &P, const std::vector<int> &dstpos, bool leaf_split)
 {
     const int T = P.T;
     bool ident = true;
@@ -716,6 +716,20 @@ void set_relabel(SweepProgram &P, const std::vector<int> &dstpos)
     for (int i = 0; i < T; ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](int a, int b) { return P.tdst[a] < P.tdst[b]; });
     for (int i = 0; i < T; ++i) P.st_tb[i] = (uint8_t)order[i];
+    P.leaf_fuse = 0;
+    if (leaf_split && T == 12 && P.TB == 7 && kRegBits == 5) {
+        bool whole_leaves = true;
+        for (int i = 0; i < 10; ++i) whole_leaves = whole_leaves && P.tdst[order[i]] == i;
+        if (whole_leaves) {
+            // thread bits: destination bits 0..4 (lanes) and the two tile bits above the leaf (warps);
+            // slot bits: destination bits 5..9 -> slot i of lane l is element l + 32 i of the warp's leaf
+            const int sel[12] = { 0, 1, 2, 3, 4, 10, 11, 5, 6, 7, 8, 9 };
+            std::vector<int> o2(T);
+            for (int i = 0; i < T; ++i) o2[i] = order[sel[i]];
+            order = o2;
+            P.leaf_fuse = 1;
+        }
+    }
     int pos[kMaxThrBits + 1];
     for (int i = 0; i < P.TB; ++i) pos[i] = P.tdst[order[i]];
     P.st_nruns = make_runs(pos, P.TB, P.st_runs);

@@ -117,7 +117,9 @@ private:
 // relabelling sweep: dstpos[p] = destination position of source bit p
 PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos);
 // turn the store side of an existing sweep into a relabelling one (out-of-place launch required)
-void set_relabel(SweepProgram &P, const std::vector<int> &dstpos);
+// leaf_split: if the tile holds destination bits 0..9 (whole canonical leaves of 1024 amplitudes), lay the
+// store pass out as one leaf per warp (lanes = destination bits 0..4, slots = bits 5..9) and set P.leaf_fuse
+void set_relabel(SweepProgram &P, const std::vector<int> &dstpos, bool leaf_split = false);
 bool can_fuse_relabel(const SweepProgram &P, const std::vector<int> &dstpos);
 
 // reduce an angle in half-turns to [-1, 1)

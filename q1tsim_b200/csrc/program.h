@@ -102,7 +102,8 @@ struct SweepProgram {
     // a batch: the column leaves dense); 0: no tracking.
     uint64_t sup_mask;
     int32_t sup_mode;
-    int32_t pad_sup;
+    int32_t leaf_fuse;    // staged (relabelling) store laid out one canonical leaf per warp: the store pass also
+                          // produces the leaf totals of abs(amp)^2 in the canonical order
     double gen_scale;     // value of the basis element of a generated input (1, or the normalisation of the whole batch of sweeps)
     // tile bits are numbered by ascending source position; outer bits likewise
     uint8_t tsrc[kMaxTileBits + 3], tdst[kMaxTileBits + 3];

@@ -450,3 +450,41 @@ def test_conditional_swap_moves_only_flagged_columns():
     assert e.counts == o.counts
     for c in range(len(o.counts)):
         assert rel_l2(e.column(c), o.column(c)) < TOL
+
+
+@pytest.mark.parametrize("n,prep", [(12, "zero"), (14, "zero"), (17, "zero"), (20, "zero"), (12, "collapsed"), (14, "collapsed"),
+                                    (13, "dense"), (20, "collapsed")])
+def test_measure_all_after_qft_fused_leaf_totals(n, prep):
+    """measure_all right after a QFT: when the last sweep's tile holds whole canonical leaves its store pass
+    also produces the leaf totals (no separate read pass).  Outcomes must stay bit-exact (canonical order,
+    DESIGN.md 4.2) against the oracle and against the unfused path."""
+    shots = 2000
+    outs = []
+    for fuse in (1, 0):
+        e, o = E.VectorState(n, shots), O.OracleState(n, shots, mode=1, order=1)
+        e.set_option("fuse_leaf_totals", fuse)
+        words = O.splitmix64_words(21, 3 * shots + 64)
+        re_, ro = np.zeros(shots, dtype=np.uint64), np.zeros(shots, dtype=np.uint64)
+        rng_e, rng_o = E.Rng(words=words), O.Rng(words=words)
+        if prep == "collapsed":
+            for q in range(0, n, 2):
+                m = O.gate_matrix("h"); e.apply_gate(m, [q], "H"); o.apply_gate(m, [q])
+            e.measure_all_into(list(range(n)), re_, rng_e); o.measure_all_into(list(range(n)), ro, rng_o)
+            assert np.array_equal(re_, ro)
+        elif prep == "dense":
+            for op in W.u3_layer_ops(n, seed=4):
+                m = O.gate_matrix(op[1], op[2]); e.apply_gate(m, op[3], op[1]); o.apply_gate(m, op[3])
+            e.flush()
+        e.reset_stats()
+        for op in W.qft_ops(n, measure=False):
+            m = O.gate_matrix(op[1], op[2]); e.apply_gate(m, op[3], op[1]); o.apply_gate(m, op[3])
+        e.measure_all_into(list(range(n)), re_, rng_e); o.measure_all_into(list(range(n)), ro, rng_o)
+        assert np.array_equal(re_, ro), "outcomes differ from the oracle (fuse=%d)" % fuse
+        assert e.counts == o.counts
+        st = e.stats()
+        if prep == "zero" and n in (12, 20):
+            # QFT-12 is one tile, QFT-20 two sweeps of 10 bits: the last tile holds whole leaves of 1024
+            assert st["read_passes"] == (0 if fuse else 1)       # fused: no leaf_totals launch at all
+        outs.append(re_.copy())
+        e.close()
+    assert np.array_equal(outs[0], outs[1])
