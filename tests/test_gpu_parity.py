@@ -453,7 +453,7 @@ def test_conditional_swap_moves_only_flagged_columns():
 
 
 @pytest.mark.parametrize("n,prep", [(12, "zero"), (14, "zero"), (17, "zero"), (20, "zero"), (12, "collapsed"), (14, "collapsed"),
-                                    (13, "dense"), (20, "collapsed")])
+                                    (13, "dense")])
 def test_measure_all_after_qft_fused_leaf_totals(n, prep):
     """measure_all right after a QFT: when the last sweep's tile holds whole canonical leaves its store pass
     also produces the leaf totals (no separate read pass).  Outcomes must stay bit-exact (canonical order,
