@@ -60,6 +60,7 @@ typedef struct {
 /* circuit-level variants (used by the outer ABI, include/q1tsim_ffi.h) */
 #define Q1T_ERR_INVALID_CBIT (-10)                /* Error::InvalidCBit */
 #define Q1T_ERR_NOT_EXECUTED (-11)                /* Error::NotExecuted */
+#define Q1T_ERR_EXPORT (-13)                      /* Error::ExportError */
 #define Q1T_ERR_PARSE (-12)                       /* Error::ParseError(UnknownGate | InvalidNrArguments) */
 
 /* ---- construction: VectorState::new / from_qubit_coefs (vectorstate.rs:41-83) ---- */

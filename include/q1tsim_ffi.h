@@ -9,9 +9,10 @@
  *   - circuit_execute always runs the statevector backend on the GPU (the
  *     reference switches to its stabilizer backend for all-Clifford circuits,
  *     circuit.rs:576-583, which is out of scope here);
- *   - circuit_latex / circuit_open_qasm / circuit_c_qasm return an error result
- *     (text exporters are out of scope);
- *   - extra entry points: circuit_add_matrix_gate, circuit_add_composite_gate, circuit_execute_with_rng,
+ *   - circuit_open_qasm / circuit_c_qasm produce the reference's text (circuit.rs:877-1146);
+ *     circuit_latex returns an error result (the qcircuit drawing back-end is out of scope);
+ *   - extra entry points: circuit_add_matrix_gate, circuit_add_composite_gate, circuit_add_loop_gate,
+ *     circuit_execute_with_rng,
  *     circuit_reexecute_with_rng, circuit_histogram_u64, circuit_engine_stats,
  *     circuit_set_device, circuit_state.
  * Ownership (ffi.rs:139-169): every result_t is returned by value and owns
@@ -59,8 +60,8 @@ result_t   circuit_execute(circuit_t *ptr, size_t nr_shots);                 /* 
 result_t   circuit_reexecute(circuit_t *ptr);                                /* ffi.rs:588-603 */
 result_t   circuit_histogram(const circuit_t *ptr);                          /* ffi.rs:606-621 */
 result_t   circuit_latex(const circuit_t *ptr);                              /* ffi.rs:624-639 (out of scope: error) */
-result_t   circuit_open_qasm(const circuit_t *ptr);                          /* ffi.rs:643-658 (out of scope: error) */
-result_t   circuit_c_qasm(const circuit_t *ptr);                             /* ffi.rs:661-676 (out of scope: error) */
+result_t   circuit_open_qasm(const circuit_t *ptr);                          /* ffi.rs:643-658; circuit.rs:877-1017 */
+result_t   circuit_c_qasm(const circuit_t *ptr);                             /* ffi.rs:661-676; circuit.rs:1019-1146 */
 
 /* ---- additive entry points ---- */
 /* arbitrary user gate given by its matrix() (gates.rs:174), row-major (re,im) */
@@ -76,6 +77,11 @@ result_t   circuit_barrier(circuit_t *ptr, const size_t *qbits, size_t nr_qbits)
  * ParseError texts (error.rs:93-127) and "Expected {} bits for \"{}\", got {}". */
 result_t   circuit_add_composite_gate(circuit_t *ptr, const char *name, const char *description,
                                       const size_t *qbits, size_t nr_qbits, size_t nr_iterations);
+/* Loop::new(label, nr_iterations, Composite::from_string(label, body)) (staticloop.rs:38-50): like
+ * circuit_add_composite_gate, but exported as a loop (`.label(n) ... .end` in c-Qasm) even for one
+ * iteration.  A loop of 0 iterations adds nothing (the reference keeps an empty instruction). */
+result_t   circuit_add_loop_gate(circuit_t *ptr, const char *label, const char *body_description,
+                                 const size_t *qbits, size_t nr_qbits, size_t nr_iterations);
 size_t     circuit_nr_ops(const circuit_t *ptr);
 /* execute_with_rng / reexecute_with_rng (circuit.rs:573-641) with a caller-owned generator */
 result_t   circuit_execute_with_rng(circuit_t *ptr, size_t nr_shots, q1t_rng rng);

@@ -40,7 +40,7 @@ OUTER_ABI_SYMBOLS = [
     "circuit_add_matrix_gate", "circuit_add_conditional_matrix_gate", "circuit_barrier", "circuit_execute_with_rng",
     "circuit_reexecute_with_rng", "circuit_execute_with_qubit_coefs", "circuit_histogram_u64", "circuit_cstate_into",
     "circuit_set_cstate", "circuit_set_device", "circuit_state", "circuit_engine_stats", "circuit_add_composite_gate",
-    "circuit_nr_ops",
+    "circuit_add_loop_gate", "circuit_nr_ops",
 ]
 
 _bound = False
@@ -69,6 +69,7 @@ def _lib():
         "circuit_add_conditional_matrix_gate": (R, [vp, szp, sz, C.c_uint64, C.c_char_p, dp, sz, szp, sz]),
         "circuit_barrier": (R, [vp, szp, sz]),
         "circuit_add_composite_gate": (R, [vp, C.c_char_p, C.c_char_p, szp, sz, sz]),
+        "circuit_add_loop_gate": (R, [vp, C.c_char_p, C.c_char_p, szp, sz, sz]),
         "circuit_nr_ops": (sz, [vp]),
         "circuit_execute_with_rng": (R, [vp, sz, RNG]), "circuit_reexecute_with_rng": (R, [vp, RNG]),
         "circuit_execute_with_qubit_coefs": (R, [vp, sz, RNG, dp]),
@@ -190,6 +191,11 @@ class Circuit:
         q, nq = _sz(qbits)
         return _unpack(self._L.circuit_add_composite_gate(self._p, name.encode(), description.encode(), q, nq, int(nr_iterations)))
 
+    def add_loop_gate(self, label, body_description, qbits, nr_iterations):
+        """`Loop::new(label, nr_iterations, body)` (staticloop.rs:38-50): flattened like a composite, exported as a loop"""
+        q, nq = _sz(qbits)
+        return _unpack(self._L.circuit_add_loop_gate(self._p, label.encode(), body_description.encode(), q, nq, int(nr_iterations)))
+
     def nr_ops(self):
         return int(self._L.circuit_nr_ops(self._p))
 
@@ -296,6 +302,16 @@ class Circuit:
         for k, v in self.histogram_u64().items():
             out[k] = v
         return out
+
+    # ---- export (circuit.rs:877-1146; python/q1tsim.py open_qasm / c_qasm / latex) ----
+    def open_qasm(self):
+        return _unpack(self._L.circuit_open_qasm(self._p))
+
+    def c_qasm(self):
+        return _unpack(self._L.circuit_c_qasm(self._p))
+
+    def latex(self):
+        return _unpack(self._L.circuit_latex(self._p))
 
     def engine_stats(self):
         s = E.Stats()

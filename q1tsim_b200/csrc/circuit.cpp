@@ -34,7 +34,7 @@ static CircuitError invalid_cbit(size_t b)
 // description(): "H", "CX", "RX(1.2300)", "S†" ... (src/gates/*.rs `description`)
 std::string GateSpec::description(bool with_values) const
 {
-    if (name.empty()) return "matrix gate";
+    if (name.empty()) return user_desc.empty() ? "matrix gate" : user_desc;
     // every table name that starts with 'c' is C<..> of a base gate (controlled.rs:402-552)
     std::string inner = name, prefix;
     while (inner.size() > 1 && inner[0] == 'c') { prefix += "C"; inner = inner.substr(1); }

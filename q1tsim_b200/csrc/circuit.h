@@ -27,6 +27,7 @@ struct GateSpec {
     std::vector<Param> params;
     std::vector<std::complex<double>> matrix;   // user gate: matrix() given directly
     size_t nr_bits = 0;
+    std::string user_desc;             // description() of a matrix gate, as given by the caller
     std::string description(bool with_values = true) const;
     // evaluate matrix() now (gates read their parameters at execution time)
     int evaluate(std::vector<std::complex<double>> &out) const;
@@ -40,6 +41,11 @@ struct CircuitOp {       // circuit.rs:27-51
     uint64_t target = 0;
     size_t qbit = 0, cbit = 0;
     Basis basis = Basis::Z;
+    // sub-gate of a flattened Composite / Loop (add_composite): the exporters print the group as the
+    // single instruction it is in the reference's op list
+    size_t group_id = 0, group_repeat = 1;
+    bool group_loop = false;
+    std::string group_name;
 };
 
 struct CircuitError {
@@ -66,7 +72,8 @@ public:
     CircuitError barrier(const std::vector<size_t> &qbits);
     // Composite::from_string (composite.rs:273-450) / Loop (staticloop.rs:71-92): the sub-gates of the
     // description are flattened into the op list on `bits`, the body `repeat` times
-    CircuitError add_composite(const std::string &name, const std::string &desc, const std::vector<size_t> &bits, size_t repeat = 1);
+    CircuitError add_composite(const std::string &name, const std::string &desc, const std::vector<size_t> &bits, size_t repeat = 1,
+                               bool is_loop = false);
     size_t nr_ops() const { return ops_.size(); }
 
     CircuitError execute(size_t nr_shots, q1t_rng rng, const double *qubit_coefs = nullptr);
@@ -77,6 +84,9 @@ public:
     CircuitError set_cstate(const uint64_t *w, size_t n);
     std::map<uint64_t, size_t> histogram() const;
     std::map<std::string, size_t> histogram_string() const;
+    // export.cpp: circuit.rs:877-1146
+    CircuitError open_qasm(std::string &out) const;
+    CircuitError c_qasm(std::string &out) const;
     DeviceVectorState *state() { return q_state_.get(); }
     int device = 0;
 
@@ -86,6 +96,8 @@ private:
     bool has_cstate_ = false;
     std::vector<uint64_t> c_state_;
     std::vector<CircuitOp> ops_;
+    size_t next_group_ = 0;
+    size_t export_group(size_t at, const std::vector<std::string> &names, bool cq, std::string &out, CircuitError &err) const;
     CircuitError state_err(int rc);
     CircuitError do_execute(q1t_rng rng);
 };

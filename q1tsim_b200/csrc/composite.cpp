@@ -325,7 +325,8 @@ bool parse_composite(const std::string &desc, std::vector<SubGateDesc> &out, siz
 
 // Flatten: sub-gate bit i of the composite -> bits[i]; the body is appended `repeat` times
 // (Loop::apply_slice, staticloop.rs:78-84).  Every sub-gate is validated like a gate added directly.
-CircuitError Circuit::add_composite(const std::string &name, const std::string &desc, const std::vector<size_t> &bits, size_t repeat)
+CircuitError Circuit::add_composite(const std::string &name, const std::string &desc, const std::vector<size_t> &bits, size_t repeat,
+                                    bool is_loop)
 {
     std::vector<SubGateDesc> subs;
     size_t k = 0;
@@ -350,7 +351,14 @@ CircuitError Circuit::add_composite(const std::string &name, const std::string &
             e = add_gate(spec, mapped);
             if (e) break;
         }
-    if (e) ops_.erase(ops_.begin() + (long)mark, ops_.end());      // all or nothing
+    if (e) { ops_.erase(ops_.begin() + (long)mark, ops_.end()); return e; }      // all or nothing
+    ++next_group_;
+    for (size_t i = mark; i < ops_.size(); ++i) {
+        ops_[i].group_id = next_group_;
+        ops_[i].group_repeat = repeat;
+        ops_[i].group_loop = is_loop;
+        ops_[i].group_name = name;
+    }
     return e;
 }
 

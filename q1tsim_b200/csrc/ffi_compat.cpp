@@ -138,7 +138,7 @@ static bool make_matrix_gate(const char *desc, const double *m, size_t dim, Gate
     g.nr_bits = k;
     g.matrix.resize(dim * dim);
     std::memcpy(static_cast<void *>(g.matrix.data()), m, sizeof(double) * 2 * dim * dim);
-    (void)desc;
+    if (desc) g.user_desc = desc;
     return true;
 }
 
@@ -174,7 +174,17 @@ result_t circuit_add_composite_gate(circuit_t *ptr, const char *name, const char
     if (!qbits && nr_qbits) return res_error("Pointer to bit indices is NULL");
     if (!description) return res_error("Invalid gate description");
     return res_from(ptr->impl.add_composite(name ? name : "composite", description,
-                                            std::vector<size_t>(qbits, qbits + nr_qbits), nr_iterations));
+                                            std::vector<size_t>(qbits, qbits + nr_qbits), nr_iterations, nr_iterations != 1));
+}
+
+result_t circuit_add_loop_gate(circuit_t *ptr, const char *label, const char *body_description,
+                               const size_t *qbits, size_t nr_qbits, size_t nr_iterations)
+{
+    if (!ptr) return res_error("Pointer to circuit is NULL");
+    if (!qbits && nr_qbits) return res_error("Pointer to bit indices is NULL");
+    if (!body_description) return res_error("Invalid gate description");
+    return res_from(ptr->impl.add_composite(label ? label : "loop", body_description,
+                                            std::vector<size_t>(qbits, qbits + nr_qbits), nr_iterations, true));
 }
 
 size_t circuit_nr_ops(const circuit_t *ptr) { return ptr ? ptr->impl.nr_ops() : 0; }
@@ -286,20 +296,27 @@ result_t circuit_set_cstate(circuit_t *ptr, const uint64_t *words, size_t n)
     return res_from(ptr->impl.set_cstate(words, n));
 }
 
+static result_t res_string(const std::string &text) { result_t r = { dup_cstring(text), 0, 0, RESULT_STRING }; return r; }
+
 result_t circuit_latex(const circuit_t *ptr)
 {
-    (void)ptr;
-    return res_error("Operation latex is not implemented by the B200 statevector engine (text exporters are out of scope)");
+    if (!ptr) return res_error("Pointer to circuit is NULL");
+    // ExportError::NotImplemented wording (error.rs:53-55); the qcircuit drawing back-end is out of scope
+    return res_error("Export to LaTeX was not implemented for \"the B200 statevector engine\"");
 }
 result_t circuit_open_qasm(const circuit_t *ptr)
 {
-    (void)ptr;
-    return res_error("Operation open_qasm is not implemented by the B200 statevector engine (text exporters are out of scope)");
+    if (!ptr) return res_error("Pointer to circuit is NULL");
+    std::string text;
+    const CircuitError e = ptr->impl.open_qasm(text);
+    return e.code ? res_error(e.msg) : res_string(text);
 }
 result_t circuit_c_qasm(const circuit_t *ptr)
 {
-    (void)ptr;
-    return res_error("Operation c_qasm is not implemented by the B200 statevector engine (text exporters are out of scope)");
+    if (!ptr) return res_error("Pointer to circuit is NULL");
+    std::string text;
+    const CircuitError e = ptr->impl.c_qasm(text);
+    return e.code ? res_error(e.msg) : res_string(text);
 }
 
 int circuit_set_device(circuit_t *ptr, int device)

@@ -1,0 +1,191 @@
+"""OpenQasm / c-Qasm export, q1tsim_b200/csrc/export.cpp, pinned to the reference's own
+unit tests: circuit.rs:1987-2158 (whole circuits), the per-gate `test_open_qasm` / `test_c_qasm` of
+src/gates/*.rs, controlled.rs:691-817, composite.rs:1619-1666, staticloop.rs:324-376,
+export/openqasm.rs:53-60.  The reference tests name the bits qb0, qb1, ...; a circuit names them
+q[0], q[1], ... (circuit.rs:893-899), so the expected strings are transcribed with that renaming.
+Host-side text only: no GPU needed."""
+import math
+
+import pytest
+
+from q1tsim_b200 import circuit as QC
+
+OQ_HEAD = 'OPENQASM 2.0;\ninclude "qelib1.inc";\n'
+
+
+def _q(text):
+    for i in range(3):
+        text = text.replace("qb%d" % i, "q[%d]" % i)
+    return text
+
+
+def _gate_lines(name, bits, params=(), nq=3):
+    with QC.Circuit(nq, nq) as c:
+        c.add_gate(name, bits, params)
+        oq, cq = c.open_qasm(), c.c_qasm()
+    head = OQ_HEAD + "qreg q[%d];\ncreg b[%d];\n" % (nq, nq)
+    assert oq.startswith(head) and oq.endswith(";\n")
+    chead = "version 1.0\nqubits %d\n" % nq
+    assert cq.startswith(chead) and cq.endswith("\n")
+    return oq[len(head):-2], cq[len(chead):-1]
+
+
+def test_circuit_open_qasm():
+    # circuit.rs:1987-2016
+    with QC.Circuit(2, 2) as c:
+        c.x(0); c.cx(0, 1); c.barrier([0, 1]); c.cx(1, 0); c.barrier([1]); c.cx(0, 1); c.barrier([1, 0])
+        c.measure_x(0, 0); c.measure_y(1, 1)
+        assert c.open_qasm() == OQ_HEAD + (
+            "qreg q[2];\ncreg b[2];\nx q[0];\ncx q[0], q[1];\nbarrier q;\ncx q[1], q[0];\nbarrier q[1];\n"
+            "cx q[0], q[1];\nbarrier q[1], q[0];\nh q[0];\nmeasure q[0] -> b[0];\nsdg q[1];\nh q[1];\nmeasure q[1] -> b[1];\n")
+    # circuit.rs:2018-2039
+    with QC.Circuit(2, 2) as c:
+        c.x(0); c.measure_all([0, 1]); c.measure_all([1, 0]); c.measure_all_basis([0, 1], "X"); c.measure_all_basis([0, 1], "Y")
+        assert c.open_qasm() == OQ_HEAD + (
+            "qreg q[2];\ncreg b[2];\nx q[0];\nmeasure q -> b;\nmeasure q[0] -> b[1];\nmeasure q[1] -> b[0];\n"
+            "h q;\nmeasure q -> b;\nsdg q;\nh q;\nmeasure q -> b;\n")
+    # circuit.rs:2041-2057
+    with QC.Circuit(2, 0) as c:
+        c.x(0); c.h(1); c.reset(0); c.x(0); c.reset_all()
+        assert c.open_qasm() == OQ_HEAD + "qreg q[2];\nx q[0];\nh q[1];\nreset q[0];\nx q[0];\nreset q;\n"
+    # circuit.rs:2059-2075
+    with QC.Circuit(2, 2) as c:
+        c.x(0); c.measure_all([0, 1]); c.add_conditional_gate([0, 1], 1, "x", [0]); c.add_conditional_gate([], 1, "x", [1])
+        assert c.open_qasm() == OQ_HEAD + "qreg q[2];\ncreg b[2];\nx q[0];\nmeasure q -> b;\nif (b == 1) x q[0];\nx q[1];\n"
+    # circuit.rs:2077-2080: condition on part of the register
+    with QC.Circuit(2, 2) as c:
+        c.add_conditional_gate([0], 1, "x", [0])
+        with pytest.raises(QC.CircuitError, match="complete classical register"):
+            c.open_qasm()
+
+
+def test_open_qasm_condition_bits_in_any_order():
+    # circuit.rs:919-927: control bit k of the target word is classical bit control[k]
+    with QC.Circuit(1, 3) as c:
+        c.add_conditional_gate([2, 0, 1], 0b011, "h", [0])
+        assert c.open_qasm().endswith("if (b == 5) h q[0];\n")
+
+
+def test_circuit_c_qasm():
+    # circuit.rs:2084-2107
+    with QC.Circuit(3, 3) as c:
+        c.x(0); c.cx(0, 1); c.cx(1, 0); c.cx(0, 1); c.measure(0, 0); c.measure_x(1, 1); c.measure_y(2, 2)
+        assert c.c_qasm() == ("version 1.0\nqubits 3\nx q[0]\ncnot q[0], q[1]\ncnot q[1], q[0]\ncnot q[0], q[1]\n"
+                              "measure q[0]\nmeasure_x q[1]\nmeasure_y q[2]\n")
+    # circuit.rs:2109-2135
+    with QC.Circuit(2, 2) as c:
+        c.x(0); c.h(1); c.measure_all([0, 1]); c.reset_all(); c.measure_all_basis([0, 1], "X"); c.reset(1)
+        c.measure_all_basis([0, 1], "Y")
+        assert c.c_qasm() == ("version 1.0\nqubits 2\nx q[0]\nh q[1]\nmeasure_all\nprep_z q[0]\nprep_z q[1]\nh q[0]\nh q[1]\n"
+                              "measure_all\nprep_z q[1]\nsdag q[0]\nh q[0]\nsdag q[1]\nh q[1]\nmeasure_all\n")
+    # circuit.rs:2137-2151
+    with QC.Circuit(2, 2) as c:
+        c.x(0); c.measure_all([0, 1]); c.add_conditional_gate([0, 1], 1, "x", [0]); c.add_conditional_gate([], 1, "x", [1])
+        assert c.c_qasm() == "version 1.0\nqubits 2\nx q[0]\nmeasure_all\nnot b[1]\nc-x b[0], b[1], q[0]\nnot b[1]\nx q[1]\n"
+    # circuit.rs:2153-2157: c-Qasm measures into the classical bit with the qubit's own index
+    with QC.Circuit(2, 2) as c:
+        c.measure(0, 1)
+        with pytest.raises(QC.CircuitError, match="no classical registers can be specified"):
+            c.c_qasm()
+
+
+def test_peek_cannot_be_exported():
+    # circuit.rs:984-993, :1117-1126
+    with QC.Circuit(1, 1) as c:
+        c.peek(0, 0)
+        with pytest.raises(QC.CircuitError, match="not supported in OpenQasm"):
+            c.open_qasm()
+        with pytest.raises(QC.CircuitError, match="not supported in c-Qasm"):
+            c.c_qasm()
+
+
+@pytest.mark.parametrize("name,params,bits,open_qasm,c_qasm", [
+    # src/gates/<gate>.rs test_open_qasm / test_c_qasm
+    ("h", (), [0], "h qb0", "h qb0"), ("i", (), [0], "id qb0", "i qb0"), ("x", (), [0], "x qb0", "x qb0"),
+    ("y", (), [0], "y qb0", "y qb0"), ("z", (), [0], "z qb0", "z qb0"), ("s", (), [0], "s qb0", "s qb0"),
+    ("sdg", (), [0], "sdg qb0", "sdag qb0"), ("t", (), [0], "t qb0", "t qb0"), ("tdg", (), [0], "tdg qb0", "tdag qb0"),
+    ("v", (), [0], "u3(pi/2, -pi/2, pi/2) qb0", "x90 qb0"), ("vdg", (), [0], "u3(pi/2, pi/2, -pi/2) qb0", "mx90 qb0"),
+    ("rx", (2.25,), [0], "rx(2.25) qb0", "rx qb0, 2.25"), ("ry", (2.25,), [0], "u3(2.25, 0, 0) qb0", "ry qb0, 2.25"),
+    ("rz", (2.25,), [0], "rz(2.25) qb0", "rz qb0, 2.25"), ("u1", (math.pi / 4,), [0], "u1(0.7853981633974483) qb0", "rz qb0, 0.7853981633974483"),
+    ("u2", (1.0, 2.25), [0], "u2(1, 2.25) qb0", "rz qb0, 5.391592653589793\nh qb0\nrz qb0 1"),
+    ("u3", (1.0, 2.25, 3.5), [0], "u3(1, 2.25, 3.5) qb0", "rz qb0, 3.5\nry qb0, 1\n; rz qb0 2.25"),
+    ("cx", (), [0, 1], "cx qb0, qb1", "cnot qb0, qb1"), ("cy", (), [0, 1], "cy qb0, qb1", "sdag qb1\ncnot qb0, qb1\ns qb1"),
+    ("cz", (), [0, 1], "cz qb0, qb1", "cz qb0, qb1"), ("swap", (), [0, 1], "cx qb0, qb1; cx qb1, qb0; cx qb0, qb1", "swap qb0, qb1"),
+    # controlled.rs:691-817
+    ("ccrx", (0.9,), [0, 1, 2],
+     "s qb2; cx qb1, qb2; ry(-0.9/4) qb2; cx qb1, qb2; ry(0.9/4) qb2; cx qb0, qb1; cx qb1, qb2; ry(0.9/4) qb2; cx qb1, qb2; "
+     "ry(-0.9/4) qb2; cx qb0, qb1; cx qb0, qb2; ry(-0.9/4) qb2; cx qb0, qb2; ry(0.9/4) qb2; sdg qb2",
+     "s qb2\ncnot qb1, qb2\nry qb2, -0.225\ncnot qb1, qb2\nry qb2, 0.225\ncnot qb0, qb1\ncnot qb1, qb2\nry qb2, 0.225\n"
+     "cnot qb1, qb2\nry qb2, -0.225\ncnot qb0, qb1\ncnot qb0, qb2\nry qb2, -0.225\ncnot qb0, qb2\nry qb2, 0.225\nsdag qb2"),
+    ("ccry", (1.6,), [1, 2, 0],
+     "cx qb2, qb0; u3(-1.6/4, 0, 0) qb0; cx qb2, qb0; u3(1.6/4, 0, 0) qb0; cx qb1, qb2; cx qb2, qb0; u3(1.6/4, 0, 0) qb0; "
+     "cx qb2, qb0; u3(-1.6/4, 0, 0) qb0; cx qb1, qb2; cx qb1, qb0; u3(-1.6/4, 0, 0) qb0; cx qb1, qb0; u3(1.6/4, 0, 0) qb0",
+     "cnot qb2, qb0\nry qb0, -0.4\ncnot qb2, qb0\nry qb0, 0.4\ncnot qb1, qb2\ncnot qb2, qb0\nry qb0, 0.4\ncnot qb2, qb0\n"
+     "ry qb0, -0.4\ncnot qb1, qb2\ncnot qb1, qb0\nry qb0, -0.4\ncnot qb1, qb0\nry qb0, 0.4"),
+    ("ccrz", (2.12,), [1, 2, 0],
+     "crz(2.12/2) qb2, qb0; cx qb1, qb2; crz(-2.12/2) qb2, qb0; cx qb1, qb2; crz(2.12/2) qb1, qb0",
+     "cr qb2, qb0, 1.06\ncnot qb1, qb2\ncr qb2, qb0, -1.06\ncnot qb1, qb2\ncr qb1, qb0, 1.06"),
+    ("crx", (0.9,), [0, 1], "s qb1; cx qb0, qb1; ry(-0.9/2) qb1; cx qb0, qb1; ry(0.9/2) qb1; sdg qb1",
+     "s qb1\ncnot qb0, qb1\nry qb1, -0.45\ncnot qb0, qb1\nry qb1, 0.45\nsdag qb1"),
+    ("ccz", (), [0, 1, 2], "h qb2; ccx qb0, qb1, qb2; h qb2", "h qb2\ntoffoli qb0, qb1, qb2\nh qb2"),
+    ("cs", (), [0, 1], "cu1(pi/2) qb0, qb1", "crk qb0, qb1, 1"),
+    ("ctdg", (), [0, 1], "cu1(-pi/4) qb0, qb1", "cr qb0, qb1, -0.7853981633974483"),
+    ("cu1", (1.2345678,), [0, 1], "cu1(1.2345678) qb0, qb1", "cr qb0, qb1, 1.2345678"),
+    ("cu3", (1.2345678, 3.1415, -0.9876), [0, 1], "cu3(1.2345678, 3.1415, -0.9876) qb0, qb1",
+     "rz qb1, -2.06455\ncnot qb0, qb1\nrz qb1, -1.07695\nry qb1, -0.6172839\ncnot qb0, qb1\nry qb1, 0.6172839\n"
+     "rz qb1, 3.1415\nrz qb0, 1.07695"),
+    # declare_controlled_qasm! default form (controlled.rs:224-262)
+    ("ch", (), [1, 0], "ch qb1, qb0", "ch qb1, qb0"), ("crz", (0.5,), [0, 2], "crz(0.5) qb0, qb2", "crz qb0, qb2, 0.5"),
+    ("cu2", (0.5, 1.5), [0, 1], "cu2(0.5, 1.5) qb0, qb1", "cu2 qb0, qb1, 0.5, 1.5"), ("ccx", (), [2, 1, 0], "ccx qb2, qb1, qb0", "toffoli qb2, qb1, qb0"),
+    ("cv", (), [0, 1], "cv qb0, qb1", "cv qb0, qb1"),
+])
+def test_gate_instructions(name, params, bits, open_qasm, c_qasm):
+    oq, cq = _gate_lines(name, bits, params)
+    assert oq == _q(open_qasm)
+    assert cq == _q(c_qasm)
+
+
+def test_float_formatting_is_rusts_display():
+    # `{}` of an f64: shortest round-trip digits, no exponent, integers without ".0"
+    oq, _ = _gate_lines("u3", [0], (1e-7, -3.0, 1e21))
+    assert oq == "u3(0.0000001, -3, 1000000000000000000000) q[0]"
+
+
+def test_conditional_gate_forms():
+    # export/openqasm.rs:53-60, export/cqasm.rs:67-75
+    with QC.Circuit(2, 2) as c:
+        c.add_conditional_gate([0, 1], 0, "h", [1])
+        assert c.open_qasm().endswith("if (b == 0) h q[1];\n")
+        assert c.c_qasm().endswith("not b[0]\nnot b[1]\nc-h b[0], b[1], q[1]\nnot b[0]\nnot b[1]\n")
+
+
+def test_composite_and_loop_groups():
+    # composite.rs:1619-1628, :1643-1652: one instruction, sub-gates joined by "; " / newline
+    with QC.Circuit(2, 0) as c:
+        c.add_composite_gate("Inc2", "CX 0 1; X 1", [0, 1])
+        c.h(0)
+        assert c.open_qasm() == OQ_HEAD + "qreg q[2];\ncx q[0], q[1]; x q[1];\nh q[0];\n"
+        assert c.c_qasm() == "version 1.0\nqubits 2\ncnot q[0], q[1]\nx q[1]\nh q[0]\n"
+    # staticloop.rs:324-340, :358-366
+    with QC.Circuit(2, 0) as c:
+        c.add_loop_gate("myloop", "H 0; H 1; CX 0 1", [0, 1], 3)
+        body = "h q[0]; h q[1]; cx q[0], q[1]"
+        assert c.open_qasm() == OQ_HEAD + "qreg q[2];\n" + ";\n".join([body] * 3) + ";\n"
+        assert c.c_qasm() == "version 1.0\nqubits 2\n.myloop(3)\nh q[0]\nh q[1]\ncnot q[0], q[1]\n.end\n"
+    # two adjacent composites stay two instructions
+    with QC.Circuit(1, 0) as c:
+        c.add_composite_gate("a", "H 0; X 0", [0])
+        c.add_composite_gate("b", "H 0; X 0", [0])
+        assert c.open_qasm() == OQ_HEAD + "qreg q[1];\nh q[0]; x q[0];\nh q[0]; x q[0];\n"
+
+
+def test_user_gate_has_no_export():
+    # default trait methods: ExportError::NotImplemented (export/openqasm.rs:23-30, error.rs:53-55)
+    with QC.Circuit(1, 0) as c:
+        c.add_matrix_gate([[0, 1], [1, 0]], [0], description="MyX")
+        with pytest.raises(QC.CircuitError, match='Export to OpenQasm was not implemented for "MyX"'):
+            c.open_qasm()
+        with pytest.raises(QC.CircuitError, match='Export to c-Qasm was not implemented for "MyX"'):
+            c.c_qasm()
+        with pytest.raises(QC.CircuitError, match="Export to LaTeX was not implemented"):
+            c.latex()
