@@ -203,13 +203,20 @@ def run_ours(args, rank, world, local):
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(dev)
+    # device-side timing: CUDA events bracket the K steps.  Every step ends synchronously (execute() returns the
+    # sampled classical register), so the events see the whole region, host planning included; the host clock is
+    # kept beside it as a cross-check (`wall_ms_per_step`)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
+    ev0.record()
     for _ in range(args.steps):
         step()
+    ev1.record()
     barrier()
-    dt = time.perf_counter() - t0
+    dt_wall = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop()
     stats = circ.engine_stats()                # statistics of the last execute()
     if world > 1:
@@ -238,16 +245,22 @@ def run_ours(args, rank, world, local):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
 
-    def roof(t, reps):
+    # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    # capture of these launches (profiles/r1_ladder_kernel.md, QFT-30 only): dense 17.18 + 17.12 GB per launch;
+    # |0..0>: (0.1 MB) + (0.2 MB + 1 MB) + (33.8 MB + 17.12 GB) over the three launches
+    ncu_traffic = {"dense": 34.30e9, "tracked": 17.155e9 / 3.0} if n == 30 else {}
+
+    def roof(t, reps, which):
         ms = t["sweep_ms"] / max(t["sweeps"], 1)
         by = t["sweep_bytes"] / max(t["sweeps"], 1)
         ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         return {"bound": "hbm", "kernel": "ladder_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "bytes_per_launch": by, "avg_launch_ms": ms,
+                "traffic": ncu_traffic.get(which), "traffic_source": "profiles/r1_ladder_kernel.md (ncu --set full, per launch)" if which in ncu_traffic else None,
+                "peak_source": peak_src, "bytes_per_launch": by, "avg_launch_ms": ms,
                 "sweeps_per_step": t["sweeps"] / float(reps), "sweep_ms_per_step": t["sweep_ms"] / float(reps),
                 "read_pass_ms_per_step": t["read_ms"] / float(reps)}
 
-    roofline = roof(ts, 2)
+    roofline = roof(ts, 2, "tracked")
     roofline["input"] = "|0..0> (the timed workload): support tracking, bytes_per_launch = bytes the launches have to move"
     r = W.SplitMix64(1)
     coefs = []
@@ -269,7 +282,7 @@ def run_ours(args, rank, world, local):
         sd.flush()                      # (the state stays dense; repeated QFTs of it are as good as any dense input)
     td = sd.stats()
     sd.close()
-    dense = roof(td, 2)
+    dense = roof(td, 2, "dense")
     dense["input"] = "dense seeded product state (from_qubit_coefs), same QFT-%d gate list: 32 B per amplitude and sweep" % n
     roofline["dense_input"] = dense
 
@@ -288,11 +301,12 @@ def run_ours(args, rank, world, local):
 
     e2e_step()
     barrier()
-    t0 = time.perf_counter()
+    ev0.record()
     for _ in range(e2e_steps):
         e2e_step()
+    ev1.record()
     barrier()
-    dte = time.perf_counter() - t0
+    dte = ev0.elapsed_time(ev1) * 1e-3
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([dte], device="cuda", dtype=torch.float64)
@@ -311,7 +325,8 @@ def run_ours(args, rank, world, local):
         "config": {"workload": "QFT-%d f64 + measure_all, %d shots, input |0..0>" % (n, shots), "gates": ngates,
                    "state_bytes": 16 << n, "l2": "state (16 GiB at n=30) is far larger than the 126 MB L2; no explicit flush",
                    "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
-        "circuit_ms": 1e3 * dt / args.steps,
+        "circuit_ms": 1e3 * dt / args.steps, "wall_ms_per_step": 1e3 * dt_wall / args.steps,
+        "timing": "CUDA events around the K steps (every step ends synchronously), max over ranks",
         "e2e": {"value": e2e_val, "unit": "gate_amp_updates/s", "ms_per_step": 1e3 * dte / e2e_steps,
                 "h2d_bytes_per_step": int(stats["sweeps"] * 28000 + shots * 8),
                 "d2h_bytes_per_step": int(shots * 8 + 8), "steps": e2e_steps,
@@ -384,13 +399,15 @@ def run_sharded(args, rank, world, local):
     for k in acc:
         acc[k] = 0
     sampler = ClockSampler(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
-    t0 = time.perf_counter()
+    ev0.record()
     for _ in range(args.steps):
         step()
+    ev1.record()
     barrier()
-    dt = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3       # every step ends synchronously (sampled outcomes gathered on the host)
     clocks = sampler.stop()
     t = torch.tensor([dt], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -166,7 +166,8 @@ int q1t_get_stats(q1t_state *st, q1t_stats *out);
 int q1t_reset_stats(q1t_state *st);
 /* enable per-kernel CUDA-event timing (bench only; serialises the stream) */
 int q1t_set_timing(q1t_state *st, int enabled);
-/* engine knobs: "tile_bits" (8..13), "fuse" (0/1), "coalesce_bits" (2/3), "balance" (-1/0/1), "track_support" (0/1).
+/* engine knobs: "tile_bits" (8..13), "fuse" (0/1), "coalesce_bits" (2/3), "balance" (-1/0/1), "track_support" (0/1),
+ * "inplace_relabel" (-1 never, 0 only when no second column buffer fits into device memory, 1 always).
  * Returns Q1T_ERR_INVALID_ARGUMENT for unknown keys. */
 int q1t_set_option(q1t_state *st, const char *key, long value);
 
@@ -195,6 +196,12 @@ int q1t_eval_expression(const char *text, double *value_out, size_t *consumed, c
  * out[3]=fallback gates out[4]=permute sweeps needed to restore canonical order */
 int q1t_plan_dry_run(size_t nr_bits, size_t nr_gates, const double *matrices, const size_t *matrix_dims,
                      const size_t *bits, const size_t *nr_gate_bits, long tile_bits, uint64_t *out);
+/* in-place relabelling dry run (no device): the passes that restore canonical order when no second column
+ * buffer fits.  dstpos[p] = destination position of index bit p.  Writes, per pass, tile_bits
+ * tile positions into out_tiles and nr_bits destination positions into out_dstpos; returns the number of
+ * passes (0 for the identity), Q1T_ERR_NOT_ENOUGH_SPACE if more than max_passes are needed. */
+int q1t_plan_inplace_relabel(size_t nr_bits, long tile_bits, long coalesce_bits, const int *dstpos,
+                             int *out_tiles, int *out_dstpos, size_t max_passes);
 int q1t_device_count(void);
 const char *q1t_version(void);
 

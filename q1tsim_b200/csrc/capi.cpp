@@ -194,6 +194,28 @@ int q1t_composite_matrix(const char *description, double *out, size_t cap, char 
     return k;
 }
 
+int q1t_plan_inplace_relabel(size_t nr_bits, long tile_bits, long coalesce_bits, const int *dstpos,
+                             int *out_tiles, int *out_dstpos, size_t max_passes)
+{
+    if (!dstpos || nr_bits == 0 || nr_bits > (size_t)q1t::kMaxBits || tile_bits < 5 || tile_bits > q1t::kMaxTileBits ||
+        coalesce_bits < 0 || coalesce_bits + 2 > tile_bits)
+        return Q1T_ERR_INVALID_ARGUMENT;
+    std::vector<int> dp(dstpos, dstpos + nr_bits);
+    std::vector<char> hit(nr_bits, 0);
+    for (int d : dp) {
+        if (d < 0 || (size_t)d >= nr_bits || hit[d]) return Q1T_ERR_INVALID_ARGUMENT;
+        hit[d] = 1;
+    }
+    const std::vector<q1t::InplacePass> passes = q1t::plan_inplace_relabel((int)nr_bits, (int)tile_bits, (int)coalesce_bits, dp);
+    if (passes.size() > max_passes) return Q1T_ERR_NOT_ENOUGH_SPACE;
+    const size_t T = (size_t)tile_bits < nr_bits ? (size_t)tile_bits : nr_bits;
+    for (size_t k = 0; k < passes.size(); ++k) {
+        if (out_tiles) for (size_t i = 0; i < T; ++i) out_tiles[k * T + i] = passes[k].tile[i];
+        if (out_dstpos) for (size_t i = 0; i < nr_bits; ++i) out_dstpos[k * nr_bits + i] = passes[k].dstpos[i];
+    }
+    return (int)passes.size();
+}
+
 int q1t_eval_expression(const char *text, double *value_out, size_t *consumed, char *err_out, size_t err_cap)
 {
     if (!text || !value_out) return Q1T_ERR_INVALID_ARGUMENT;

@@ -114,6 +114,7 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
     if (const char *e = std::getenv("Q1T_TRACK_SUPPORT")) track_support_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_SPARSE_C2")) sparse_c2_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_FUSE_LEAF")) fuse_leaf_totals_ = std::atol(e) != 0;
+    if (const char *e = std::getenv("Q1T_INPLACE_RELABEL")) inplace_relabel_ = std::atol(e);
     if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
 }
 
@@ -506,7 +507,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
         ps.prog.generate = (generate && si == 0) ? 1 : 0;
         const bool last = si + 1 == sweeps.size();
         bool relabel = false;
-        if (last && final_relabel && !ident && which.size() == cols_.size()) {
+        if (last && final_relabel && !ident && which.size() == cols_.size() && !want_inplace_relabel()) {
             std::vector<int> dstpos(n_);
             for (int l = 0; l < n_; ++l) dstpos[perm_[l]] = l;
             if (can_fuse_relabel(ps.prog, dstpos)) {
@@ -679,7 +680,27 @@ int DeviceVectorState::run_queue(bool final_relabel)
     return run_sweeps(sw, which, final_relabel);
 }
 
+// Relabel in place?  Forced by the "inplace_relabel" option, else only when the live columns plus one
+// scratch column cannot fit into 90 % of the device memory.
+bool DeviceVectorState::want_inplace_relabel()
+{
+    if (inplace_relabel_ > 0) return n_ >= 5;
+    if (inplace_relabel_ < 0) return false;
+    size_t live = 0;
+    for (const Column &c : cols_)
+        if (c.buf) ++live;
+    static size_t total_of[64] = { 0 };
+    size_t total_b = (device_ >= 0 && device_ < 64) ? total_of[device_] : 0;
+    if (!total_b) {
+        size_t free_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (device_ >= 0 && device_ < 64) total_of[device_] = total_b;
+    }
+    return (live + 1) * (sizeof(double2) << n_) > total_b / 100 * 90;
+}
+
 // undo the zero-byte swap relabelling: one out-of-place relabel sweep per column
+// (or a few in-place passes when memory is tight)
 int DeviceVectorState::canonicalize()
 {
     bool ident = true;
@@ -688,6 +709,32 @@ int DeviceVectorState::canonicalize()
     if (ident) return Q1T_OK;
     std::vector<int> dstpos(n_);
     for (int l = 0; l < n_; ++l) dstpos[perm_[l]] = l;
+    if (want_inplace_relabel()) {
+        // no room for a second column buffer (128 GiB shards): a few tile-closed passes with
+        // source == destination instead of one out-of-place sweep (planner.cpp, plan_inplace_relabel)
+        const std::vector<InplacePass> passes = plan_inplace_relabel(n_, (int)tile_bits_, 3, dstpos);
+        if (passes.empty()) return fail(Q1T_ERR_UNSUPPORTED, "in-place relabelling needs at least 5 tile bits");
+        for (const InplacePass &pass : passes) {
+            PlannedSweep ps = build_permute_sweep(n_, (int)tile_bits_, pass.dstpos, &pass.tile);
+            for (size_t c = 0; c < cols_.size(); ++c) {
+                Column &col = cols_[c];
+                if (col.basis) continue;     // lazy basis columns are stored by logical index; nothing to move
+                double2 *h[2] = { col.buf, col.buf };
+                // d_pair_ is rewritten per launch: stream order keeps the previous launch's copy intact until it has run
+                CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
+                time_begin();
+                CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, nullptr, stream_));
+                time_end(stats.sweep_ms);
+                stats.kernel_launches++;
+                stats.sweeps++;
+                stats.permute_sweeps++;
+                stats.sweep_column_passes++;
+                stats.sweep_bytes += 32ull << n_;
+            }
+        }
+        for (int l = 0; l < n_; ++l) perm_[l] = l;
+        return Q1T_OK;
+    }
     PlannedSweep ps = build_permute_sweep(n_, (int)tile_bits_, dstpos);
     for (size_t c = 0; c < cols_.size(); ++c) {
         Column &col = cols_[c];
@@ -1392,6 +1439,10 @@ int DeviceVectorState::set_option(const char *key, long value)
         int rc = run_queue();
         if (rc) return rc;
         balance_ = value;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "inplace_relabel")) {
+        inplace_relabel_ = value;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "fuse_leaf_totals")) {

@@ -89,6 +89,8 @@ private:
     long dbg_skip_ = 0;
     bool fuse_ = true;
     bool no_relabel_ = false;                // conditional gates: Swap must move data, not relabel
+    long inplace_relabel_ = 0;               // -1 never, 0 when a second column buffer cannot fit, 1 always
+    bool want_inplace_relabel();
 
     // device scratch
     double2 **d_colptrs_ = nullptr; size_t colptrs_cap_ = 0;

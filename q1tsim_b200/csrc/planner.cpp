@@ -777,17 +777,102 @@ bool can_fuse_relabel(const SweepProgram &P, const std::vector<int> &dstpos)
     return found >= (P.n < P.coalesce ? P.n : P.coalesce);
 }
 
-PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos)
+// ---------------------------------------------------------------------------
+// in-place relabelling.  A relabel sweep may run with source == destination when its permutation is
+// TILE-CLOSED: it maps the tile's bit positions onto themselves and fixes every outer bit, so a CTA
+// writes exactly the addresses it has read (and it has read all of them before its first store).
+// Any bit permutation is a product of such passes: each pass takes the low `coalesce` bits (kept
+// for 128-byte accesses, moved or not) plus as many whole cycles of the remaining permutation as fit
+// into the tile; of a cycle that does not fit it takes a segment a1..am, puts a1..a(m-1) into their
+// final places and parks am at a1, which shortens the cycle by m-1.  The bit reversal of QFT-30
+// takes 4 passes at 12 tile bits.  Used when no second column buffer fits into device memory
+// (128 GiB shards); otherwise the relabel is one out-of-place sweep.
+// ---------------------------------------------------------------------------
+std::vector<InplacePass> plan_inplace_relabel(int n, int tile_bits, int coalesce, const std::vector<int> &dstpos)
+{
+    std::vector<InplacePass> passes;
+    const int T = std::min(tile_bits, n), c = std::min(coalesce, n);
+    std::vector<int> R(dstpos);                  // data now at position p still has to go to R[p]
+    for (;;) {
+        std::vector<char> seen(n, 0), in_tile(n, 0);
+        std::vector<std::vector<int>> cycles;
+        for (int p = 0; p < n; ++p) {
+            if (seen[p] || R[p] == p) continue;
+            std::vector<int> cyc;
+            for (int q = p; !seen[q]; q = R[q]) { seen[q] = 1; cyc.push_back(q); }
+            cycles.push_back(cyc);
+        }
+        if (cycles.empty()) break;
+        auto low_members = [&](const std::vector<int> &cy) { int k = 0; for (int q : cy) k += q < c; return k; };
+        std::stable_sort(cycles.begin(), cycles.end(), [&](const std::vector<int> &a, const std::vector<int> &b) {
+            const int la = low_members(a), lb = low_members(b);
+            if ((la > 0) != (lb > 0)) return la > 0;             // cycles through the low bits first: they cost less
+            return a.size() - la < b.size() - lb;                // then the cheapest
+        });
+        InplacePass ps;
+        ps.dstpos.resize(n);
+        for (int p = 0; p < n; ++p) ps.dstpos[p] = p;
+        for (int b = 0; b < c; ++b) in_tile[b] = 1;
+        int freeb = T - c;
+        bool progress = false;
+        for (const std::vector<int> &cy : cycles) {
+            const int L = (int)cy.size();
+            const int cost = L - low_members(cy);
+            if (cost <= freeb) {                                 // the whole cycle
+                for (int q : cy) { ps.dstpos[q] = R[q]; in_tile[q] = 1; }
+                freeb -= cost;
+                progress = true;
+                continue;
+            }
+            // longest affordable segment: try every start, keep the longest (a start at a low bit is cheaper)
+            int best_start = -1, best_len = 0;
+            for (int s0 = 0; s0 < L; ++s0) {
+                int len = 0, spent = 0;
+                while (len < L - 1) {
+                    const int q = cy[(s0 + len) % L];
+                    const int add = q < c ? 0 : 1;
+                    if (spent + add > freeb) break;
+                    spent += add;
+                    ++len;
+                }
+                if (len > best_len) { best_len = len; best_start = s0; }
+            }
+            if (best_len < 2) continue;
+            for (int i = 0; i < best_len; ++i) {
+                const int q = cy[(best_start + i) % L];
+                if (q >= c) --freeb;
+                in_tile[q] = 1;
+                ps.dstpos[q] = i + 1 < best_len ? R[q] : cy[best_start];      // the last one is parked at the segment's head
+            }
+            progress = true;
+        }
+        if (!progress) { passes.clear(); return passes; }       // cannot happen for T >= coalesce + 2
+        // fill the tile with the lowest free bits (fixed passengers: longer contiguous runs)
+        for (int p = 0; p < n && freeb > 0; ++p)
+            if (!in_tile[p]) { in_tile[p] = 1; --freeb; }
+        for (int p = 0; p < n; ++p)
+            if (in_tile[p]) ps.tile.push_back(p);
+        // what is left: the data now at ps.dstpos[p] still has to go to R[p]
+        std::vector<int> R2(n);
+        for (int p = 0; p < n; ++p) R2[ps.dstpos[p]] = R[p];
+        R.swap(R2);
+        passes.push_back(ps);
+    }
+    return passes;
+}
+
+PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos, const std::vector<int> *forced_tile)
 {
     PlannedSweep ps;
     ps.is_permute = true;
     SweepProgram &P = ps.prog;
     std::memset(&P, 0, sizeof P);
-    const int T = std::min(tile_bits, n);
+    const int T = forced_tile ? (int)forced_tile->size() : std::min(tile_bits, n);
     std::vector<int> srcpos_of_dst(n);
     for (int p = 0; p < n; ++p) srcpos_of_dst[dstpos[p]] = p;
     // tile = low source bits + sources of the low destination bits, alternating until full
     std::vector<int> tile;
+    if (forced_tile) tile = *forced_tile;
     for (int i = 0; i < n && (int)tile.size() < T; ++i) {
         if (std::find(tile.begin(), tile.end(), i) == tile.end()) tile.push_back(i);
         if ((int)tile.size() >= T) break;

@@ -115,7 +115,13 @@ private:
 };
 
 // relabelling sweep: dstpos[p] = destination position of source bit p
-PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos);
+PlannedSweep build_permute_sweep(int n, int tile_bits, const std::vector<int> &dstpos, const std::vector<int> *forced_tile = nullptr);
+// a bit permutation as a sequence of tile-closed passes that may run in place (source == destination)
+struct InplacePass {
+    std::vector<int> tile;      // bit positions of the tile, ascending; contains the low `coalesce` bits
+    std::vector<int> dstpos;    // this pass moves the data at bit p to dstpos[p]; identity outside `tile`
+};
+std::vector<InplacePass> plan_inplace_relabel(int n, int tile_bits, int coalesce, const std::vector<int> &dstpos);
 // turn the store side of an existing sweep into a relabelling one (out-of-place launch required)
 // leaf_split: if the tile holds destination bits 0..9 (whole canonical leaves of 1024 amplitudes), lay the
 // store pass out as one leaf per warp (lanes = destination bits 0..4, slots = bits 5..9) and set P.leaf_fuse

@@ -95,6 +95,7 @@ def lib():
         "q1t_binomial": (C.c_uint64, [R, C.c_uint64, C.c_double]),
         "q1t_gate_matrix": (C.c_int, [C.c_char_p, dp, sz, dp]),
         "q1t_plan_dry_run": (C.c_int, [sz, sz, dp, szp, szp, szp, C.c_long, u64p]),
+        "q1t_plan_inplace_relabel": (C.c_int, [sz, C.c_long, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), sz]),
         "q1t_composite_matrix": (C.c_int, [C.c_char_p, dp, sz, C.c_char_p, sz]),
         "q1t_eval_expression": (C.c_int, [C.c_char_p, dp, szp, C.c_char_p, sz]),
         "q1t_device_count": (C.c_int, []),
@@ -115,7 +116,7 @@ INNER_ABI_SYMBOLS = [
     "q1t_counts", "q1t_read_amplitudes", "q1t_write_amplitudes", "q1t_marginal0", "q1t_column_totals", "q1t_flush",
     "q1t_last_error", "q1t_get_stats", "q1t_reset_stats", "q1t_set_timing", "q1t_set_option", "q1t_rng_splitmix64",
     "q1t_rng_from_words", "q1t_rng_entropy", "q1t_rng_consumed", "q1t_rng_free", "q1t_rng_handle", "q1t_binomial",
-    "q1t_gate_matrix", "q1t_plan_dry_run", "q1t_composite_matrix", "q1t_eval_expression", "q1t_device_count", "q1t_version",
+    "q1t_gate_matrix", "q1t_plan_dry_run", "q1t_plan_inplace_relabel", "q1t_composite_matrix", "q1t_eval_expression", "q1t_device_count", "q1t_version",
 ]
 
 
@@ -207,6 +208,20 @@ def plan_dry_run(nr_bits, gates, tile_bits=12):
     if rc:
         raise EngineError(rc, "plan_dry_run failed")
     return dict(zip(("sweeps", "rounds", "ops", "fallback", "permute"), [int(v) for v in out]))
+
+
+def plan_inplace_relabel(dstpos, tile_bits=12, coalesce_bits=3, max_passes=64):
+    """The tile-closed passes the engine runs when it has to restore canonical order in place (no room for a
+    second column buffer).  dstpos[p] = destination position of index bit p.  Returns [(tile, pass_dstpos), ...]."""
+    n = len(dstpos)
+    T = min(tile_bits, n)
+    dp = (C.c_int * n)(*[int(d) for d in dstpos])
+    tiles = (C.c_int * (max_passes * T))()
+    outs = (C.c_int * (max_passes * n))()
+    k = lib().q1t_plan_inplace_relabel(n, tile_bits, coalesce_bits, dp, tiles, outs, max_passes)
+    if k < 0:
+        raise EngineError(k, "plan_inplace_relabel failed")
+    return [(list(tiles[i * T:(i + 1) * T]), list(outs[i * n:(i + 1) * n])) for i in range(k)]
 
 
 class VectorState:

@@ -488,3 +488,4 @@ def test_measure_all_after_qft_fused_leaf_totals(n, prep):
         outs.append(re_.copy())
         e.close()
     assert np.array_equal(outs[0], outs[1])
+
