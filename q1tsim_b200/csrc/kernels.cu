@@ -635,6 +635,27 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     }
     s_off[2 * tid] = soff_t;            // only ever read back by the same thread
     s_off[2 * tid + 1] = doff_t;
+    // Broadcast sweeps.  A step computes (x, y) -> (x + f y, x - f y) on its slot bit.  When that bit is still
+    // pinned to 0 the y half is zero: the phase drops out and the step copies x into the other half.  If that
+    // holds for every step of every round (first gates on fresh |0> qubits: QFT or an H layer on |0..0>), the
+    // whole sweep is out[l] = in[l with the target bits cleared]: no rounds, no phase tables -- the staged
+    // store pass reads the few live inputs straight from the tile.  bc_keep = tile-local mask of the
+    // non-target bits (all ones: not a broadcast sweep).
+    unsigned bc_keep = 0xffffffffu;
+    if (sup_mode && !generate && staged_store && P.nrounds > 0) {
+        unsigned tgt = 0;
+        bool ok = true;
+        for (int r = 0; r < P.nrounds; ++r) {
+            const RoundDesc &R = P.rounds[r];
+            for (int j = kRegBits - R.nsteps; j < kRegBits; ++j) {
+                const unsigned tb = R.reg_tb[j];
+                if (!((R.smask >> j) & 1u) || ((sup_vt >> tb) & 1u) || ((tgt >> tb) & 1u)) ok = false;
+                tgt |= 1u << tb;
+            }
+        }
+        if (ok) bc_keep = ~tgt & ((1u << T) - 1u);
+    }
+    const bool bcast = bc_keep != 0xffffffffu;
     auto in_support = [&](unsigned long long o) {
         return ((outer_base(P.o_src, o, P.n_outer) ^ sup_g) & sup_mo) == 0ull;
     };
@@ -739,9 +760,11 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         s_coef[e] = i < P.n_outer ? ptabs[pid].outer_coef[i] : ptabs[pid].base;
     }
     __syncthreads();
-    tables_phase1(o);
-    __syncthreads();
-    tables_phase2(0);
+    if (!bcast) {
+        tables_phase1(o);
+        __syncthreads();
+        tables_phase2(0);
+    }
     int buf = 0;
     unsigned long long o_next = 0;
     PCLK_DECL
@@ -754,7 +777,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         __syncthreads();                       // tile o and its tables are visible to the whole CTA
         PCLK(2);
         const double2 *const hiF = s_hiF + buf * ntab;
-        for (int r = 0; r < P.nrounds; ++r) {
+        for (int r = 0; r < (bcast ? 0 : P.nrounds); ++r) {
             const RoundDesc &R = P.rounds[r];
             const bool last = r + 1 == P.nrounds;
             unsigned thrL = 0;
@@ -846,6 +869,32 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             unsigned swl = sw_lo;
             asm volatile("" : "+r"(swl));     // as in issue_loads: no hoisting of the 32 addresses
             double leaf_acc = 0.0;
+            if (bcast) {
+                // element l of the tile = the input element with the target bits cleared, or zero where a
+                // pinned bit outside the targets differs from the basis index
+                unsigned l_lo = 0;
+                for (int k = 0; k < P.st_nruns; ++k) {
+                    const int sh = P.st_lruns[k].shift;
+                    const unsigned t = tid & P.st_lruns[k].mask;
+                    l_lo |= sh >= 0 ? t << sh : t >> -sh;
+                }
+                const unsigned chk = sup_mt & bc_keep;
+                double2 v[kSlots];
+#pragma unroll
+                for (int i = 0; i < kSlots; ++i) {
+                    const unsigned l = l_lo | tile_swizzle(P.st_l_hi[i] >> 4);     // the swizzle is an involution
+                    v[i] = ((l ^ sup_vt) & chk) == 0u ? *reinterpret_cast<const double2 *>(tile_b + tile_swizzle(l & bc_keep) * 16u)
+                                                      : make_double2(0.0, 0.0);
+                }
+                __syncthreads();               // every input is in registers: the tile is dead
+                if (has_next) issue_loads(o_next);
+#pragma unroll
+                for (int i = 0; i < kSlots; ++i) {
+                    const double2 x = scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i];
+                    if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
+                    st_global_cs(q + P.st_off_hi[i], x);
+                }
+            } else {
             {   // first half: read and store right away
                 double2 v[kSlots / 2];
 #pragma unroll
@@ -877,6 +926,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                     if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
                     st_global_cs(q + P.st_off_hi[kSlots / 2 + i], x);
                 }
+            }
             }
             if (leaf_fuse) {
                 // lane l has summed elements l, l+32, ... of its warp's leaf in increasing order: finish
