@@ -553,6 +553,108 @@ sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__rest
 }
 
 // ---------------------------------------------------------------------------
+// Broadcast sweeps (ladder kernel, support tracking).  A ladder step computes (x, y) -> (x + f y, x - f y) on
+// its slot bit.  When that bit is still pinned to 0 the y half is zero: the phase drops out and the step copies
+// x into the other half.  If that holds for every step of every round of a sweep (first gates on fresh |0>
+// qubits: a QFT or an H layer on a basis state whose target bits are 0), the whole sweep is
+//     out[l] = in[l with the target bits cleared]
+// -- no rounds, no phase tables: the staged store pass reads the few live inputs straight from the tile.
+// The live inputs of a tile have all target bits clear, so the tile positions with target bits set are free:
+// two target bits select one of four slots, and the inputs of the next three tiles are in flight while a
+// tile is stored (under a saturating write stream a read takes several tile times to come back).
+// Separate no-inline function: keeps the register allocation of the dense path as it was.
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                                                    double *__restrict__ leaf_col, char *tile_b, const unsigned long long *s_off,
+                                                    unsigned bc_keep, unsigned sup_mt, unsigned sup_vt, unsigned long long sup_g,
+                                                    unsigned long long sup_mo)
+{
+    const SweepProgram &P = c_prog;
+    const int T = P.T, TB = P.TB;
+    const unsigned tid = threadIdx.x;
+    const unsigned long long ntiles = 1ull << P.n_outer;
+    const unsigned long long soff_t = s_off[2 * tid], doff_t = s_off[2 * tid + 1];
+    const double scale = P.scale;
+    const bool leaf_fuse = leaf_col != nullptr;
+    const bool zero_fill = P.sup_mode == 2;
+    const unsigned sw_tid = tile_swizzle(tid) * 16u;
+    const unsigned tgt = ~bc_keep & ((1u << T) - 1u);
+    const unsigned tb_a = __ffs(tgt) - 1, tb_b = __ffs(tgt & (tgt - 1u)) - 1;
+    auto slot_pat = [&](unsigned k) { return ((k & 1u) << tb_a) | (((k >> 1) & 1u) << tb_b); };
+    // Tiles are walked in DESTINATION order (w_src / w_dst): the CTAs of the grid then write a few sequential
+    // streams instead of chunks scattered by the relabelling.
+    // first tile at or after t (stride: the grid) that holds data; tiles passed on the way are zero-filled when
+    // the column has to leave the batch dense
+    auto next_from = [&](unsigned long long t) {
+        for (; t < ntiles; t += gridDim.x) {
+            const unsigned long long ob = outer_base(P.w_src, t, P.n_outer);
+            if (!sup_mo || ((ob ^ sup_g) & sup_mo) == 0ull) break;
+            if (zero_fill) {
+                const unsigned long long db = outer_base(P.w_dst, t, P.n_outer) | doff_t;
+                const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < kSlots; ++i) st_global_cs(dst + db + P.st_off_hi[i], z);
+                if (leaf_fuse && (tid & 31) == 0) leaf_col[db >> 10] = 0.0;
+            }
+        }
+        return t;
+    };
+    auto issue_slot = [&](unsigned long long t, unsigned k) {
+        if (t < ntiles) {
+            const double2 *__restrict__ p = src + (outer_base(P.w_src, t, P.n_outer) | soff_t);
+            const unsigned sw = sw_tid ^ (tile_swizzle(slot_pat(k)) * 16u);
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                const unsigned e = tid | ((unsigned)i << TB);
+                if (((e ^ sup_vt) & sup_mt) == 0u) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);     // one group per tile, empty ones included
+    };
+    unsigned l_lo = 0;
+    for (int k = 0; k < P.st_nruns; ++k) {
+        const int sh = P.st_lruns[k].shift;
+        const unsigned t = tid & P.st_lruns[k].mask;
+        l_lo |= sh >= 0 ? t << sh : t >> -sh;
+    }
+    const unsigned chk = sup_mt & bc_keep;
+    unsigned long long o = next_from(blockIdx.x);
+    unsigned long long o1 = o < ntiles ? next_from(o + gridDim.x) : o, o2 = o1 < ntiles ? next_from(o1 + gridDim.x) : o1,
+                       o3 = o2 < ntiles ? next_from(o2 + gridDim.x) : o2;
+    issue_slot(o, 0);
+    issue_slot(o1, 1);
+    issue_slot(o2, 2);
+    for (unsigned k = 0; o < ntiles; ++k) {
+        asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+        __syncthreads();                   // the inputs of tile o are visible; every thread is done with slot (k + 3) & 3
+        issue_slot(o3, k + 3);
+        const unsigned pat = slot_pat(k);
+        const unsigned long long db = outer_base(P.w_dst, o, P.n_outer) | doff_t;
+        double2 *__restrict__ q = dst + db;
+        double leaf_acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            // element l of the tile = the input element with the target bits cleared, or zero where a
+            // pinned bit outside the targets differs from the basis index
+            const unsigned l = l_lo | tile_swizzle(P.st_l_hi[i] >> 4);     // the swizzle is an involution
+            double2 x = make_double2(0.0, 0.0);
+            if (((l ^ sup_vt) & chk) == 0u) x = *reinterpret_cast<const double2 *>(tile_b + tile_swizzle((l & bc_keep) | pat) * 16u);
+            if (scale != 1.0) x = make_double2(x.x * scale, x.y * scale);
+            if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
+            st_global_cs(q + P.st_off_hi[i], x);
+        }
+        if (leaf_fuse) {
+            // lane l has summed elements l, l+32, ... of its warp's leaf in increasing order: the canonical butterfly
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) leaf_acc = __dadd_rn(leaf_acc, __shfl_xor_sync(0xffffffffu, leaf_acc, off));
+            if ((tid & 31) == 0) leaf_col[db >> 10] = leaf_acc;
+        }
+        o = o1; o1 = o2; o2 = o3;
+        if (o3 < ntiles) o3 = next_from(o3 + gridDim.x);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // the ladder kernel: sweeps whose rounds are all ROUND_PH ladders (QFT-like circuits).
 //
 // Persistent CTAs (a few per SM) walk over the tiles.  A CTA is a serial chain
@@ -635,12 +737,8 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     }
     s_off[2 * tid] = soff_t;            // only ever read back by the same thread
     s_off[2 * tid + 1] = doff_t;
-    // Broadcast sweeps.  A step computes (x, y) -> (x + f y, x - f y) on its slot bit.  When that bit is still
-    // pinned to 0 the y half is zero: the phase drops out and the step copies x into the other half.  If that
-    // holds for every step of every round (first gates on fresh |0> qubits: QFT or an H layer on |0..0>), the
-    // whole sweep is out[l] = in[l with the target bits cleared]: no rounds, no phase tables -- the staged
-    // store pass reads the few live inputs straight from the tile.  bc_keep = tile-local mask of the
-    // non-target bits (all ones: not a broadcast sweep).
+    // broadcast sweep (see ladder_broadcast_tiles)?  bc_keep = tile-local mask of the non-target bits,
+    // all ones when the sweep does not qualify for this column
     unsigned bc_keep = 0xffffffffu;
     if (sup_mode && !generate && staged_store && P.nrounds > 0) {
         unsigned tgt = 0;
@@ -653,7 +751,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 tgt |= 1u << tb;
             }
         }
-        if (ok) bc_keep = ~tgt & ((1u << T) - 1u);
+        if (ok && __popc(tgt) >= 2) bc_keep = ~tgt & ((1u << T) - 1u);
     }
     const bool bcast = bc_keep != 0xffffffffu;
     auto in_support = [&](unsigned long long o) {
@@ -745,6 +843,10 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         }
     };
 
+    if (bcast) {
+        ladder_broadcast_tiles(src, dst, leaf_col, tile_b, s_off, bc_keep, sup_mt, sup_vt, sup_g, sup_mo);
+        return;
+    }
     unsigned long long o = blockIdx.x;
     if (o >= ntiles) return;
     if (sup_mo && !in_support(o)) {
@@ -760,11 +862,9 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         s_coef[e] = i < P.n_outer ? ptabs[pid].outer_coef[i] : ptabs[pid].base;
     }
     __syncthreads();
-    if (!bcast) {
-        tables_phase1(o);
-        __syncthreads();
-        tables_phase2(0);
-    }
+    tables_phase1(o);
+    __syncthreads();
+    tables_phase2(0);
     int buf = 0;
     unsigned long long o_next = 0;
     PCLK_DECL
@@ -777,7 +877,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         __syncthreads();                       // tile o and its tables are visible to the whole CTA
         PCLK(2);
         const double2 *const hiF = s_hiF + buf * ntab;
-        for (int r = 0; r < (bcast ? 0 : P.nrounds); ++r) {
+        for (int r = 0; r < P.nrounds; ++r) {
             const RoundDesc &R = P.rounds[r];
             const bool last = r + 1 == P.nrounds;
             unsigned thrL = 0;
@@ -869,32 +969,6 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             unsigned swl = sw_lo;
             asm volatile("" : "+r"(swl));     // as in issue_loads: no hoisting of the 32 addresses
             double leaf_acc = 0.0;
-            if (bcast) {
-                // element l of the tile = the input element with the target bits cleared, or zero where a
-                // pinned bit outside the targets differs from the basis index
-                unsigned l_lo = 0;
-                for (int k = 0; k < P.st_nruns; ++k) {
-                    const int sh = P.st_lruns[k].shift;
-                    const unsigned t = tid & P.st_lruns[k].mask;
-                    l_lo |= sh >= 0 ? t << sh : t >> -sh;
-                }
-                const unsigned chk = sup_mt & bc_keep;
-                double2 v[kSlots];
-#pragma unroll
-                for (int i = 0; i < kSlots; ++i) {
-                    const unsigned l = l_lo | tile_swizzle(P.st_l_hi[i] >> 4);     // the swizzle is an involution
-                    v[i] = ((l ^ sup_vt) & chk) == 0u ? *reinterpret_cast<const double2 *>(tile_b + tile_swizzle(l & bc_keep) * 16u)
-                                                      : make_double2(0.0, 0.0);
-                }
-                __syncthreads();               // every input is in registers: the tile is dead
-                if (has_next) issue_loads(o_next);
-#pragma unroll
-                for (int i = 0; i < kSlots; ++i) {
-                    const double2 x = scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i];
-                    if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
-                    st_global_cs(q + P.st_off_hi[i], x);
-                }
-            } else {
             {   // first half: read and store right away
                 double2 v[kSlots / 2];
 #pragma unroll
@@ -926,7 +1000,6 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                     if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
                     st_global_cs(q + P.st_off_hi[kSlots / 2 + i], x);
                 }
-            }
             }
             if (leaf_fuse) {
                 // lane l has summed elements l, l+32, ... of its warp's leaf in increasing order: finish

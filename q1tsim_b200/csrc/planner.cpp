@@ -77,6 +77,22 @@ static void fill_outer_tables(SweepProgram &P)
             P.o_src[c][v] = so;
             P.o_dst[c][v] = dof;
         }
+    // destination-ordered walk: walk bit i = the outer bit with the i-th lowest destination position
+    int ord[kMaxBits];
+    for (int i = 0; i < P.n_outer; ++i) ord[i] = i;
+    std::sort(ord, ord + P.n_outer, [&](int a, int b) { return P.odst[a] < P.odst[b]; });
+    for (int c = 0; c < kOuterChunks; ++c)
+        for (int v = 0; v < (1 << kOuterChunkBits); ++v) {
+            uint64_t so = 0, dof = 0;
+            for (int b = 0; b < kOuterChunkBits; ++b) {
+                const int i = c * kOuterChunkBits + b;
+                if (i >= P.n_outer || !((v >> b) & 1)) continue;
+                so |= 1ull << P.osrc[ord[i]];
+                dof |= 1ull << P.odst[ord[i]];
+            }
+            P.w_src[c][v] = so;
+            P.w_dst[c][v] = dof;
+        }
 }
 
 // Decide which rounds can skip shared-memory staging and how wide each inter-round barrier must be.

@@ -111,6 +111,11 @@ struct SweepProgram {
     // tile base address of outer index o = OR over chunks c of o_src[c][(o >> 6c) & 63]
     uint64_t o_src[kOuterChunks][1 << kOuterChunkBits];
     uint64_t o_dst[kOuterChunks][1 << kOuterChunkBits];
+    // the same maps for a walk index whose bits are the outer bits in ascending DESTINATION order: a kernel
+    // that walks w = 0, 1, 2, .. writes its tiles as a few sequential streams (broadcast sweeps: the reads
+    // are negligible there, the write pattern is everything)
+    uint64_t w_src[kOuterChunks][1 << kOuterChunkBits];
+    uint64_t w_dst[kOuterChunks][1 << kOuterChunkBits];
     // load: element e = tid | i<<TB lives at source offset dep(tid) | ld_hi[i], tile index e
     BitRun ld_runs[kMaxRuns];          // tid -> source offset (shift < 64)
     uint64_t ld_hi[kSlots];
