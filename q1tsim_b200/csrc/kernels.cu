@@ -43,6 +43,12 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
     return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
+__device__ __forceinline__ double2 ld_shared_f64x2(unsigned saddr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ void st_global_cs(double2 *p, double2 v)
 {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
@@ -578,6 +584,7 @@ __device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ 
     const bool leaf_fuse = leaf_col != nullptr;
     const bool zero_fill = P.sup_mode == 2;
     const unsigned sw_tid = tile_swizzle(tid) * 16u;
+    const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile_b));
     const unsigned tgt = ~bc_keep & ((1u << T) - 1u);
     const unsigned tb_a = __ffs(tgt) - 1, tb_b = __ffs(tgt & (tgt - 1u)) - 1;
     auto slot_pat = [&](unsigned k) { return ((k & 1u) << tb_a) | (((k >> 1) & 1u) << tb_b); };
@@ -599,14 +606,20 @@ __device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ 
         }
         return t;
     };
+    // which of its 32 load slots a thread has to fetch: the elements inside the support (for most threads: none)
+    unsigned ldmask = 0;
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i) {
+        const unsigned e = tid | ((unsigned)i << TB);
+        ldmask |= (((e ^ sup_vt) & sup_mt) == 0u ? 1u : 0u) << i;
+    }
     auto issue_slot = [&](unsigned long long t, unsigned k) {
-        if (t < ntiles) {
+        if (ldmask != 0u && t < ntiles) {
             const double2 *__restrict__ p = src + (outer_base(P.w_src, t, P.n_outer) | soff_t);
             const unsigned sw = sw_tid ^ (tile_swizzle(slot_pat(k)) * 16u);
-#pragma unroll
-            for (int i = 0; i < kSlots; ++i) {
-                const unsigned e = tid | ((unsigned)i << TB);
-                if (((e ^ sup_vt) & sup_mt) == 0u) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+            for (unsigned m = ldmask; m != 0u; m &= m - 1u) {
+                const int i = __ffs(m) - 1;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(tile_s + (sw ^ P.ld_sw_hi[i])), "l"(p + P.ld_hi[i]));
             }
         }
         asm volatile("cp.async.commit_group;\n" ::);     // one group per tile, empty ones included
@@ -617,7 +630,17 @@ __device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ 
         const unsigned t = tid & P.st_lruns[k].mask;
         l_lo |= sh >= 0 ? t << sh : t >> -sh;
     }
+    // per thread and slot, once: where the source element sits in the tile (slot pattern not yet applied) and
+    // whether it can be non-zero at all
     const unsigned chk = sup_mt & bc_keep;
+    unsigned so[kSlots];
+    unsigned valid = 0;
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i) {
+        const unsigned l = l_lo | tile_swizzle(P.st_l_hi[i] >> 4);     // the swizzle is an involution
+        so[i] = tile_swizzle(l & bc_keep) * 16u;
+        valid |= (((l ^ sup_vt) & chk) == 0u ? 1u : 0u) << i;
+    }
     unsigned long long o = next_from(blockIdx.x);
     unsigned long long o1 = o < ntiles ? next_from(o + gridDim.x) : o, o2 = o1 < ntiles ? next_from(o1 + gridDim.x) : o1,
                        o3 = o2 < ntiles ? next_from(o2 + gridDim.x) : o2;
@@ -628,7 +651,7 @@ __device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ 
         asm volatile("cp.async.wait_group 2;\n" ::: "memory");
         __syncthreads();                   // the inputs of tile o are visible; every thread is done with slot (k + 3) & 3
         issue_slot(o3, k + 3);
-        const unsigned pat = slot_pat(k);
+        const unsigned patsw = tile_swizzle(slot_pat(k)) * 16u;           // the swizzle is linear over xor
         const unsigned long long db = outer_base(P.w_dst, o, P.n_outer) | doff_t;
         double2 *__restrict__ q = dst + db;
         double leaf_acc = 0.0;
@@ -636,9 +659,8 @@ __device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ 
         for (int i = 0; i < kSlots; ++i) {
             // element l of the tile = the input element with the target bits cleared, or zero where a
             // pinned bit outside the targets differs from the basis index
-            const unsigned l = l_lo | tile_swizzle(P.st_l_hi[i] >> 4);     // the swizzle is an involution
             double2 x = make_double2(0.0, 0.0);
-            if (((l ^ sup_vt) & chk) == 0u) x = *reinterpret_cast<const double2 *>(tile_b + tile_swizzle((l & bc_keep) | pat) * 16u);
+            if ((valid >> i) & 1u) x = ld_shared_f64x2(tile_s + (so[i] ^ patsw));
             if (scale != 1.0) x = make_double2(x.x * scale, x.y * scale);
             if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
             st_global_cs(q + P.st_off_hi[i], x);
