@@ -5,7 +5,9 @@
 //   histograms       circuit.rs:773-841
 #include "circuit.h"
 
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace q1t {
@@ -207,8 +209,20 @@ CircuitError Circuit::state_err(int rc)
 
 // circuit.rs:562-600: fresh quantum state (always the statevector backend here),
 // classical register cleared
+// Q1T_HOST_PROFILE=1: one line per execute() on stderr with the host-side phases (microseconds)
+static bool host_profile_on()
+{
+    static const bool on = std::getenv("Q1T_HOST_PROFILE") && std::atoi(std::getenv("Q1T_HOST_PROFILE")) != 0;
+    return on;
+}
+static double now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 CircuitError Circuit::execute(size_t nr_shots, q1t_rng rng, const double *qubit_coefs)
 {
+    const double t0 = host_profile_on() ? now_us() : 0.0;
     q_state_.reset(new DeviceVectorState(nr_qbits_, nr_shots, device));
     const int rc = qubit_coefs ? q_state_->init_from_qubit_coefs(qubit_coefs) : q_state_->init_zero_state();
     if (rc) {
@@ -219,6 +233,7 @@ CircuitError Circuit::execute(size_t nr_shots, q1t_rng rng, const double *qubit_
     }
     c_state_.assign(nr_shots, 0);
     has_cstate_ = true;
+    if (host_profile_on()) std::fprintf(stderr, "q1t host profile: new state + init %.0f us\n", now_us() - t0);
     return do_execute(rng);
 }
 
@@ -252,10 +267,18 @@ CircuitError Circuit::do_execute(q1t_rng rng)
     std::vector<std::complex<double>> mat;
     std::vector<uint8_t> apply;
 #define TRY(expr) do { const int rc__ = (expr); if (rc__) return state_err(rc__); } while (0)
+    const bool prof = host_profile_on();
+    double t_kind[2] = { 0.0, 0.0 }, t_eval = 0.0;          // [0] gates (evaluate + lower + queue), [1] everything that observes the state
     for (const CircuitOp &op : ops_) {
+        const double t_op = prof ? now_us() : 0.0;
+        struct Tick {
+            bool on; double t0; double &acc;
+            ~Tick() { if (on) acc += now_us() - t0; }
+        } tick{ prof, t_op, t_kind[op.kind == CircuitOp::Gate || op.kind == CircuitOp::ConditionalGate ? 0 : 1] };
         switch (op.kind) {
         case CircuitOp::Gate: {
             const int nb = op.gate.evaluate(mat);
+            if (prof) t_eval += now_us() - t_op;
             if (nb < 0) return mkerr(Q1T_ERR_PARSE, "invalid gate");
             TRY(q.apply_gate(reinterpret_cast<const double *>(mat.data()), (size_t)1 << nb, op.bits.data(), op.bits.size(),
                              op.gate.description().c_str()));
@@ -309,7 +332,11 @@ CircuitError Circuit::do_execute(q1t_rng rng)
 #undef TRY
     // the reference's execute() returns with the state fully evolved; queued gates after the
     // last measurement are run here so that errors surface now
+    const double t_fl = prof ? now_us() : 0.0;
     const int rc = q.flush();
+    if (prof)
+        std::fprintf(stderr, "q1t host profile: %zu ops: gates %.0f us (matrix() %.0f us), measure/peek/reset %.0f us, final flush %.0f us\n",
+                     ops_.size(), t_kind[0], t_eval, t_kind[1], now_us() - t_fl);
     if (rc) return state_err(rc);
     return ok();
 }

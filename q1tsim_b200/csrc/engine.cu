@@ -763,13 +763,18 @@ int DeviceVectorState::canonicalize()
     return Q1T_OK;
 }
 
-int DeviceVectorState::flush()
+int DeviceVectorState::flush_async()
 {
     int rc = ensure_device();
     if (rc) return rc;
     rc = run_queue(true);
     if (rc) return rc;
-    rc = canonicalize();
+    return canonicalize();
+}
+
+int DeviceVectorState::flush()
+{
+    int rc = flush_async();
     if (rc) return rc;
     CK(cudaStreamSynchronize(stream_));
     return Q1T_OK;
@@ -903,10 +908,27 @@ int DeviceVectorState::ensure_scratch(size_t ncols)
 int DeviceVectorState::reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols,
                                       bool leaf_totals_ready)
 {
+    int rc = reduce_launch(mask, want, dev_cols, leaf_totals_ready);
+    if (rc) return rc;
+    return reduce_fetch(totals, dev_cols.size());
+}
+
+// column totals back on the host (blocks until the stream has drained)
+int DeviceVectorState::reduce_fetch(std::vector<double> &totals, size_t ndev)
+{
+    totals.assign(ndev, 0.0);
+    if (!ndev) return Q1T_OK;
+    CK(cudaMemcpyAsync(totals.data(), d_totals_, sizeof(double) * ndev, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// canonical leaf totals + prefix scan of every dense column, enqueued only
+int DeviceVectorState::reduce_launch(uint64_t mask, uint64_t want, std::vector<int> &dev_cols, bool leaf_totals_ready)
+{
     dev_cols.clear();
     for (size_t c = 0; c < cols_.size(); ++c)
         if (!cols_[c].basis) dev_cols.push_back((int)c);
-    totals.assign(dev_cols.size(), 0.0);
     if (dev_cols.empty()) return Q1T_OK;
     int rc = ensure_scratch(dev_cols.size());
     if (rc) return rc;
@@ -921,8 +943,6 @@ int DeviceVectorState::reduce_columns(uint64_t mask, uint64_t want, std::vector<
     CK(launch_scan(d_leaf_, d_block_, d_totals_, (int)dev_cols.size(), n_, stream_));
     time_end(stats.read_ms);
     stats.kernel_launches += 2;
-    CK(cudaMemcpyAsync(totals.data(), d_totals_, sizeof(double) * dev_cols.size(), cudaMemcpyDeviceToHost, stream_));
-    CK(cudaStreamSynchronize(stream_));
     return Q1T_OK;
 }
 
@@ -1273,14 +1293,37 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
         if (cbits[j] >= 64) return fail(Q1T_ERR_INVALID_ARGUMENT, "classical bit index must be < 64");
     want_leaf_fusion_ = fuse_leaf_totals_;
     leaf_fused_ = false;
-    int rc = flush();
+    int rc = flush_async();                 // sweeps (and relabel) enqueued, not waited for
     const bool leaf_ready = leaf_fused_;
     want_leaf_fusion_ = leaf_fused_ = false;
     if (rc) return rc;
     std::vector<double> totals;
     std::vector<int> dev;
-    rc = reduce_columns(0, 0, totals, dev, leaf_ready);
+    rc = reduce_launch(0, 0, dev, leaf_ready);
     if (rc) return rc;
+    // While the device works: draw the uniforms of every shot (one word per shot, column order, as
+    // vectorstate.rs:120-133 consumes them) and sort them per column.  chosen = u * scale + low is monotone in
+    // u, so scaling the sorted u's later gives exactly the sorted `chosen` values.
+    std::vector<double> unit;               // value0_1 of every shot of the dense columns, grouped per column, sorted
+    {
+        size_t ndense = 0;
+        for (const Column &c : cols_)
+            if (!c.basis) ndense += c.count;
+        unit.reserve(ndense);
+        for (const Column &c : cols_) {
+            if (c.basis) {
+                // WeightedIndex over a unit vector: every draw consumes one word and returns basis_idx
+                for (size_t j = 0; j < c.count; ++j) (void)rng.next_u64(rng.ctx);
+                continue;
+            }
+            const size_t at = unit.size();
+            for (size_t j = 0; j < c.count; ++j) unit.push_back(uniform_unit(rng));
+            std::sort(unit.begin() + (long)at, unit.end());
+        }
+    }
+    rc = reduce_fetch(totals, dev.size());
+    if (rc) return rc;
+    if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
     const int leaf_bits = n_ < kCanonLeafBits ? n_ : kCanonLeafBits;
     const size_t nleaves = (size_t)1 << (n_ - leaf_bits);
     const size_t nblocks = (nleaves + kCanonBlock - 1) / kCanonBlock;
@@ -1288,14 +1331,11 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
     std::vector<std::pair<uint64_t, size_t>> state_counts;   // (basis index, multiplicity), grouped per column
     std::vector<double> chosen;
     std::vector<uint64_t> idx;
-    size_t k = 0;
+    size_t k = 0, unit_at = 0;
     for (size_t c = 0; c < cols_.size(); ++c) {
         const size_t cnt = cols_[c].count;
         if (cols_[c].basis && cols_[c].basis_idx == UINT64_MAX) return fail(Q1T_ERR_INVALID_ARGUMENT, "state column has zero norm");
         if (cols_[c].basis) {
-            // WeightedIndex over a unit vector: every draw consumes one word and returns basis_idx
-            for (size_t j = 0; j < cnt; ++j) (void)rng.next_u64(rng.ctx);
-            if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
             if (cnt) state_counts.push_back(std::make_pair(cols_[c].basis_idx, cnt));
             continue;
         }
@@ -1303,9 +1343,8 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
         if (!(total > 0.0)) return fail(Q1T_ERR_INVALID_ARGUMENT, "state column has zero norm");
         const UniformF64 u = uniform_new(0.0, total);
         chosen.resize(cnt);
-        for (size_t j = 0; j < cnt; ++j) chosen[j] = uniform_sample(u, rng);
-        if (rng_failed(rng)) return fail(Q1T_ERR_RNG, "the injected random generator ran out of words");
-        std::sort(chosen.begin(), chosen.end());
+        for (size_t j = 0; j < cnt; ++j) chosen[j] = uniform_scale(u, unit[unit_at + j]);
+        unit_at += cnt;
         if (cnt > draws_cap_) {
             CK(cudaStreamSynchronize(stream_));
             scratch_free(device_, d_chosen_, sizeof(double) * draws_cap_);
@@ -1335,11 +1374,18 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
     uint64_t m = 0;
     for (size_t j = 0; j < ncbits; ++j) m |= 1ull << cbits[j];
     const uint64_t mask = ~m;
+    // one 256-entry table per byte of the basis index instead of a loop over the qubits per outcome
+    const int nbytes = (n_ + 7) / 8;
+    std::vector<uint64_t> route((size_t)nbytes * 256, 0);
+    for (int b = 0; b < nbytes; ++b)
+        for (int v = 1; v < 256; ++v) {
+            const int low = v & (v - 1), bit = 8 * b + __builtin_ctz((unsigned)v);      // index bit `bit` <-> qubit n-1-bit
+            route[(size_t)b * 256 + v] = route[(size_t)b * 256 + low] | (bit < n_ ? 1ull << cbits[n_ - 1 - bit] : 0ull);
+        }
     size_t off = 0;
     for (const auto &sc : state_counts) {
         uint64_t word = 0;
-        for (int q = 0; q < n_; ++q)
-            if ((sc.first >> (n_ - 1 - q)) & 1ull) word |= 1ull << cbits[q];
+        for (int b = 0; b < nbytes; ++b) word |= route[(size_t)b * 256 + ((sc.first >> (8 * b)) & 255ull)];
         for (size_t j = off; j < off + sc.second; ++j) res[j] = (res[j] & mask) | word;
         off += sc.second;
     }

@@ -58,6 +58,7 @@ public:
     int marginal0(size_t qbit, double *w0_out);
     int column_totals(double *out);
     int flush();                 // run queued gates, restore canonical layout, synchronise
+    int flush_async();           // the same, enqueued only
     int set_option(const char *key, long value);
 
     size_t nr_bits() const { return n_; }
@@ -115,6 +116,8 @@ private:
     int run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel);
     int run_generic(const LoweredGate &g, const std::vector<int> &which);
     int canonicalize();                      // undo swap relabelling (perm_ -> identity)
+    int reduce_launch(uint64_t mask, uint64_t want, std::vector<int> &dev_cols, bool leaf_totals_ready);
+    int reduce_fetch(std::vector<double> &totals, size_t ndev);
     int reduce_columns(uint64_t mask, uint64_t want, std::vector<double> &totals, std::vector<int> &dev_cols,
                        bool leaf_totals_ready = false);
     int ensure_scratch(size_t ncols);
@@ -127,6 +130,8 @@ private:
 struct UniformF64 { double low, scale; };
 UniformF64 uniform_new(double low, double high);
 double uniform_sample(const UniformF64 &u, q1t_rng rng);
+double uniform_unit(q1t_rng rng);                          // uniform_sample == uniform_scale(u, uniform_unit(rng))
+double uniform_scale(const UniformF64 &u, double v01);
 uint64_t binomial_sample(q1t_rng rng, uint64_t n, double p);
 bool rng_failed(q1t_rng rng);    // true if a built-in injected generator ran dry
 

@@ -64,6 +64,16 @@ double uniform_sample(const UniformF64 &u, q1t_rng rng)
     return (v12 - 1.0) * u.scale + u.low;
 }
 
+// the same draw in two halves: value0_1 now, the affine map when low / scale are known (monotone in v)
+double uniform_unit(q1t_rng rng)
+{
+    const uint64_t bits = (rng.next_u64(rng.ctx) >> 12) | 0x3FF0000000000000ull;
+    double v12;
+    std::memcpy(&v12, &bits, sizeof v12);
+    return v12 - 1.0;
+}
+double uniform_scale(const UniformF64 &u, double v01) { return v01 * u.scale + u.low; }
+
 static double standard_f64(q1t_rng rng)
 {
     return (double)(rng.next_u64(rng.ctx) >> 11) * (1.0 / 9007199254740992.0);
