@@ -93,6 +93,8 @@ class CircuitError(Exception):
 
 def _unpack(res):
     """python/q1tsimffi.py:85-108 (unpack_result)"""
+    if res.restype == RESULT_EMPTY:       # owns no data (ffi.rs:139-169): nothing to free
+        return None
     L = _lib()
     try:
         if res.restype == RESULT_ERROR:
@@ -132,8 +134,26 @@ class RefParam:
         return C.pointer(self._v)
 
 
+_ARR_T = {}          # ctypes array types by (element type, length): creating them is the slow part of a call
+_NAME_B = {}         # gate name -> bytes
+
+
+def _arr_t(elem, n):
+    t = _ARR_T.get((elem, n))
+    if t is None:
+        t = _ARR_T[(elem, n)] = elem * n
+    return t
+
+
+def _name_b(name):
+    b = _NAME_B.get(name)
+    if b is None:
+        b = _NAME_B[name] = name.encode()
+    return b
+
+
 def _params(values):
-    arr = (_Param * max(len(values), 1))()
+    arr = _arr_t(_Param, max(len(values), 1))()
     for i, v in enumerate(values):
         if isinstance(v, RefParam):
             arr[i].value = 0.0
@@ -144,9 +164,19 @@ def _params(values):
     return arr
 
 
+_SZ_CACHE = {}       # tuple of indices -> (read-only c_size_t array, length); the library copies what it is given
+_PARAM_CACHE = {}    # tuple of plain float parameters -> read-only parameter_t array
+
+
 def _sz(xs):
-    xs = [int(x) for x in xs]
-    return (C.c_size_t * max(len(xs), 1))(*xs), len(xs)
+    key = tuple(xs)
+    hit = _SZ_CACHE.get(key)
+    if hit is None:
+        n = len(key)
+        hit = (_arr_t(C.c_size_t, max(n, 1))(*[int(x) for x in key]), n)
+        if len(_SZ_CACHE) < 65536:
+            _SZ_CACHE[key] = hit
+    return hit
 
 
 class Circuit:
@@ -180,10 +210,19 @@ class Circuit:
     def add_gate(self, name, qbits, params=()):
         if not isinstance(name, str):
             return self.add_matrix_gate(name, qbits)
-        params = list(params or ())
-        self._keep.extend(p for p in params if isinstance(p, RefParam))
         q, nq = _sz(qbits)
-        return _unpack(self._L.circuit_add_gate(self._p, name.encode(), q, nq, _params(params) if params else None, len(params)))
+        if not params:
+            return _unpack(self._L.circuit_add_gate(self._p, _name_b(name), q, nq, None, 0))
+        params = tuple(params)
+        arr = _PARAM_CACHE.get(params)             # only tuples of plain numbers are ever stored
+        if arr is None:
+            refs = [p for p in params if isinstance(p, RefParam)]
+            arr = _params(params)
+            if refs:
+                self._keep.extend(refs)
+            elif len(_PARAM_CACHE) < 65536:
+                _PARAM_CACHE[params] = arr
+        return _unpack(self._L.circuit_add_gate(self._p, _name_b(name), q, nq, arr, len(params)))
 
     def add_composite_gate(self, name, description, qbits, nr_iterations=1):
         """`Composite::from_string(name, description)` on `qbits` (composite.rs:273-450), body repeated

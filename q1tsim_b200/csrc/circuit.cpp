@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace q1t {
 
@@ -73,21 +74,33 @@ int gate_spec_from_name(const char *name, const Param *params, size_t nparams, G
 {
     out = GateSpec();
     std::string nm(name ? name : "");
-    const std::string original = nm;
     for (char &ch : nm) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32);
-    out.name = nm;
     // arity check the way the reference reports it (ffi.rs:216-305, error.rs ParseError)
     static const struct { const char *n; int np; } arity[] = {
         { "rx", 1 }, { "ry", 1 }, { "rz", 1 }, { "u1", 1 }, { "u2", 2 }, { "u3", 3 }, { "crx", 1 }, { "cry", 1 }, { "crz", 1 },
         { "cu1", 1 }, { "cu2", 2 }, { "cu3", 3 }, { "ccrx", 1 }, { "ccry", 1 }, { "ccrz", 1 }, { nullptr, 0 } };
-    int want = 0;
-    for (int a = 0; arity[a].n; ++a) if (nm == arity[a].n) want = arity[a].np;
-    double probe[4] = { 0.1, 0.2, 0.3, 0.4 };
-    std::complex<double> tmp[64];
-    const int nb = builtin_gate_matrix(nm.c_str(), probe, (size_t)want, tmp);
-    if (nb == -1) { err = "Unknown gate \"" + original + "\""; return Q1T_ERR_PARSE; }
+    // (name -> number of qubits) is a fixed table: probe every name once per process, not once per gate added
+    struct Known { std::string name; int nb, np; };
+    static std::vector<Known> known;
+    static std::mutex known_mu;
+    int want = 0, nb = -1;
+    {
+        std::lock_guard<std::mutex> lk(known_mu);
+        bool hit = false;
+        for (const Known &k : known)
+            if (k.name == nm) { nb = k.nb; want = k.np; hit = true; break; }
+        if (!hit) {
+            for (int a = 0; arity[a].n; ++a) if (nm == arity[a].n) want = arity[a].np;
+            const double probe[4] = { 0.1, 0.2, 0.3, 0.4 };
+            std::complex<double> tmp[64];
+            nb = builtin_gate_matrix(nm.c_str(), probe, (size_t)want, tmp);
+            if (nb != -1 && known.size() < 256) known.push_back({ nm, nb, want });
+        }
+    }
+    if (nb == -1) { err = "Unknown gate \"" + std::string(name ? name : "") + "\""; return Q1T_ERR_PARSE; }
+    out.name.swap(nm);
     if ((int)nparams != want && want > 0) {
-        std::string up = nm;
+        std::string up = out.name;
         for (char &ch : up) if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
         char buf[160];
         std::snprintf(buf, sizeof buf, "Expected %d arguments to \"%s\" gate, got %zu", want, up.c_str(), nparams);
@@ -104,11 +117,11 @@ CircuitError Circuit::add_gate(const GateSpec &g, const std::vector<size_t> &bit
 {
     for (size_t b : bits)
         if (b >= nr_qbits_) return invalid_qbit(b);          // circuit.rs:164-167
-    CircuitOp op;
+    ops_.emplace_back();
+    CircuitOp &op = ops_.back();
     op.kind = CircuitOp::Gate;
     op.gate = g;
     op.bits = bits;
-    ops_.push_back(op);
     return ok();
 }
 
