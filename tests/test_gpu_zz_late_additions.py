@@ -1,6 +1,7 @@
-"""GPU parity of the in-place relabelling path (planner.cpp plan_inplace_relabel, engine.cu
-canonicalize): forced at small sizes with the "inplace_relabel" option, against the CPU oracle.  Kept in its own
-file, after the other GPU suites."""
+"""GPU parity tests added late in round 1, kept in one file that sorts after the other GPU suites:
+* the in-place relabelling path (planner.cpp plan_inplace_relabel, engine.cu canonicalize), forced
+  at small sizes with the "inplace_relabel" option, against the CPU oracle;
+* the reference's own gate known-answer vectors (tests/golden/gate_kats.json) through the engine."""
 import numpy as np
 import pytest
 
@@ -65,3 +66,21 @@ def test_inplace_relabel_multi_column():
     for c in range(len(o.counts)):
         assert rel_l2(e.column(c), o.column(c)) < TOL
     e.close()
+
+
+def test_reference_gate_kats_on_the_engine():
+    """the reference's own gate known-answer vectors (tests/golden/gate_kats.json, src/gates/*.rs unit tests)
+    through the CUDA engine: the gate on the first k qubits of every column of `state`"""
+    from tests import kat_fixtures as K
+    for case in K.cases("apply"):
+        state, want = K.carray(case["state"]), K.carray(case["result"])
+        m = K.matrix_of(case["gate"], O.gate_matrix)
+        k, n = int(np.log2(m.shape[0])), int(np.log2(state.shape[0]))
+        for col in range(state.shape[1]):
+            if not np.any(state[:, col]):
+                continue
+            e = E.VectorState(n, 1)
+            e.set_column(0, state[:, col])
+            e.apply_gate(m, list(range(k)), case["gate"]["name"])
+            assert np.abs(e.column(0) - want[:, col]).max() <= 1e-12, (case["source"], col)
+            e.close()
