@@ -9,8 +9,7 @@
  *   - circuit_execute always runs the statevector backend on the GPU (the
  *     reference switches to its stabilizer backend for all-Clifford circuits,
  *     circuit.rs:576-583, which is out of scope here);
- *   - circuit_open_qasm / circuit_c_qasm produce the reference's text (circuit.rs:877-1146);
- *     circuit_latex returns an error result (the qcircuit drawing back-end is out of scope);
+ *   - circuit_open_qasm / circuit_c_qasm / circuit_latex produce the reference's text (circuit.rs:877-1231);
  *   - extra entry points: circuit_add_matrix_gate, circuit_add_composite_gate, circuit_add_loop_gate,
  *     circuit_execute_with_rng,
  *     circuit_reexecute_with_rng, circuit_histogram_u64, circuit_engine_stats,
@@ -59,7 +58,7 @@ result_t   circuit_reset_all(circuit_t *ptr);                                /* 
 result_t   circuit_execute(circuit_t *ptr, size_t nr_shots);                 /* ffi.rs:570-585 */
 result_t   circuit_reexecute(circuit_t *ptr);                                /* ffi.rs:588-603 */
 result_t   circuit_histogram(const circuit_t *ptr);                          /* ffi.rs:606-621 */
-result_t   circuit_latex(const circuit_t *ptr);                              /* ffi.rs:624-639 (out of scope: error) */
+result_t   circuit_latex(const circuit_t *ptr);                              /* ffi.rs:624-639; circuit.rs:1148-1231 */
 result_t   circuit_open_qasm(const circuit_t *ptr);                          /* ffi.rs:643-658; circuit.rs:877-1017 */
 result_t   circuit_c_qasm(const circuit_t *ptr);                             /* ffi.rs:661-676; circuit.rs:1019-1146 */
 

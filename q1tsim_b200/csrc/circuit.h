@@ -46,6 +46,7 @@ struct CircuitOp {       // circuit.rs:27-51
     size_t group_id = 0, group_repeat = 1;
     bool group_loop = false;
     std::string group_name;
+    std::vector<size_t> group_bits;    // the qubits the composite / loop was added on
 };
 
 struct CircuitError {
@@ -87,6 +88,7 @@ public:
     // export.cpp: circuit.rs:877-1146
     CircuitError open_qasm(std::string &out) const;
     CircuitError c_qasm(std::string &out) const;
+    CircuitError latex(std::string &out) const;          // latex.cpp: circuit.rs:1148-1231
     DeviceVectorState *state() { return q_state_.get(); }
     int device = 0;
 

@@ -358,6 +358,7 @@ CircuitError Circuit::add_composite(const std::string &name, const std::string &
         ops_[i].group_repeat = repeat;
         ops_[i].group_loop = is_loop;
         ops_[i].group_name = name;
+        ops_[i].group_bits = bits;
     }
     return e;
 }

@@ -301,8 +301,9 @@ static result_t res_string(const std::string &text) { result_t r = { dup_cstring
 result_t circuit_latex(const circuit_t *ptr)
 {
     if (!ptr) return res_error("Pointer to circuit is NULL");
-    // ExportError::NotImplemented wording (error.rs:53-55); the qcircuit drawing back-end is out of scope
-    return res_error("Export to LaTeX was not implemented for \"the B200 statevector engine\"");
+    std::string text;
+    const CircuitError e = ptr->impl.latex(text);
+    return e.code ? res_error(e.msg) : res_string(text);
 }
 result_t circuit_open_qasm(const circuit_t *ptr)
 {

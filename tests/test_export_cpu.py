@@ -1,4 +1,5 @@
-"""OpenQasm / c-Qasm export, q1tsim_b200/csrc/export.cpp, pinned to the reference's own
+"""OpenQasm / c-Qasm export, q1tsim_b200/csrc/export.cpp, and LaTeX export
+(csrc/latex.cpp, tests at the end), pinned to the reference's own
 unit tests: circuit.rs:1987-2158 (whole circuits), the per-gate `test_open_qasm` / `test_c_qasm` of
 src/gates/*.rs, controlled.rs:691-817, composite.rs:1619-1666, staticloop.rs:324-376,
 export/openqasm.rs:53-60.  The reference tests name the bits qb0, qb1, ...; a circuit names them
@@ -187,5 +188,75 @@ def test_user_gate_has_no_export():
             c.open_qasm()
         with pytest.raises(QC.CircuitError, match='Export to c-Qasm was not implemented for "MyX"'):
             c.c_qasm()
-        with pytest.raises(QC.CircuitError, match="Export to LaTeX was not implemented"):
+        # default `Latex` trait method (export/latex.rs:547-554): a block with the description
+        assert c.latex() == "\\Qcircuit @C=1em @R=.7em {\n    \\lstick{\\ket{0}} & \\gate{MyX} & \\qw \\\\\n}\n"
+
+
+# ---- LaTeX / Qcircuit (csrc/latex.cpp) ---------------------------------------------------------------------
+import json  # noqa: E402
+import os  # noqa: E402
+
+_LATEX = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "latex_kats.json")))["cases"]
+_TABLE = {"H", "I", "X", "Y", "Z", "S", "Sdg", "T", "Tdg", "V", "Vdg", "RX", "RY", "RZ", "U1", "U2", "U3", "CX", "CY", "CZ", "Swap", "CH",
+          "CRX", "CRY", "CRZ", "CS", "CSdg", "CT", "CTdg", "CU1", "CU2", "CU3", "CV", "CVdg", "CCX", "CCZ", "CCRX", "CCRY", "CCRZ"}
+
+
+def _nr_bits(g):
+    if g["name"] == "Kron":
+        return _nr_bits(g["args"][0]) + _nr_bits(g["args"][1])
+    if g["name"] == "C":
+        return 1 + _nr_bits(g["args"][0])
+    n = g["name"].lower()
+    return (3 if n.startswith("cc") else 2 if n.startswith("c") or n == "swap" else 1)
+
+
+def _add(c, g, bits):
+    """one gate description of the fixtures -> builder calls"""
+    name, args = g["name"], g["args"]
+    if name == "Kron":                      # kron.rs:147-156: the two halves one after the other
+        n0 = _nr_bits(args[0])
+        _add(c, args[0], bits[:n0]); _add(c, args[1], bits[n0:])
+    elif name == "C":                       # C<G> of a table gate is the table's c<g>
+        c.add_gate("c" + args[0]["name"].lower(), bits, args[0]["args"])
+    elif name == "Composite":
+        c.add_composite_gate(args[0], args[1], bits)
+    elif name == "Loop":
+        c.add_loop_gate(args[0], args[2]["args"][1], bits, args[1])
+    else:
+        assert name in _TABLE, name
+        c.add_gate(name.lower(), bits, args)
+
+
+@pytest.mark.parametrize("case", _LATEX, ids=lambda k: "%s-%s" % (k["source"].replace("src/gates/", ""), k["gate"]["name"]))
+def test_latex_gate_kats(case):
+    """the reference's per-gate test_latex expectations (tests/golden/latex_kats.json)"""
+    with QC.Circuit(case["nr_qbits"], case["nr_cbits"]) as c:
+        _add(c, case["gate"], case["bits"])
+        assert c.latex() == case["latex"]
+
+
+def test_latex_circuit():
+    # circuit.rs:2160-2184
+    with QC.Circuit(2, 2) as c:
+        c.h(0); c.x(1); c.measure(0, 0); c.measure_x(1, 1); c.add_conditional_gate([0, 1], 2, "x", [0]); c.reset_all()
+        c.measure_all_basis([1, 0], "Y"); c.reset(0); c.measure_y(1, 0); c.barrier([1])
+        assert c.latex() == (
+            "\\Qcircuit @C=1em @R=.7em {\n"
+            "    \\lstick{\\ket{0}} & \\gate{H} & \\meter & \\qw & \\targ & \\push{~\\ket{0}~} \\ar @{|-{}} [0,-1] & \\meterB{Y} & "
+            "\\push{~\\ket{0}~} \\ar @{|-{}} [0,-1] & \\qw & \\qw & \\qw \\\\\n"
+            "    \\lstick{\\ket{0}} & \\gate{X} & \\qw & \\meterB{X} & \\qw & \\push{~\\ket{0}~} \\ar @{|-{}} [0,-1] & \\qw & \\meterB{Y} & "
+            "\\meterB{Y} & \\qw \\barrier{0} & \\qw \\\\\n"
+            "    \\lstick{0} & \\cw & \\cw \\cwx[-2] & \\cw & \\cctrlo{-2} & \\cw & \\cw & \\cw \\cwx[-1] & \\cw \\cwx[-1] & \\cw & \\cw \\\\\n"
+            "    \\lstick{0} & \\cw & \\cw & \\cw \\cwx[-2] & \\cctrl{-1} & \\cw & \\cw \\cwx[-3] & \\cw & \\cw & \\cw & \\cw \\\\\n"
+            "}\n")
+
+
+def test_latex_errors():
+    with QC.Circuit(3, 1) as c:
+        c.peek(0, 0)
+        with pytest.raises(QC.CircuitError, match='Export to LaTeX was not implemented for "peek"'):      # circuit.rs:1196-1202
+            c.latex()
+    with QC.Circuit(3, 0) as c:
+        c.add_gate("ccx", [1, 2, 0])          # controlled.rs:823-829: the reference panics, here an error result
+        with pytest.raises(QC.CircuitError, match="control in the middle"):
             c.latex()
