@@ -262,6 +262,10 @@ def run_ours(args, rank, world, local):
 
     roofline = roof(ts, 2, "tracked")
     roofline["input"] = "|0..0> (the timed workload): support tracking, bytes_per_launch = bytes the launches have to move"
+    # these launches are almost pure writes (broadcast sweep: 32 MiB read, 16 GiB written at n = 30); the device's
+    # write-only rate, measured with tools/write_bw_probe.py (torch fill_ of 16 GiB, round 1), is 7.5 TB/s
+    roofline["write_only_peak_gbs"] = 7500.0
+    roofline["frac_of_write_only_peak"] = roofline["achieved"] / 7500.0
     r = W.SplitMix64(1)
     coefs = []
     for _ in range(n):
