@@ -47,7 +47,8 @@ def main():
 
             def stash(mm):
                 key = "__s%d" % len(strings)
-                strings[key] = mm.group(1) if mm.group(1) is not None else mm.group(2)
+                # raw strings verbatim; ordinary literals with their escapes resolved
+                strings[key] = mm.group(1) if mm.group(1) is not None else mm.group(2).replace("\\n", "\n").replace('\\"', '"').replace("\\\\", "\\")
                 return key
             body = re.sub(r'r#"(.*?)"#|"((?:[^"\\]|\\.)*)"', stash, body, flags=re.S)
             env = dict(ENV0)

@@ -7,6 +7,8 @@ q[0], q[1], ... (circuit.rs:893-899), so the expected strings are transcribed wi
 Host-side text only: no GPU needed."""
 import math
 
+import re
+
 import pytest
 
 from q1tsim_b200 import circuit as QC
@@ -260,3 +262,44 @@ def test_latex_errors():
         c.add_gate("ccx", [1, 2, 0])          # controlled.rs:823-829: the reference panics, here an error result
         with pytest.raises(QC.CircuitError, match="control in the middle"):
             c.latex()
+
+
+# ---- every per-gate test_open_qasm / test_c_qasm expectation of the reference (tests/golden/qasm_kats.json) ----
+_QASM = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qasm_kats.json")))["cases"]
+
+
+def _sub_desc(g, bits):
+    """gate description -> one sub-gate of a Composite::from_string text on composite bits `bits`"""
+    if g["name"] == "Kron":
+        n0 = _nr_bits(g["args"][0])
+        return _sub_desc(g["args"][0], bits[:n0]) + "; " + _sub_desc(g["args"][1], bits[n0:])
+    name = ("C" + g["args"][0]["name"]) if g["name"] == "C" else g["name"]
+    args = g["args"][0]["args"] if g["name"] == "C" else g["args"]
+    return name + ("(" + ",".join(repr(float(a)) for a in args) + ")" if args else "") + " " + " ".join(str(b) for b in bits)
+
+
+@pytest.mark.parametrize("case", _QASM, ids=lambda k: "%s-%s-%s" % (k["source"].replace("src/gates/", ""), k["kind"], k["gate"]["name"]))
+def test_qasm_gate_kats(case):
+    g, names, bits = case["gate"], case["bit_names"], case["bits"]
+    cq = case["kind"] == "c_qasm"
+    if g["name"] == "Kron" and cq:
+        pytest.skip("Kron's c-Qasm form `{ a | b }` (kron.rs:117-124) has no builder equivalent: a Kron is added as its two halves")
+    if g["name"] == "Loop" and g["args"][1] == 0:
+        pytest.skip("a loop of 0 iterations adds nothing here (include/q1tsim_ffi.h)")
+    want = case["text"]
+    for i in sorted(range(len(names)), key=lambda k: -len(names[k])):
+        want = want.replace(names[i], "\0%d\0" % i)
+    want = re.sub("\0(\\d+)\0", lambda m: "q[%s]" % m.group(1), want)
+    n = len(names)
+    with QC.Circuit(n, n) as c:
+        if g["name"] == "Kron":          # kron.rs:94-101: "op0; op1" -- the composite of its halves
+            c.add_composite_gate("kron", _sub_desc(g, list(range(len(bits)))), bits)
+        else:
+            _add(c, g, bits)
+        text = c.c_qasm() if cq else c.open_qasm()
+    if cq:
+        head, tail = "version 1.0\nqubits %d\n" % n, "\n"
+    else:
+        head, tail = OQ_HEAD + "qreg q[%d];\ncreg b[%d];\n" % (n, n), ";\n"
+    assert text.startswith(head) and text.endswith(tail)
+    assert text[len(head):len(text) - len(tail)] == want
