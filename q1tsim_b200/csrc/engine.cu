@@ -568,6 +568,15 @@ int DeviceVectorState::run_queue(bool final_relabel)
     std::vector<LoweredGate> q;
     q.swap(queue_);
     queue_cols_.clear();
+    // A lazy all-zero column (a shard that holds nothing yet) stays all-zero under any gate: nothing to run for
+    // it.  EXPERIMENT, off by default (Q1T_SKIP_ZERO_SHARDS=1): written without a multi-GPU box at hand, to be
+    // measured on the sharded QFT where ranks other than 0 sweep over zeros until the first exchange.
+    static const bool skip_zero = std::getenv("Q1T_SKIP_ZERO_SHARDS") && std::atoi(std::getenv("Q1T_SKIP_ZERO_SHARDS")) != 0;
+    if (skip_zero) {
+        which.erase(std::remove_if(which.begin(), which.end(),
+                                   [&](int c) { return cols_[c].basis && cols_[c].basis_idx == UINT64_MAX; }), which.end());
+        if (which.empty()) return Q1T_OK;
+    }
     auto materialize_all = [&]() -> int {
         for (int c : which) {
             int r = materialize(cols_[c]);
