@@ -202,6 +202,16 @@ int q1t_plan_dry_run(size_t nr_bits, size_t nr_gates, const double *matrices, co
  * passes (0 for the identity), Q1T_ERR_NOT_ENOUGH_SPACE if more than max_passes are needed. */
 int q1t_plan_inplace_relabel(size_t nr_bits, long tile_bits, long coalesce_bits, const int *dstpos,
                              int *out_tiles, int *out_dstpos, size_t max_passes);
+/* test hooks (no device): the sweep programs the planner produces for a fusable gate list, as the raw structs of
+ * csrc/program.h (SweepProgram x max_sweeps, PhaseTab x max_ptabs, ptab_counts[i] = tables of sweep i) and the final
+ * logical->physical bit map; returns the number of sweeps.  tests/plan_interpreter.py executes them on the CPU.
+ * balance: bit 0 = the planner's balanced packing; bits 4.. = how the Swap relabelling is undone at the end (0 not at
+ * all, 1 as the engine does out of place: fused into the last sweep or one relabel sweep, 2 the in-place passes).
+ * q1t_plan_layout: struct sizes and constants for the reader. */
+int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const size_t *matrix_dims, const size_t *bits,
+                  const size_t *nr_gate_bits, long tile_bits, long coalesce_bits, int balance,
+                  void *progs_out, size_t max_sweeps, void *ptabs_out, size_t max_ptabs, int *ptab_counts, int *perm_out);
+int q1t_plan_layout(size_t *out, size_t n);
 int q1t_device_count(void);
 const char *q1t_version(void);
 

@@ -272,6 +272,87 @@ int q1t_plan_dry_run(size_t nr_bits, size_t nr_gates, const double *matrices, co
     return Q1T_OK;
 }
 
+// test hook: the sweep programs the planner produces for a gate list, as raw structs (program.h), so that a
+// CPU interpreter in tests/ can execute exactly what the kernels would be given
+int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const size_t *dims, const size_t *bits,
+                  const size_t *nbits, long tile_bits, long coalesce_bits, int balance,
+                  void *progs_out, size_t max_sweeps, void *ptabs_out, size_t max_ptabs, int *ptab_counts, int *perm_out)
+{
+    if (!progs_out || !ptabs_out || !ptab_counts || !perm_out || nr_bits < 5 || nr_bits > (size_t)q1t::kMaxBits)
+        return Q1T_ERR_INVALID_ARGUMENT;
+    if (tile_bits < 5 || tile_bits > q1t::kMaxTileBits || coalesce_bits < 2 || coalesce_bits > 3) return Q1T_ERR_INVALID_ARGUMENT;
+    const int n = (int)nr_bits;
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    q1t::Planner pl(n, (int)tile_bits, (int)coalesce_bits, (balance & 1) != 0);
+    size_t moff = 0, boff = 0;
+    for (size_t g = 0; g < nr_gates; ++g) {
+        const size_t k = nbits[g], dim = dims[g];
+        if (dim != ((size_t)1 << k) || k > 12) return Q1T_ERR_INVALID_NR_BITS;
+        int phys[16];
+        for (size_t j = 0; j < k; ++j) {
+            if (bits[boff + j] >= nr_bits) return Q1T_ERR_INVALID_QBIT;
+            phys[j] = perm[n - 1 - (int)bits[boff + j]];
+        }
+        q1t::LoweredGate lg;
+        std::string err;
+        if (!q1t::lower_gate(reinterpret_cast<const q1t::cplx *>(matrices + moff), (int)k, phys, lg, err)) return Q1T_ERR_UNSUPPORTED;
+        if (lg.kind == q1t::LoweredGate::SWAP) {
+            for (int l = 0; l < n; ++l) {
+                if (perm[l] == lg.b[0]) perm[l] = lg.b[1];
+                else if (perm[l] == lg.b[1]) perm[l] = lg.b[0];
+            }
+        } else if (lg.kind == q1t::LoweredGate::GENERIC) return Q1T_ERR_UNSUPPORTED;      // only fusable gate lists
+        else if (!(lg.kind == q1t::LoweredGate::POLY && lg.nb == 0)) pl.add(lg);
+        moff += 2 * dim * dim;
+        boff += k;
+    }
+    pl.finish();
+    std::vector<q1t::PlannedSweep> sweeps = pl.take();
+    // balance >> 4 selects how the Swap relabelling is undone, as DeviceVectorState::run_sweeps / canonicalize do:
+    // 0 not at all (perm_out tells the reader), 1 fused into the last sweep when its tile allows it, else one
+    // relabel sweep, 2 the in-place passes
+    const int relabel_mode = balance >> 4;
+    bool ident = true;
+    for (int l = 0; l < n; ++l) ident = ident && perm[l] == l;
+    if (relabel_mode && !ident) {
+        std::vector<int> dstpos(n);
+        for (int l = 0; l < n; ++l) dstpos[perm[l]] = l;
+        if (relabel_mode == 1) {
+            if (!sweeps.empty() && q1t::can_fuse_relabel(sweeps.back().prog, dstpos)) q1t::set_relabel(sweeps.back().prog, dstpos, false);
+            else sweeps.push_back(q1t::build_permute_sweep(n, (int)tile_bits, dstpos));
+        } else {
+            for (const q1t::InplacePass &pass : q1t::plan_inplace_relabel(n, (int)tile_bits, 3, dstpos))
+                sweeps.push_back(q1t::build_permute_sweep(n, (int)tile_bits, pass.dstpos, &pass.tile));
+        }
+        for (int l = 0; l < n; ++l) perm[l] = l;
+    }
+    if (sweeps.size() > max_sweeps) return Q1T_ERR_NOT_ENOUGH_SPACE;
+    size_t np = 0;
+    for (size_t i = 0; i < sweeps.size(); ++i) {
+        if (np + sweeps[i].ptabs.size() > max_ptabs) return Q1T_ERR_NOT_ENOUGH_SPACE;
+        std::memcpy(static_cast<char *>(progs_out) + i * sizeof(q1t::SweepProgram), &sweeps[i].prog, sizeof(q1t::SweepProgram));
+        if (!sweeps[i].ptabs.empty())
+            std::memcpy(static_cast<char *>(ptabs_out) + np * sizeof(q1t::PhaseTab), sweeps[i].ptabs.data(),
+                        sweeps[i].ptabs.size() * sizeof(q1t::PhaseTab));
+        ptab_counts[i] = (int)sweeps[i].ptabs.size();
+        np += sweeps[i].ptabs.size();
+    }
+    for (int l = 0; l < n; ++l) perm_out[l] = perm[l];
+    return (int)sweeps.size();
+}
+
+// sizes and constants of the structs q1t_plan_dump hands out: out[0..] = sizeof(SweepProgram), sizeof(PhaseTab),
+// sizeof(OpDesc), sizeof(RoundDesc), kRegBits, kMaxTileBits, kMaxBits, kMaxRounds, kMaxOps, kMaxRuns
+int q1t_plan_layout(size_t *out, size_t n)
+{
+    const size_t v[10] = { sizeof(q1t::SweepProgram), sizeof(q1t::PhaseTab), sizeof(q1t::OpDesc), sizeof(q1t::RoundDesc),
+                           (size_t)q1t::kRegBits, (size_t)q1t::kMaxTileBits, (size_t)q1t::kMaxBits, (size_t)q1t::kMaxRounds,
+                           (size_t)q1t::kMaxOps, (size_t)q1t::kMaxRuns };
+    for (size_t i = 0; i < n && i < 10; ++i) out[i] = v[i];
+    return Q1T_OK;
+}
+
 int q1t_device_count(void)
 {
     int c = 0;
