@@ -24,7 +24,7 @@ import sys
 import numpy as np
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gate_kats.json")
+OUT = os.path.join(os.environ.get("Q1T_GOLDEN_OUT_DIR") or os.path.dirname(os.path.abspath(__file__)), "gate_kats.json")
 
 CONSTS = {"PI": math.pi, "FRAC_PI_2": math.pi / 2, "FRAC_PI_3": math.pi / 3, "FRAC_PI_4": math.pi / 4, "FRAC_PI_6": math.pi / 6,
           "FRAC_PI_8": math.pi / 8, "FRAC_1_SQRT_2": 0.70710678118654752440, "SQRT_2": math.sqrt(2.0), "LN_2": math.log(2.0),

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from make_gate_kats import ENV0, Gate, match_bracket, statements, translate  # noqa: E402
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "latex_kats.json")
+OUT = os.path.join(os.environ.get("Q1T_GOLDEN_OUT_DIR") or os.path.dirname(os.path.abspath(__file__)), "latex_kats.json")
 
 
 def gate_of(expr, env, strings):

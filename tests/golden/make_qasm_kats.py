@@ -17,7 +17,7 @@ from make_gate_kats import ENV0, Gate, statements  # noqa: E402
 from make_latex_kats import desc, gate_of  # noqa: E402
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "qasm_kats.json")
+OUT = os.path.join(os.environ.get("Q1T_GOLDEN_OUT_DIR") or os.path.dirname(os.path.abspath(__file__)), "qasm_kats.json")
 
 
 def main():
