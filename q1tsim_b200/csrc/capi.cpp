@@ -312,7 +312,9 @@ int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const
     // balance >> 4 selects how the Swap relabelling is undone, as DeviceVectorState::run_sweeps / canonicalize do:
     // 0 not at all (perm_out tells the reader), 1 fused into the last sweep when its tile allows it, else one
     // relabel sweep, 2 the in-place passes
-    const int relabel_mode = balance >> 4;
+    // bit 8: ladder sweeps additionally re-laid out for TMA tile loads (apply_tma_layout), where possible
+    const bool tma_layout = (balance & 0x100) != 0;
+    const int relabel_mode = (balance >> 4) & 0xf;
     bool ident = true;
     for (int l = 0; l < n; ++l) ident = ident && perm[l] == l;
     if (relabel_mode && !ident) {
@@ -327,6 +329,12 @@ int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const
         }
         for (int l = 0; l < n; ++l) perm[l] = l;
     }
+    if (tma_layout)
+        for (q1t::PlannedSweep &ps : sweeps) {
+            bool ladder = ps.prog.nrounds > 0;
+            for (int r = 0; r < ps.prog.nrounds; ++r) ladder = ladder && ps.prog.rounds[r].kind == q1t::ROUND_PH;
+            if (ladder) q1t::apply_tma_layout(ps.prog);
+        }
     if (sweeps.size() > max_sweeps) return Q1T_ERR_NOT_ENOUGH_SPACE;
     size_t np = 0;
     for (size_t i = 0; i < sweeps.size(); ++i) {

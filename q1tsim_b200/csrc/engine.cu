@@ -115,6 +115,8 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
     if (const char *e = std::getenv("Q1T_SPARSE_C2")) sparse_c2_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_FUSE_LEAF")) fuse_leaf_totals_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_INPLACE_RELABEL")) inplace_relabel_ = std::atol(e);
+    if (const char *e = std::getenv("Q1T_TMA")) tma_ = std::atol(e) != 0;
+    if (const char *e = std::getenv("Q1T_PREFETCH_AHEAD")) prefetch_ahead_ = std::atol(e);
     if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
 }
 
@@ -248,6 +250,10 @@ int DeviceVectorState::init_from_qubit_coefs(const double *coefs)
     return Q1T_OK;
 }
 
+static unsigned long long physical_index(uint64_t logical, const std::vector<int> &perm);
+
+// A lazy basis column is kept by its LOGICAL index; the buffer is laid out in the current physical order
+// (a pending zero-byte Swap relabelling makes the two differ), so the 1 goes to the physical position.
 int DeviceVectorState::materialize(Column &c)
 {
     if (!c.basis) return Q1T_OK;
@@ -255,7 +261,7 @@ int DeviceVectorState::materialize(Column &c)
     if (rc) return rc;
     CK(cudaMemsetAsync(c.buf, 0, sizeof(double2) << n_, stream_));
     if (c.basis_idx != UINT64_MAX) {        // UINT64_MAX: a lazy all-zero column (shard that does not hold the basis state)
-        CK(launch_set_basis(c.buf, c.basis_idx, stream_));
+        CK(launch_set_basis(c.buf, physical_index(c.basis_idx, perm_), stream_));
         stats.kernel_launches++;
     }
     c.basis = false;
@@ -455,7 +461,6 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     }
     for (PlannedSweep &ps : sweeps) {
         ps.prog.prefetch_ahead = (int)prefetch_ahead_;
-        ps.prog.dbg_skip = (int)dbg_skip_;
         if (!direct_) {                       // A/B switch: always stage through shared memory, CTA-wide barriers
             ps.prog.direct_load = ps.prog.direct_store = 0;
             for (int r = 0; r < ps.prog.nrounds; ++r) ps.prog.rounds[r].sync_before = 2;
@@ -519,9 +524,21 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
                 }
             }
         }
+        // dense ladder sweeps take their tiles by TMA (planner.cpp apply_tma_layout, kernels.cu ladder_kernel)
+        const bool tma_ok = tma_ && !ps.prog.generate && ps.prog.sup_mode == 0 && sweep_uses_ladder_kernel(ps.prog) && tma_available();
         if (!relabel) {
+            std::vector<const double2 *> hcols;
+            if (tma_ok && which.size() <= (size_t)kMaxTmaCols) {
+                SweepProgram q = ps.prog;
+                for (int c : which) hcols.push_back(cols_[c].buf);
+                if (apply_tma_layout(q) && tma_can_encode(q, hcols.data(), (int)hcols.size())) {
+                    ps.prog = q;
+                    stats.tma_sweeps++;
+                } else hcols.clear();
+            }
             time_begin();
-            CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_));
+            CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_, nullptr,
+                            hcols.empty() ? nullptr : hcols.data()));
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
             stats.sweeps++;
@@ -530,6 +547,16 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             continue;
         }
         // out-of-place: one column at a time through a scratch buffer
+        bool tma_here = false;
+        if (tma_ok && !which.empty()) {
+            SweepProgram q = ps.prog;
+            const double2 *h0 = cols_[which[0]].buf;
+            if (apply_tma_layout(q) && tma_can_encode(q, &h0, 1)) {
+                ps.prog = q;
+                tma_here = true;
+                stats.tma_sweeps++;
+            }
+        }
         for (size_t i = 0; i < which.size(); ++i) {
             Column &col = cols_[which[i]];
             double2 *scratch = nullptr;
@@ -538,8 +565,9 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             double2 *h[2] = { col.buf, scratch };
             CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
             time_begin();
+            const double2 *hsrc = col.buf;
             CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, d_gen_ ? d_gen_ + i : nullptr, stream_,
-                            ps.prog.leaf_fuse ? d_leaf_ + (i << (n_ - kCanonLeafBits)) : nullptr));
+                            ps.prog.leaf_fuse ? d_leaf_ + (i << (n_ - kCanonLeafBits)) : nullptr, tma_here ? &hsrc : nullptr));
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
             double2 *old = col.buf;
@@ -1514,8 +1542,8 @@ int DeviceVectorState::set_option(const char *key, long value)
         track_support_ = value != 0;
         return Q1T_OK;
     }
-    if (!std::strcmp(key, "dbg_skip")) {
-        dbg_skip_ = value;
+    if (!std::strcmp(key, "tma")) {
+        tma_ = value != 0;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "direct")) {

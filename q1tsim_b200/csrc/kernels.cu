@@ -17,10 +17,12 @@
 // 2^n amplitudes per branch column.
 #include "kernels.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace q1t {
 
@@ -52,6 +54,39 @@ __device__ __forceinline__ double2 ld_shared_f64x2(unsigned saddr)
 __device__ __forceinline__ void st_global_cs(double2 *p, double2 v)
 {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ---- TMA tile loads (cp.async.bulk.tensor + mbarrier), ladder kernel on dense sweeps ----
+struct TmaMaps { CUtensorMap m[kMaxTmaCols]; };     // one tensor map per column of the launch, in the kernel parameters
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// all threads: wait until the phase with the given parity has completed.  A tile that never arrives (a
+// malformed tensor map) traps after ~2 s instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap *map, unsigned bar, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %2, %2, %2, %3}], [%4];\n"
+                 ::"r"(dst), "l"(map), "r"(0), "r"(c4), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap *map, int c4)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %1, %1, %1, %2}];\n" ::"l"(map), "r"(0), "r"(c4) : "memory");
 }
 
 // ((v & mask) << shift) with shift of either sign (bit-deposit runs of a thread index)
@@ -236,12 +271,9 @@ struct RoundIO {
 
 __device__ __forceinline__ void round_load(double2 (&a)[kSlots], const RoundIO &io, const RoundDesc &R, const SweepProgram &P)
 {
-    if (io.gsrc && !(P.dbg_skip & 1)) {
+    if (io.gsrc) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) a[s] = __ldcs(io.gsrc + P.dl_slot[s]);
-    } else if (io.gsrc) {
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) a[s] = make_double2(1.0 + s, (double)threadIdx.x);
     } else if (io.zero_fill) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)io.gen_slot ? P.gen_scale : 0.0, 0.0);
@@ -253,12 +285,7 @@ __device__ __forceinline__ void round_load(double2 (&a)[kSlots], const RoundIO &
 
 __device__ __forceinline__ void round_store(const double2 (&a)[kSlots], const RoundIO &io, const RoundDesc &R, const SweepProgram &P)
 {
-    if (io.gdst && (P.dbg_skip & 2)) {
-        double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) acc += a[s].x * io.scale + a[s].y;
-        if (acc == 1.2345e-300) st_global_cs(io.gdst, make_double2(acc, acc));     // keeps the arithmetic alive
-    } else if (io.gdst) {
+    if (io.gdst) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) st_global_cs(io.gdst + P.ds_slot[s], make_double2(a[s].x * io.scale, a[s].y * io.scale));
     } else {
@@ -695,12 +722,13 @@ __device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ 
 #define PCLK(i) do { } while (0)
 #endif
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, bool TMA>
 __global__ void __launch_bounds__(MAXT, MINB)
 ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
-              const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx, double *__restrict__ leaf_out)
+              const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx, double *__restrict__ leaf_out,
+              const __grid_constant__ TmaMaps tmaps)
 {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     const SweepProgram &P = c_prog;
     const int T = P.T, TB = P.TB;
     const unsigned tid = threadIdx.x;
@@ -709,7 +737,8 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     char *const tile_b = reinterpret_cast<char *>(tile);
     const int he_bits = TB > kThrLoBits ? TB - kThrLoBits : 0;
     const int ntab = P.nphase << he_bits;
-    double2 *const s_hiF = tile + (1u << T);             // [2][ntab]: hi[ih] * exp(i*pi*angle(outer bits)), double-buffered
+    // tile, then 16 bytes for the mbarrier of the TMA mode, then the tables
+    double2 *const s_hiF = tile + (1u << T) + 1;         // [2][ntab]: hi[ih] * exp(i*pi*angle(outer bits)), double-buffered
     double2 *const s_tileF = s_hiF + 2 * ntab;           // [nphase]
     double2 *const s_lo = s_tileF + P.nphase;            // [nphase][16]  copies of the PhaseTab rows (the CTA is persistent)
     double *const s_coef = reinterpret_cast<double *>(s_lo + (P.nphase << kThrLoBits));   // [nphase][n_outer + 1], last = base
@@ -717,7 +746,14 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     // per-thread source / destination offsets: kept in shared memory, not in registers -- with 32
     // amplitudes per thread the compiler spilled them, and a local-memory reload is an L2 round trip
     unsigned long long *const s_off = reinterpret_cast<unsigned long long *>(s_coef + ((P.nphase * ncoef + 1) & ~1));
-    const bool generate = P.generate != 0;
+    // TMA mode (dense sweeps): the tile arrives by one cp.async.bulk.tensor request issued by thread 0 and
+    // lives in shared memory in TMA order (SweepProgram::tma_*); completion is signalled on an mbarrier
+    // (a separate instantiation: dense sweeps only, so input generation, support tracking and broadcast
+    // sweeps are compiled out of it)
+    constexpr bool tma = TMA;
+#define Q1T_TILE_S0 static_cast<unsigned>(__cvta_generic_to_shared(tile))
+#define Q1T_S_BAR (Q1T_TILE_S0 + (16u << T))
+    const bool generate = !TMA && P.generate != 0;
     const bool staged_store = P.direct_store == 0;
     const double scale = P.scale;
     // fused canonical leaf totals (one leaf of 1024 amplitudes per warp in the staged store pass)
@@ -740,12 +776,19 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             const unsigned v = tid & P.st_lruns[k].mask;
             l_lo |= sh >= 0 ? v << sh : v >> -sh;
         }
-        sw_lo = tile_swizzle(l_lo) * 16u;
+        sw_lo = (tma ? tma_swizzle(l_lo) : tile_swizzle(l_lo)) * 16u;
     } else {
         for (int k = 0; k < P.ds_nruns; ++k) doff_t |= run_bits(tid, P.ds_runs[k]);
     }
+    if (tma) {
+        if (tid == 0) {
+            if (Q1T_TILE_S0 & 1023u) __trap();     // SWIZZLE_128B needs the 1024-byte alignment
+            mbar_init(Q1T_S_BAR, 1);
+        }
+        __syncthreads();
+    }
     // support tracking: amplitudes that differ from the basis index in a bit of sup_mask are zero
-    const int sup_mode = P.sup_mode;
+    const int sup_mode = TMA ? 0 : P.sup_mode;
     const unsigned long long sup_g = (generate || sup_mode) ? gen_idx[col] : 0ull;
     const unsigned long long gen_g = sup_g;
     const unsigned long long sup_mo = sup_mode ? (P.sup_mask & ~P.tile_mask_src) : 0ull;   // pinned outer bits
@@ -820,6 +863,24 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     };
 
     auto issue_loads = [&](unsigned long long o) {
+        if (tma) {
+            if (tid == 0) {
+                // the buffer was read and written through the generic proxy up to the barrier just passed
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_expect_tx(Q1T_S_BAR, 16u << T);
+                const int line = (int)(outer_base(P.o_src, o, P.n_outer) >> 3);
+                for (int q = 0; q < P.tma_nreq; ++q)
+                    tma_load_5d(Q1T_TILE_S0 + q * P.tma_req_bytes, &tmaps.m[col], Q1T_S_BAR, line + (int)P.tma_req_line[q]);
+                if (P.prefetch_ahead > 0) {
+                    const unsigned long long oa = o + (unsigned long long)P.prefetch_ahead * gridDim.x;
+                    if (oa < ntiles) {
+                        const int la = (int)(outer_base(P.o_src, oa, P.n_outer) >> 3);
+                        for (int q = 0; q < P.tma_nreq; ++q) tma_prefetch_5d(&tmaps.m[col], la + (int)P.tma_req_line[q]);
+                    }
+                }
+            }
+            return;
+        }
         const double2 *__restrict__ p = src + (outer_base(P.o_src, o, P.n_outer) | s_off[2 * tid]);
         unsigned sw = sw_tid;
         asm volatile("" : "+r"(sw));      // keeps the 32 destination addresses from being hoisted out of the tile loop (and spilled)
@@ -918,7 +979,8 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         o_next = advance(o);
         const bool has_next = o_next < ntiles;
         PCLK(0);
-        if (!generate) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (tma) mbar_wait(Q1T_S_BAR, (unsigned)buf);          // tile k of this CTA completes phase k: parity = k & 1 = buf
+        else if (!generate) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         PCLK(1);
         __syncthreads();                       // tile o and its tables are visible to the whole CTA
         PCLK(2);
@@ -928,7 +990,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             const bool last = r + 1 == P.nrounds;
             unsigned thrL = 0;
             for (int k = 0; k < R.nruns; ++k) thrL |= (unsigned)run_bits(tid, R.runs[k]);
-            const unsigned swT = tile_swizzle(thrL) * 16u;
+            const unsigned swT = (tma ? tma_swizzle(thrL) : tile_swizzle(thrL)) * 16u;
             PCLK(3);
             if (r > 0) {
                 if (R.sync_before == 2) __syncthreads();
@@ -1076,16 +1138,75 @@ constexpr int kMaxThreads = 1 << kMaxThrBits;
 bool sweep_uses_ladder_kernel(const SweepProgram &prog)
 {
     static const bool pipe = !(std::getenv("Q1T_LADDER_PIPE") && std::atoi(std::getenv("Q1T_LADDER_PIPE")) == 0);
-    if (!pipe || prog.nrounds <= 0 || (1 << prog.TB) > kSmallThreads || prog.dbg_skip) return false;
+    if (!pipe || prog.nrounds <= 0 || (1 << prog.TB) > kSmallThreads) return false;
     for (int r = 0; r < prog.nrounds; ++r)
         if (prog.rounds[r].kind != ROUND_PH) return false;
     return true;
 }
 
+// tensor maps of the source columns for a program in TMA layout (SweepProgram::tma_*); the driver entry point
+// is looked up through the runtime, so the library does not link against libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else cudaGetLastError();
+    }
+    return fn;
+}
+bool tma_make_maps(const SweepProgram &prog, const double2 *const *h_src_cols, int ncols, TmaMaps &out)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || prog.tma_nreq <= 0 || ncols > kMaxTmaCols || !h_src_cols) return false;
+    std::memset(&out, 0, sizeof out);
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t box[5], estr[5] = { 1, 1, 1, 1, 1 };
+    for (int i = 0; i < 5; ++i) { gdim[i] = prog.tma_gdim[i]; box[i] = prog.tma_box[i]; }
+    for (int i = 0; i < 4; ++i) gstride[i] = prog.tma_gstride[i];
+    for (int c = 0; c < ncols; ++c) {
+        const CUresult r = fn(&out.m[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double2 *>(h_src_cols[c]), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+bool tma_available() { return encode_tiled_fn() != nullptr; }
+bool tma_can_encode(const SweepProgram &prog, const double2 *const *h_src_cols, int ncols)
+{
+    TmaMaps tmp;
+    const bool ok = tma_make_maps(prog, h_src_cols, ncols, tmp);
+    if (!ok) {
+        static bool warned = false;
+        if (!warned) {
+            warned = true;
+            std::fprintf(stderr, "q1tsim_b200: cuTensorMapEncodeTiled rejected a tile description (box %u %u %u %u, strides %llu %llu %llu); "
+                                 "this sweep shape keeps cp.async loads\n", prog.tma_box[1], prog.tma_box[2], prog.tma_box[3], prog.tma_box[4],
+                         (unsigned long long)prog.tma_gstride[0], (unsigned long long)prog.tma_gstride[1], (unsigned long long)prog.tma_gstride[2]);
+        }
+    }
+    return ok;
+}
+
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
-                         double *d_leaf_out)
+                         double *d_leaf_out, const double2 *const *h_src_cols)
 {
+    TmaMaps tmaps;
+    if (prog.tma_nreq > 0) {
+        // a program in TMA layout can only run in the ladder kernel with tensor maps of its source columns
+        if (!sweep_uses_ladder_kernel(prog) || prog.generate || prog.sup_mode || !tma_make_maps(prog, h_src_cols, ncols, tmaps))
+            return cudaErrorInvalidValue;
+    } else std::memset(&tmaps, 0, sizeof tmaps);
     cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     const int he_bits = prog.TB > kThrLoBits ? prog.TB - kThrLoBits : 0;
@@ -1110,23 +1231,30 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
     if (sweep_uses_ladder_kernel(prog)) {
-        static int ctas_per_sm = 0;
-        if (!ctas_per_sm) {
-            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (3 * kHiEntries + 1 + (1 << kThrLoBits)) + sizeof(double) * kMaxPhase * (kMaxBits + 1) + 16 * kSmallThreads + 16));
+        static bool attr_set = false;
+        if (!attr_set) {
+            const int max_lsmem = (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (3 * kHiEntries + 1 + (1 << kThrLoBits)) + sizeof(double) * kMaxPhase * (kMaxBits + 1) + 16 * kSmallThreads + 32);
+            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_lsmem);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
-            ctas_per_sm = Q1T_LADDER_MIN_CTAS;
+            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_lsmem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
         }
+        const bool use_tma = prog.tma_nreq > 0;
         const size_t lsmem = (sizeof(double2) << prog.T) +
                              sizeof(double2) * (((size_t)prog.nphase << he_bits) * 2 + prog.nphase + ((size_t)prog.nphase << kThrLoBits)) +
-                             sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x;
+                             sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x + 16;
         int dev = 0, nsm = 148, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS>, (int)block.x, lsmem);
+        e = use_tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true>, (int)block.x, lsmem)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, (int)block.x, lsmem);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         // persistent grid: every column gets the same share of the resident CTAs
@@ -1134,7 +1262,10 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         if (per_col < 1) per_col = 1;
         if (per_col > (1ull << prog.n_outer)) per_col = 1ull << prog.n_outer;
         dim3 pgrid((unsigned)per_col, (unsigned)ncols, 1);
-        ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out);
+        if (use_tma)
+            ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
+        else
+            ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
         return cudaGetLastError();
     }
     if (ladders_only && (int)block.x <= kSmallThreads)

@@ -21,7 +21,12 @@ struct GenericGateArgs {
 // of the written column(s), 2^(n-10) doubles per column (what launch_leaf_totals would compute afterwards)
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
-                         double *d_leaf_out = nullptr);
+                         double *d_leaf_out = nullptr, const double2 *const *h_src_cols = nullptr);
+// h_src_cols: host copy of the source column pointers, needed (only) by programs in TMA layout (prog.tma_nreq > 0)
+// to encode the tensor maps; true if the driver offers cuTensorMapEncodeTiled
+bool tma_available();
+// can the tile description of a program in TMA layout be encoded for these source columns?
+bool tma_can_encode(const SweepProgram &prog, const double2 *const *h_src_cols, int ncols);
 // true if launch_sweep() runs this program in the persistent ladder kernel (the one that honours
 // SweepProgram::sup_mask / sup_mode)
 bool sweep_uses_ladder_kernel(const SweepProgram &prog);

@@ -9,6 +9,7 @@
 #include "planner.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 
@@ -791,6 +792,175 @@ bool can_fuse_relabel(const SweepProgram &P, const std::vector<int> &dstpos)
     for (int i = 0; i < P.T; ++i)
         if (dstpos[P.tsrc[i]] < P.coalesce) ++found;
     return found >= (P.n < P.coalesce ? P.n : P.coalesce);
+}
+
+// ---------------------------------------------------------------------------
+// TMA tile layout (ladder kernel, dense sweeps).
+//
+// A cp.async.bulk.tensor load delivers the 512 lines (128 B each) of a tile in the order of the tensor
+// map's box dimensions and, with CU_TENSOR_MAP_SWIZZLE_128B, xors the 16-byte chunk index of every
+// line with the three lowest line-index bits.  That is a narrower swizzle than tile_swizzle() (which
+// folds ALL line bits into the chunk bits): a quarter warp's LDS/STS.128 is conflict-free only if its
+// three lane bits land on smem bits {0..5} with three different residues mod 3.  The line order is ours
+// to choose (any order of the box dimensions), so: pick the three tile bits that become smem bits 3, 4, 5
+// such that the lane bits every round (and the staged store pass) already uses qualify -- the thread
+// maps of the rounds, hence the phase tables, stay as they are; only the shared-memory offset tables are
+// rewritten.  Returns false (program untouched) when no such choice exists or the line order needs more
+// box dimensions / requests than the kernel supports.
+// ---------------------------------------------------------------------------
+bool apply_tma_layout(SweepProgram &P)
+{
+    const int T = P.T, TB = P.TB;
+    if (T != 12 || TB != 7 || kRegBits != 5 || P.coalesce != 3 || P.n < T + 1) return false;
+    for (int i = 0; i < 3; ++i)
+        if (P.tsrc[i] != i) return false;
+    // lane triples that must be conflict-free
+    std::vector<std::array<int, 3>> triples;
+    for (int r = 0; r < P.nrounds; ++r) triples.push_back({ P.rounds[r].thr_tb[0], P.rounds[r].thr_tb[1], P.rounds[r].thr_tb[2] });
+    // store pass: tid bit m -> tile bit st_thr[m], slot bit b -> tile bit st_reg[b] (recovered from the tables)
+    int st_thr[kMaxThrBits], st_reg[kRegBits], st_dpos[kMaxThrBits];
+    auto one_bit = [](uint64_t v) { int b = 0; while (b < 63 && !((v >> b) & 1ull)) ++b; return b; };
+    for (int m = 0; m < TB; ++m) {
+        uint64_t l = 0, d = 0;
+        for (int k = 0; k < P.st_nruns; ++k) {
+            const uint32_t v = (1u << m) & P.st_lruns[k].mask;
+            const int sh = P.st_lruns[k].shift;
+            l |= sh >= 0 ? (uint64_t)v << sh : (uint64_t)v >> -sh;
+            d |= (uint64_t)((1u << m) & P.st_runs[k].mask) << P.st_runs[k].shift;
+        }
+        if (__builtin_popcountll(l) != 1 || __builtin_popcountll(d) != 1) return false;
+        st_thr[m] = one_bit(l);
+        st_dpos[m] = one_bit(d);
+    }
+    for (int b = 0; b < kRegBits; ++b) {
+        const uint32_t l = tile_swizzle(P.st_l_hi[1 << b] >> 4);     // the swizzle is an involution
+        if (__builtin_popcount(l) != 1) return false;
+        st_reg[b] = one_bit(l);
+    }
+    const bool staged_store = P.direct_store == 0 || P.nrounds == 0;
+    if (staged_store) triples.push_back({ st_thr[0], st_thr[1], st_thr[2] });
+    int best[3] = { -1, -1, -1 }, best_cost = 1 << 30;
+    int best_pi[kMaxTileBits + 3];
+    struct Dims { int nruns; int run_len[16]; int run_pos[16]; };
+    Dims best_dims;
+    std::memset(&best_dims, 0, sizeof best_dims);
+    for (int s3 = 3; s3 < T; ++s3)
+        for (int s4 = 3; s4 < T; ++s4)
+            for (int s5 = 3; s5 < T; ++s5) {
+                if (s3 == s4 || s3 == s5 || s4 == s5) continue;
+                int pi[kMaxTileBits + 3];
+                for (int i = 0; i < T; ++i) pi[i] = -1;
+                pi[0] = 0; pi[1] = 1; pi[2] = 2; pi[s3] = 3; pi[s4] = 4; pi[s5] = 5;
+                int next = 6;
+                for (int i = 3; i < T; ++i)
+                    if (pi[i] < 0) pi[i] = next++;
+                bool ok = true;
+                for (const auto &t : triples) {
+                    bool res[3] = { false, false, false };
+                    for (int k = 0; k < 3; ++k) {
+                        const int m = pi[t[k]];
+                        if (m > 5 || res[m % 3]) { ok = false; break; }
+                        res[m % 3] = true;
+                    }
+                    if (!ok) break;
+                }
+                if (!ok) continue;
+                // line order -> runs of consecutive source bits (at most 8 bits = 256 lines per box dimension)
+                int tb_of_m[kMaxTileBits + 3];
+                for (int i = 0; i < T; ++i) tb_of_m[pi[i]] = i;
+                Dims d;
+                d.nruns = 0;
+                for (int m = 3; m < T;) {
+                    int len = 1;
+                    while (m + len < T && len < 8 && P.tsrc[tb_of_m[m + len]] == P.tsrc[tb_of_m[m]] + len) ++len;
+                    d.run_len[d.nruns] = len;
+                    d.run_pos[d.nruns] = P.tsrc[tb_of_m[m]];
+                    ++d.nruns;
+                    m += len;
+                }
+                int extra_bits = 0;
+                for (int k = 3; k < d.nruns; ++k) extra_bits += d.run_len[k];
+                if ((1 << extra_bits) > kMaxTmaReq) continue;
+                const int cost = (extra_bits << 8) + d.nruns;
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best[0] = s3; best[1] = s4; best[2] = s5;
+                    std::memcpy(best_pi, pi, sizeof pi);
+                    best_dims = d;
+                }
+            }
+    if (best[0] < 0) return false;
+    const int *pi = best_pi;
+    const Dims &d = best_dims;
+    // tensor description
+    int extra_bits = 0;
+    for (int k = 3; k < d.nruns; ++k) extra_bits += d.run_len[k];
+    P.tma_nreq = 1 << extra_bits;
+    P.tma_req_bytes = (uint32_t)((sizeof(double) * 2) << (T - extra_bits));
+    P.tma_box[0] = 16; P.tma_gdim[0] = 16;
+    for (int k = 0; k < 3; ++k) {
+        if (k < d.nruns) {
+            P.tma_box[1 + k] = 1u << d.run_len[k];
+            P.tma_gdim[1 + k] = 1ull << d.run_len[k];
+            P.tma_gstride[k] = 16ull << d.run_pos[k];
+        } else {
+            P.tma_box[1 + k] = 1;
+            P.tma_gdim[1 + k] = 1;
+            P.tma_gstride[k] = 128;
+        }
+    }
+    P.tma_box[4] = 1;
+    P.tma_gdim[4] = 1ull << (P.n - 3);
+    P.tma_gstride[3] = 128;
+    {
+        // the bits iterated by separate requests are the top smem bits, in run order
+        int xpos[16], nx = 0;
+        for (int k = 3; k < d.nruns; ++k)
+            for (int j = 0; j < d.run_len[k]; ++j) xpos[nx++] = d.run_pos[k] + j;
+        for (int q = 0; q < P.tma_nreq; ++q) {
+            uint64_t line = 0;
+            for (int j = 0; j < nx; ++j)
+                if ((q >> j) & 1) line |= 1ull << (xpos[j] - 3);
+            P.tma_req_line[q] = line;
+        }
+    }
+    for (int i = 0; i < T; ++i) P.tma_pi[i] = (uint8_t)pi[i];
+    // shared-memory offset tables in the new order
+    for (int r = 0; r < P.nrounds; ++r) {
+        RoundDesc &R = P.rounds[r];
+        int pos[kMaxThrBits + 1];
+        for (int i = 0; i < TB; ++i) pos[i] = pi[R.thr_tb[i]];
+        R.nruns = (uint8_t)make_runs(pos, TB, R.runs);
+        for (int s = 0; s < kSlots; ++s) {
+            uint32_t m = 0;
+            for (int j = 0; j < kRegBits; ++j)
+                if ((s >> j) & 1) m |= 1u << pi[R.reg_tb[j]];
+            R.sw_slot[s] = tma_swizzle(m) * 16u;
+        }
+    }
+    {
+        int n2 = 0, i = 0;
+        BitRun a[kMaxRuns * 2], b[kMaxRuns * 2];
+        while (i < TB) {
+            int j = i;
+            uint32_t mask = 0;
+            while (j < TB && st_dpos[j] - j == st_dpos[i] - i && pi[st_thr[j]] - j == pi[st_thr[i]] - i) { mask |= 1u << j; ++j; }
+            a[n2].mask = mask; a[n2].shift = st_dpos[i] - i;
+            b[n2].mask = mask; b[n2].shift = pi[st_thr[i]] - i;
+            ++n2;
+            i = j;
+        }
+        if (n2 > kMaxRuns) { P.tma_nreq = 0; return false; }
+        P.st_nruns = n2;
+        for (int k = 0; k < n2; ++k) { P.st_runs[k] = a[k]; P.st_lruns[k] = b[k]; }
+        for (int s = 0; s < kSlots; ++s) {
+            uint32_t m = 0;
+            for (int bb = 0; bb < kRegBits; ++bb)
+                if ((s >> bb) & 1) m |= 1u << pi[st_reg[bb]];
+            P.st_l_hi[s] = tma_swizzle(m) * 16u;
+        }
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------

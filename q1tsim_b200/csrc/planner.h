@@ -128,6 +128,10 @@ std::vector<InplacePass> plan_inplace_relabel(int n, int tile_bits, int coalesce
 void set_relabel(SweepProgram &P, const std::vector<int> &dstpos, bool leaf_split = false);
 bool can_fuse_relabel(const SweepProgram &P, const std::vector<int> &dstpos);
 
+// re-express the shared-memory side of a dense ladder program in the order a TMA tensor load delivers the
+// tile (planner.cpp); false = not possible, program untouched
+bool apply_tma_layout(SweepProgram &P);
+
 // reduce an angle in half-turns to [-1, 1)
 double wrap_half_turns(double a);
 

@@ -28,6 +28,8 @@ constexpr int kHiEntries = 1 << (kMaxThrBits - kThrLoBits);
 constexpr int kMaxRuns = 9;         // bit-deposit runs (mask, shift) of a thread index
 constexpr int kOuterChunkBits = 6;  // outer tile index -> address via 6-bit lookup tables
 constexpr int kOuterChunks = 5;
+constexpr int kMaxTmaReq = 16;      // TMA requests per tile (one when the tile's line bits form <= 3 runs)
+constexpr int kMaxTmaCols = 4;      // columns per launch that can be described by tensor maps in the kernel parameters
 
 enum OpKind : uint8_t {
     OP_G1_GENERIC = 0,   // dense complex 2x2 on slot bit j
@@ -88,12 +90,12 @@ struct SweepProgram {
     int32_t relabel;      // 1 if dst positions differ from src positions (out-of-place only)
     int32_t generate;     // 1: the source column is a basis state |gen_idx[col]>, nothing is read
     int32_t ld_nruns, st_nruns;
-    int32_t prefetch_ahead;   // >0: prefetch the tile this many outer indices ahead into L2 (old experiment, unused)
+    int32_t prefetch_ahead;   // TMA mode, >0: the tile this many grid strides ahead is prefetched into L2 when a tile load is issued
     int32_t direct_load;      // round 0 reads its amplitudes straight from global memory (no staging pass)
     int32_t direct_store;     // the last round writes its amplitudes straight to global memory
     int32_t dl_nruns, ds_nruns;
     uint64_t tile_mask_src;   // source positions of the tile bits
-    int32_t dbg_skip;         // timing experiments only: bit0 = skip loads, bit1 = skip stores (results are wrong)
+    int32_t reserved0;
     int32_t coalesce;         // low index bits kept contiguous in every tile (3 = 128 B, 2 = 64 B)
     double scale;         // applied to every amplitude at the store (deferred Hadamard normalisation)
     // Support tracking (ladder kernel): every amplitude whose index differs from the column's basis
@@ -134,6 +136,22 @@ struct SweepProgram {
     uint64_t ds_slot[kSlots];
     RoundDesc rounds[kMaxRounds];
     OpDesc ops[kMaxOps];
+    // TMA tile loads (ladder kernel, dense sweeps; planner.cpp apply_tma_layout).  tma_nreq > 0: the tile is
+    // kept in shared memory in the order a cp.async.bulk.tensor load delivers it -- smem index m = the tile-local
+    // index with its bits permuted (tile bit i -> smem bit tma_pi[i]), 16-byte chunk bits 0..2 xor-ed with the
+    // line bits 3..5 (CU_TENSOR_MAP_SWIZZLE_128B) -- and every shared-memory offset table of the program
+    // (rounds[].runs, rounds[].sw_slot, st_lruns, st_l_hi) is expressed in that order.  The column is described
+    // to the TMA unit as a 5-d tensor of doubles: d0 = the 16 doubles of a 128-byte line, d1..d3 = runs of
+    // consecutive index bits taken in smem order (box tma_box[i], byte stride tma_gstride[i-1]), d4 = the line
+    // index (stride 128 B), which carries the tile base; request q of a tile adds tma_req_line[q] lines.
+    int32_t tma_nreq;
+    uint32_t tma_req_bytes;
+    uint32_t tma_box[5];
+    uint32_t tma_pad;
+    uint64_t tma_gstride[4];
+    uint64_t tma_gdim[5];
+    uint64_t tma_req_line[kMaxTmaReq];
+    uint8_t tma_pi[kMaxTileBits + 3];
 };
 
 // per PHASE op, in global memory
@@ -153,6 +171,10 @@ static_assert(sizeof(PhaseTab) % 16 == 0, "PhaseTab must keep 16-byte alignment 
 #endif
 Q1T_HD inline constexpr uint32_t tile_swizzle(uint32_t l) {
     return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9) ^ (l >> 12)) & 7u);
+}
+// shared-memory order of a TMA-loaded tile (CU_TENSOR_MAP_SWIZZLE_128B on 1024-byte aligned memory)
+Q1T_HD inline constexpr uint32_t tma_swizzle(uint32_t m) {
+    return m ^ ((m >> 3) & 7u);
 }
 
 }  // namespace q1t

@@ -121,3 +121,36 @@ def load_ops(circuit, ops):
         else:
             raise ValueError(k)
     return circuit
+
+
+def product_state_coefs(n, seed=1):
+    """Seeded per-qubit coefficient pairs (a_q, b_q) for `VectorState::from_qubit_coefs` (vectorstate.rs:62-83): a dense
+    product state with no zero amplitude (cfg3 input B)."""
+    r = SplitMix64(seed)
+    coefs = []
+    for _ in range(n):
+        th, ph = math.pi * (0.15 + 0.7 * r.f64()), 2 * math.pi * r.f64()
+        coefs += [complex(math.cos(th / 2), 0.0), complex(math.cos(ph) * math.sin(th / 2), math.sin(ph) * math.sin(th / 2))]
+    return coefs
+
+
+def qft_of_product_state(n, coefs, idx):
+    """Closed form of qft_ops(n, swaps=True) applied to the product state of `coefs` (normalised per qubit, qubit 0 =
+    most significant index bit), evaluated at the basis indices `idx` (numpy int64 array).
+
+    The circuit maps |x> to 2^(-n/2) sum_y exp(2 pi i rev(x) rev(y) / 2^n) |y> (rev = n-bit reversal); with
+    psi_x = prod_q c_q[x_q] and rev(x) = sum_q x_q 2^q the sum over x factorises:
+        out[y] = 2^(-n/2) prod_q (c_q[0] + c_q[1] exp(2 pi i (2^q rev(y) mod 2^n) / 2^n)).
+    A size-independent check of the dense path: O(n) per amplitude at any n."""
+    import numpy as np
+    idx = np.asarray(idx, dtype=np.int64)
+    rev = np.zeros_like(idx)
+    for b in range(n):
+        rev |= ((idx >> b) & 1) << (n - 1 - b)
+    out = np.full(idx.shape, 2.0 ** (-n / 2), dtype=np.complex128)
+    for q in range(n):
+        a, b = complex(coefs[2 * q]), complex(coefs[2 * q + 1])
+        nrm = math.sqrt(abs(a) ** 2 + abs(b) ** 2)
+        frac = ((rev & ((1 << (n - q)) - 1)) << q).astype(np.float64) / float(1 << n)      # (2^q rev mod 2^n) / 2^n, exact
+        out *= (a + b * np.exp(2j * np.pi * frac)) / nrm
+    return out

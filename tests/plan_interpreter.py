@@ -18,6 +18,7 @@ K_REG, K_MAX_TILE, K_MAX_BITS, K_MAX_ROUNDS, K_MAX_OPS, K_MAX_RUNS = 5, 13, 40, 
 K_SLOTS, K_MAX_THR, K_THR_LO, K_CHUNKS, K_CHUNK_BITS = 1 << K_REG, K_MAX_TILE - K_REG, 4, 5, 6
 OP_G1_GENERIC, OP_G1_HADAMARD, OP_G1_ANTIDIAG, OP_G1_SWAPX, OP_PHASE, OP_G1_DIAG, OP_H_UNNORM, OP_PHASE_H, OP_LINPHASE = range(9)
 ROUND_PH = 1
+K_MAX_TMA_REQ = 16
 FLAG_C0 = 0x80
 
 
@@ -45,7 +46,7 @@ class SweepProgram(C.Structure):
                 ("nops", C.c_int32), ("nphase", C.c_int32), ("relabel", C.c_int32), ("generate", C.c_int32),
                 ("ld_nruns", C.c_int32), ("st_nruns", C.c_int32), ("prefetch_ahead", C.c_int32), ("direct_load", C.c_int32),
                 ("direct_store", C.c_int32), ("dl_nruns", C.c_int32), ("ds_nruns", C.c_int32), ("tile_mask_src", C.c_uint64),
-                ("dbg_skip", C.c_int32), ("coalesce", C.c_int32), ("scale", C.c_double), ("sup_mask", C.c_uint64),
+                ("reserved0", C.c_int32), ("coalesce", C.c_int32), ("scale", C.c_double), ("sup_mask", C.c_uint64),
                 ("sup_mode", C.c_int32), ("leaf_fuse", C.c_int32), ("gen_scale", C.c_double),
                 ("tsrc", C.c_uint8 * (K_MAX_TILE + 3)), ("tdst", C.c_uint8 * (K_MAX_TILE + 3)),
                 ("osrc", C.c_uint8 * K_MAX_BITS), ("odst", C.c_uint8 * K_MAX_BITS),
@@ -55,7 +56,10 @@ class SweepProgram(C.Structure):
                 ("st_off_hi", C.c_uint64 * K_SLOTS), ("st_l_hi", C.c_uint32 * K_SLOTS),
                 ("dl_runs", BitRun * K_MAX_RUNS), ("dl_slot", C.c_uint64 * K_SLOTS),
                 ("ds_runs", BitRun * K_MAX_RUNS), ("ds_slot", C.c_uint64 * K_SLOTS),
-                ("rounds", RoundDesc * K_MAX_ROUNDS), ("ops", OpDesc * K_MAX_OPS)]
+                ("rounds", RoundDesc * K_MAX_ROUNDS), ("ops", OpDesc * K_MAX_OPS),
+                ("tma_nreq", C.c_int32), ("tma_req_bytes", C.c_uint32), ("tma_box", C.c_uint32 * 5), ("tma_pad", C.c_uint32),
+                ("tma_gstride", C.c_uint64 * 4), ("tma_gdim", C.c_uint64 * 5), ("tma_req_line", C.c_uint64 * K_MAX_TMA_REQ),
+                ("tma_pi", C.c_uint8 * (K_MAX_TILE + 3))]
 
 
 class PhaseTab(C.Structure):
@@ -277,3 +281,62 @@ def check_tables(P):
         for s in range(K_SLOTS):
             ls = sum(((s >> j) & 1) << reg_tb[j] for j in range(K_REG))
             assert R.sw_slot[s] == tile_swizzle(ls) * 16
+
+
+def tma_swizzle(m):
+    return m ^ ((m >> 3) & 7)
+
+
+def check_tma_tables(P):
+    """a program in TMA layout (planner.cpp apply_tma_layout): the tensor description delivers every tile element to
+    the shared-memory position the rewritten offset tables expect, and every LDS/STS.128 of a quarter warp is
+    conflict-free under the 128-byte TMA swizzle"""
+    assert P.tma_nreq > 0
+    n, T, TB = P.n, P.T, P.TB
+    tsrc, tdst = [P.tsrc[i] for i in range(T)], [P.tdst[i] for i in range(T)]
+    pi = [P.tma_pi[i] for i in range(T)]
+    assert sorted(pi) == list(range(T)) and pi[:3] == [0, 1, 2]
+    l = np.arange(1 << T, dtype=np.int64)
+    m_of_l = _deposit(l, pi)
+    l_of_m = np.empty_like(l)
+    l_of_m[m_of_l] = l
+    lsrc = _deposit(l, tsrc)
+    # what the TMA unit does with the 5-d box: element (i3, i2, i1, chunk) of request q
+    box = [P.tma_box[i] for i in range(5)]
+    gs = [P.tma_gstride[i] for i in range(4)]
+    assert box[0] == 16 and box[4] == 1 and gs[3] == 128 and P.tma_gdim[4] == 1 << (n - 3)
+    assert all(1 <= b <= 256 for b in box) and all(g % 16 == 0 and 0 < g < (1 << 40) for g in gs)
+    assert P.tma_nreq * P.tma_req_bytes == 16 << T and P.tma_req_bytes == 128 * box[1] * box[2] * box[3]
+    src_at_m = np.empty(1 << T, dtype=np.int64)
+    for q in range(P.tma_nreq):
+        i1, i2, i3, c = np.meshgrid(np.arange(box[1]), np.arange(box[2]), np.arange(box[3]), np.arange(8), indexing="ij")
+        off = (i1 * gs[0] + i2 * gs[1] + i3 * gs[2]) // 16 + P.tma_req_line[q] * 8 + c
+        mlin = q * (P.tma_req_bytes // 16) + ((i3 * box[2] + i2) * box[1] + i1) * 8 + c
+        src_at_m[mlin.ravel()] = off.ravel()
+    assert np.array_equal(src_at_m[m_of_l], lsrc)           # the element at smem index m(l) is tile element l
+    tid = np.arange(1 << TB, dtype=np.uint64)
+
+    def conflict_free(addr16):                               # addr16: (threads,) 16-byte unit addresses of one LDS/STS.128
+        banks = (addr16 & 7).reshape(-1, 8)                  # a quarter warp = one 128-byte wavefront
+        return all(len(set(row.tolist())) == 8 for row in banks)
+
+    for r in range(P.nrounds):
+        R = P.rounds[r]
+        reg_tb, thr_tb = [R.reg_tb[j] for j in range(K_REG)], [R.thr_tb[i] for i in range(TB)]
+        thrM = _run_bits(tid, R.runs, R.nruns).astype(np.int64)
+        assert np.array_equal(thrM, _deposit(tid.astype(np.int64), [pi[tb] for tb in thr_tb]))
+        for s in range(K_SLOTS):
+            ms = sum(((s >> j) & 1) << pi[reg_tb[j]] for j in range(K_REG))
+            assert R.sw_slot[s] == tma_swizzle(ms) * 16
+            assert conflict_free((tma_swizzle(thrM) * 16 ^ R.sw_slot[s]) >> 4)
+    ldst = _deposit(l, tdst)
+    doff = _run_bits(tid, P.st_runs, P.st_nruns).astype(np.int64)
+    mlo = _run_bits(tid, P.st_lruns, P.st_nruns).astype(np.int64)
+    seen = np.zeros(1 << T, dtype=bool)
+    for i in range(K_SLOTS):
+        midx = mlo | np.int64(tma_swizzle(P.st_l_hi[i] >> 4))
+        assert np.array_equal(doff | np.int64(P.st_off_hi[i]), ldst[l_of_m[midx]])
+        seen[midx] = True
+        if not P.direct_store:
+            assert conflict_free((tma_swizzle(mlo) * 16 ^ P.st_l_hi[i]) >> 4)
+    assert seen.all()

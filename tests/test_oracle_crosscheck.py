@@ -173,3 +173,16 @@ def test_error_codes():
     with pytest.raises(O.OracleError) as e:
         s.apply_gate(O.gate_matrix("cx"), [0])
     assert e.value.kind == "InvalidNrBits"
+
+
+@pytest.mark.parametrize("n", [3, 8, 13])
+def test_closed_form_of_qft_on_a_product_state(n):
+    """workloads.qft_of_product_state (the size-independent check the GPU tests and bench.py use at n = 30 on a dense
+    input) pinned against the oracle applying the QFT gate by gate"""
+    from q1tsim_b200 import workloads as W
+    coefs = W.product_state_coefs(n, seed=n)
+    o = O.OracleState.from_qubit_coefs(coefs, 1)
+    for op in W.qft_ops(n, measure=False):
+        o.apply_gate(O.gate_matrix(op[1], op[2]), op[3])
+    want = W.qft_of_product_state(n, coefs, np.arange(1 << n))
+    assert np.linalg.norm(o.column(0) - want) < 1e-13

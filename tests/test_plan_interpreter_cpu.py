@@ -91,3 +91,19 @@ def test_swap_relabelling_undone(n, tile_bits, relabel_mode):
                 T, no = P.T, P.n_outer
                 assert sorted(P.tsrc[i] for i in range(T)) == sorted(P.tdst[i] for i in range(T))
                 assert [P.osrc[i] for i in range(no)] == [P.odst[i] for i in range(no)]
+
+
+@pytest.mark.parametrize("n,relabel_mode", [(13, 0), (16, 0), (16, 1), (22, 1), (30, 1), (33, 1)])
+def test_tma_layout_of_dense_ladder_sweeps(n, relabel_mode):
+    """dense ladder sweeps load their tiles by TMA: the tensor description (box, strides, requests) and the
+    shared-memory tables rewritten by apply_tma_layout are consistent, and the rounds' LDS/STS stay conflict-free"""
+    gates = [(O.gate_matrix(o[1], o[2]), o[3]) for o in W.qft_ops(n, measure=False)]
+    sweeps, perm = PI.plan(n, gates, 12, 3, (relabel_mode << 4) | 0x100)
+    got = 0
+    for P, _ in sweeps:
+        if P.tma_nreq > 0:
+            PI.check_tma_tables(P)
+            got += 1
+        else:
+            PI.check_tables(P)
+    assert got == len([1 for P, _ in sweeps if P.nrounds > 0]), "every QFT ladder sweep must qualify for TMA loads"
