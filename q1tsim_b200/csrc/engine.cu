@@ -294,6 +294,8 @@ void DeviceVectorState::time_end(double &acc)
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0_, ev1_);
     acc += ms;
+    static const bool log_each = std::getenv("Q1T_SWEEP_LOG") != nullptr;      // tools/: per-launch times on stderr
+    if (log_each) std::fprintf(stderr, "q1t launch %.4f ms\n", ms);
 }
 
 // ---------------------------------------------------------------------------

@@ -87,7 +87,7 @@ private:
     long balance_ = -1;                      // sweep packing: -1 try both, 0 greedy, 1 balanced
     long prefetch_ahead_ = 0;
     bool direct_ = true;
-    bool tma_ = true;                        // dense ladder sweeps load their tiles by TMA (cp.async.bulk.tensor)
+    bool tma_ = false;                       // dense ladder sweeps load their tiles by TMA (cp.async.bulk.tensor): measured slower than cp.async (profiles/r2_ladder_tma.md), off
     bool fuse_ = true;
     bool no_relabel_ = false;                // conditional gates: Swap must move data, not relabel
     long inplace_relabel_ = 0;               // -1 never, 0 when a second column buffer cannot fit, 1 always

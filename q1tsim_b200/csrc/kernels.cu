@@ -300,16 +300,16 @@ __device__ __forceinline__ void round_store(const double2 (&a)[kSlots], const Ro
 // within the register budget of 3 CTAs per SM.
 template <int J, int I>
 struct LadderStep {
-    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const OpDesc &op, double2 f, int u)
+    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const double *qm, double2 f, int u)
     {
-        LadderStep<J, I - 1>::run(a, op, f, u);
-        const double2 q = make_double2(op.m[2 * I], op.m[2 * I + 1]);
-        LadderStep<J, I - 1>::run(a, op, cmul(f, q), u | (1 << I));
+        LadderStep<J, I - 1>::run(a, qm, f, u);
+        const double2 q = make_double2(qm[2 * I], qm[2 * I + 1]);
+        LadderStep<J, I - 1>::run(a, qm, cmul(f, q), u | (1 << I));
     }
 };
 template <int J>
 struct LadderStep<J, -1> {
-    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const OpDesc &, double2 f, int u)
+    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const double *, double2 f, int u)
     {
 #pragma unroll
         for (int h = 0; h < (kSlots >> (J + 1)); ++h) {
@@ -333,7 +333,7 @@ struct LadderSteps {
         const double2 lo = LO_SHARED ? s_lo[(op.phase_id << kThrLoBits) + il]
                                      : __ldg(reinterpret_cast<const double2 *>(ptabs[op.phase_id].lo) + il);
         const double2 hi = s_hiF[(op.phase_id << he_bits) + ih];          // hi[ih] * tile factor
-        LadderStep<J, J - 1>::run(a, op, cmul(lo, hi), 0);
+        LadderStep<J, J - 1>::run(a, op.m, cmul(lo, hi), 0);
         LadderSteps<NS, J + 1, LO_SHARED>::run(a, R, P, ptabs, s_hiF, he_bits, il, ih, s_lo);
     }
 };
@@ -1231,30 +1231,26 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
     if (sweep_uses_ladder_kernel(prog)) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            const int max_lsmem = (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (3 * kHiEntries + 1 + (1 << kThrLoBits)) + sizeof(double) * kMaxPhase * (kMaxBits + 1) + 16 * kSmallThreads + 32);
-            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_lsmem);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_lsmem);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        const bool use_tma = prog.tma_nreq > 0;
-        const size_t lsmem = (sizeof(double2) << prog.T) +
-                             sizeof(double2) * (((size_t)prog.nphase << he_bits) * 2 + prog.nphase + ((size_t)prog.nphase << kThrLoBits)) +
-                             sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x + 16;
+        typedef void (*LadderFn)(const double2 *const *, double2 *const *, const PhaseTab *, const unsigned long long *, double *, const TmaMaps);
+        static const LadderFn fns[2] = { ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true> };
+        static int attr_dev_mask[2] = { 0, 0 };            // function attributes are per device
         int dev = 0, nsm = 148, occ = 0;
         cudaGetDevice(&dev);
+        const int variant = prog.tma_nreq > 0 ? 1 : 0;
+        const LadderFn fn = fns[variant];
+        if (!((attr_dev_mask[variant] >> (dev & 31)) & 1)) {
+            const int max_lsmem = (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (3 * kHiEntries + 1 + (1 << kThrLoBits)) + sizeof(double) * kMaxPhase * (kMaxBits + 1) + 16 * kSmallThreads + 32);
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_lsmem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            attr_dev_mask[variant] |= 1 << (dev & 31);
+        }
+        const size_t lsmem = (sizeof(double2) << prog.T) + 16 +
+                             sizeof(double2) * (((size_t)prog.nphase << he_bits) * 2 + prog.nphase + ((size_t)prog.nphase << kThrLoBits)) +
+                             sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        e = use_tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true>, (int)block.x, lsmem)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, (int)block.x, lsmem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block.x, lsmem);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         // persistent grid: every column gets the same share of the resident CTAs
@@ -1262,10 +1258,7 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         if (per_col < 1) per_col = 1;
         if (per_col > (1ull << prog.n_outer)) per_col = 1ull << prog.n_outer;
         dim3 pgrid((unsigned)per_col, (unsigned)ncols, 1);
-        if (use_tma)
-            ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
-        else
-            ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false><<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
+        fn<<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
         return cudaGetLastError();
     }
     if (ladders_only && (int)block.x <= kSmallThreads)
