@@ -74,6 +74,10 @@ void q1t_state_free(q1t_state *st);
 int q1t_apply_gate(q1t_state *st, const double *matrix, size_t matrix_dim, const size_t *bits, size_t nr_bits,
                    const char *desc);
 /* apply_unary_gate_all (vectorstate.rs:180-189) */
+/* a batch of q1t_apply_gate calls in one crossing of the boundary: matrices concatenated (2 * dim^2 doubles each,
+ * row-major, re/im interleaved), bit lists concatenated; stops at the first error */
+int q1t_apply_gates(q1t_state *st, size_t nr_gates, const double *matrices, const size_t *matrix_dims, const size_t *bits,
+                    const size_t *nr_bits_per_gate);
 int q1t_apply_unary_gate_all(q1t_state *st, const double *matrix, size_t matrix_dim, const char *desc);
 /* apply_conditional_gate (vectorstate.rs:193-227); control = one byte per shot */
 int q1t_apply_conditional_gate(q1t_state *st, const uint8_t *control, size_t nr_control, const double *matrix,
@@ -141,6 +145,25 @@ int    q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr);
  * amplitude, no staging buffer.  Both ranks must call it between two barriers. */
 int    q1t_ipc_export(q1t_state *st, size_t col, unsigned char *handle64);
 int    q1t_peer_swap(q1t_state *st, size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit);
+/* Peer group: the stream-ordered form of the qubit remap (no host synchronisation, no allocation, no handle
+ * exchange per remap).  q1t_group_export registers the two shard buffers a one-column state alternates between
+ * and a mailbox, and returns their CUDA IPC handles (3 x 64 bytes: buffer 0, buffer 1 -- all zero when only one
+ * fits --, mailbox) and device pointers.  q1t_group_open maps the peers' once: `all_handles` = nranks x 3 x 64
+ * bytes in rank order (ranks in other processes), or `all_ptrs` = nranks x 3 device pointers (ranks that are
+ * states of this process, one per device or all on one device).  q1t_group_barrier enqueues a device-side
+ * barrier over the group; q1t_group_remap enqueues barrier + swap + barrier: rank bit rank_bits[j] and local
+ * qubit local_qubits[j] (j < k <= 4) trade places in one in-place pass, every rank exchanging with its 2^k - 1
+ * partners at once.  All ranks must make the same calls in the same order. */
+/* every column times the scalar re + i*im (a rank's share of a one-qubit gate on a rank bit that is still
+ * pinned to a basis value); real factors are deferred into the next fused sweep like the Hadamard normalisations */
+int    q1t_scale(q1t_state *st, double re, double im);
+/* VectorState::from_qubit_coefs (vectorstate.rs:62-83) into an existing state: 2 * nr_bits complex coefficients */
+int    q1t_set_product_state(q1t_state *st, const double *coefs);
+int    q1t_group_export(q1t_state *st, unsigned char *handles3x64, void **ptrs3);
+int    q1t_group_open(q1t_state *st, size_t nranks, size_t rank, const unsigned char *all_handles, void *const *all_ptrs);
+int    q1t_group_barrier(q1t_state *st);
+int    q1t_group_remap(q1t_state *st, size_t k, const int *rank_bits, const size_t *local_qubits);
+int    q1t_group_close(q1t_state *st);
 /* rand 0.7 Uniform(0,total) draws as WeightedIndex::sample makes them (vectorstate.rs:126) */
 double q1t_uniform_draw(q1t_rng rng, double total);
 void   q1t_uniform_draws(q1t_rng rng, double total, size_t n, double *out);

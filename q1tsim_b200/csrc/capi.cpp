@@ -61,6 +61,20 @@ int q1t_apply_gate(q1t_state *st, const double *m, size_t dim, const size_t *bit
     ST_OR_FAIL;
     return st->impl->apply_gate(m, dim, bits, k, desc);
 }
+// a batch of gates in one call: matrices concatenated (2 * dim^2 doubles each), bits concatenated
+int q1t_apply_gates(q1t_state *st, size_t ngates, const double *mats, const size_t *dims, const size_t *bits, const size_t *nbits)
+{
+    ST_OR_FAIL;
+    if (ngates && (!mats || !dims || !bits || !nbits)) return Q1T_ERR_INVALID_ARGUMENT;
+    size_t moff = 0, boff = 0;
+    for (size_t g = 0; g < ngates; ++g) {
+        const int rc = st->impl->apply_gate(mats + moff, dims[g], bits + boff, nbits[g], "gate");
+        if (rc) return rc;
+        moff += 2 * dims[g] * dims[g];
+        boff += nbits[g];
+    }
+    return Q1T_OK;
+}
 int q1t_apply_unary_gate_all(q1t_state *st, const double *m, size_t dim, const char *desc)
 {
     ST_OR_FAIL;
@@ -152,6 +166,26 @@ int q1t_replace_columns(q1t_state *st, size_t ncols, const uint64_t *idx, const 
 }
 int q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr) { ST_OR_FAIL; return st->impl->column_ptr(col, ptr); }
 int q1t_ipc_export(q1t_state *st, size_t col, unsigned char *handle64) { ST_OR_FAIL; return st->impl->ipc_export(col, handle64); }
+int q1t_set_product_state(q1t_state *st, const double *coefs)
+{
+    ST_OR_FAIL;
+    if (!coefs) return Q1T_ERR_INVALID_ARGUMENT;
+    return st->impl->set_product_state(coefs);
+}
+int q1t_scale(q1t_state *st, double re, double im) { ST_OR_FAIL; return st->impl->scale_all(re, im); }
+int q1t_group_export(q1t_state *st, unsigned char *handles3x64, void **ptrs3) { ST_OR_FAIL; return st->impl->group_export(handles3x64, ptrs3); }
+int q1t_group_open(q1t_state *st, size_t nranks, size_t rank, const unsigned char *all_handles, void *const *all_ptrs)
+{
+    ST_OR_FAIL;
+    return st->impl->group_open(nranks, rank, all_handles, all_ptrs);
+}
+int q1t_group_barrier(q1t_state *st) { ST_OR_FAIL; return st->impl->group_barrier(); }
+int q1t_group_remap(q1t_state *st, size_t k, const int *rank_bits, const size_t *local_qubits)
+{
+    ST_OR_FAIL;
+    return st->impl->group_remap(k, rank_bits, local_qubits);
+}
+int q1t_group_close(q1t_state *st) { ST_OR_FAIL; return st->impl->group_close(); }
 int q1t_peer_swap(q1t_state *st, size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit)
 {
     ST_OR_FAIL;

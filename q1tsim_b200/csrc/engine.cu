@@ -126,10 +126,17 @@ DeviceVectorState::~DeviceVectorState()
         cudaSetDevice(device_);
         cudaStreamSynchronize(stream_);
         const size_t bytes = sizeof(double2) << n_;
+        group_close();
+        // buffers that were exported to peers are freed, never pooled: a pooled buffer could be handed to another
+        // state while a peer still holds a mapping of it
+        auto exported = [&](double2 *p) { return grp_.exported && (p == grp_.bufs[0] || p == grp_.bufs[1]); };
         for (Column &c : cols_)
-            if (c.buf && !pool_give(device_, bytes, c.buf)) cudaFree(c.buf);
+            if (c.buf && (exported(c.buf) || !pool_give(device_, bytes, c.buf))) cudaFree(c.buf);
         for (double2 *p : free_bufs_)
-            if (!pool_give(device_, bytes, p)) cudaFree(p);
+            if (exported(p) || !pool_give(device_, bytes, p)) cudaFree(p);
+        if (grp_.mail) cudaFree(grp_.mail);
+        if (grp_.ev0) cudaEventDestroy(grp_.ev0);
+        if (grp_.ev1) cudaEventDestroy(grp_.ev1);
         scratch_free(device_, d_colptrs_, sizeof(double2 *) * colptrs_cap_);
         scratch_free(device_, d_ptabs_, sizeof(PhaseTab) * kMaxPhase);
         scratch_free(device_, d_leaf_, sizeof(double) * leaf_cap_);
@@ -205,7 +212,8 @@ void DeviceVectorState::release_column(double2 *p)
         if (device_ >= 0 && device_ < 64) total_of[device_] = total_b;
     }
     const bool fits = total_b == 0 || (live + free_bufs_.size() + 1) * bytes <= total_b / 100 * 80;
-    if (free_bufs_.size() < 2 && fits) free_bufs_.push_back(p);
+    const bool registered = grp_.exported && (p == grp_.bufs[0] || p == grp_.bufs[1]);    // peers have it mapped: keep
+    if (registered || (free_bufs_.size() < 2 && fits)) free_bufs_.push_back(p);
     else { cudaStreamSynchronize(stream_); cudaFree(p); }
 }
 
@@ -254,6 +262,22 @@ static unsigned long long physical_index(uint64_t logical, const std::vector<int
 
 // A lazy basis column is kept by its LOGICAL index; the buffer is laid out in the current physical order
 // (a pending zero-byte Swap relabelling makes the two differ), so the 1 goes to the physical position.
+// the state becomes the product state of `coefs` in place (its column buffers stay the ones it has)
+int DeviceVectorState::set_product_state(const double *coefs)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    queue_.clear();
+    queue_cols_.clear();
+    pending_scale_ = 1.0;
+    CK(cudaStreamSynchronize(stream_));
+    for (Column &c : cols_)
+        if (c.buf) release_column(c.buf);
+    cols_.clear();
+    for (int l = 0; l < n_; ++l) perm_[l] = l;
+    return init_from_qubit_coefs(coefs);
+}
+
 int DeviceVectorState::materialize(Column &c)
 {
     if (!c.basis) return Q1T_OK;
@@ -458,6 +482,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     {
         double total = 1.0;
         for (PlannedSweep &ps : sweeps) { total *= ps.prog.scale; ps.prog.scale = 1.0; ps.prog.gen_scale = 1.0; }
+        if (which.size() == cols_.size()) { total *= pending_scale_; pending_scale_ = 1.0; }
         if (generate) sweeps.front().prog.gen_scale = total;
         else sweeps.back().prog.scale = total;
     }
@@ -808,7 +833,43 @@ int DeviceVectorState::flush_async()
     if (rc) return rc;
     rc = run_queue(true);
     if (rc) return rc;
-    return canonicalize();
+    rc = canonicalize();
+    if (rc) return rc;
+    return apply_pending_scale();
+}
+
+// a scalar that no sweep has taken along: one scaling pass over the dense columns (lazy basis columns
+// cannot carry a factor, they are materialised)
+int DeviceVectorState::apply_pending_scale()
+{
+    if (pending_scale_ == 1.0) return Q1T_OK;
+    const double f = pending_scale_;
+    pending_scale_ = 1.0;
+    for (Column &c : cols_) {
+        if (c.basis && c.basis_idx == UINT64_MAX) continue;            // all-zero stays all-zero
+        int rc = materialize(c);
+        if (rc) return rc;
+        CK(launch_scale2(c.buf, c.buf, nullptr, n_, f, 0.0, stream_));
+        stats.kernel_launches++;
+        stats.sweep_column_passes++;
+        stats.sweep_bytes += 32ull << n_;
+    }
+    stats.sweeps++;
+    return Q1T_OK;
+}
+
+// every column times re + i im.  The modulus (with the sign of a real factor) is deferred like the Hadamard
+// normalisations; a genuine phase is queued as a global-phase gate.
+int DeviceVectorState::scale_all(double re, double im)
+{
+    if (!queue_cols_.empty()) { int rc = run_queue(); if (rc) return rc; }
+    if (im == 0.0) { pending_scale_ *= re; return Q1T_OK; }
+    const double mod = std::hypot(re, im);
+    pending_scale_ *= mod;
+    if (mod == 0.0) return Q1T_OK;
+    const double m[8] = { re / mod, im / mod, 0, 0, 0, 0, re / mod, im / mod };
+    const size_t bit = 0;
+    return apply_gate(m, 2, &bit, 1, "phase");
 }
 
 int DeviceVectorState::flush()
@@ -1229,6 +1290,7 @@ int DeviceVectorState::replace_columns(size_t ncols, const uint64_t *idx, const 
     if (rc) return rc;
     queue_.clear();
     queue_cols_.clear();
+    pending_scale_ = 1.0;
     CK(cudaStreamSynchronize(stream_));
     for (Column &c : cols_)
         if (c.buf) release_column(c.buf);
@@ -1298,6 +1360,195 @@ int DeviceVectorState::peer_swap(size_t col, const unsigned char *peer_handle64,
     stats.peer_swap_ms += ms;
     stats.peer_swap_bytes += (16ull << n_) / 2;      // a quarter shard read remotely + a quarter written remotely
     stats.kernel_launches++;
+    return Q1T_OK;
+}
+
+// ---------------------------------------------------------------------------
+// peer group.  group_export(): this rank registers the (up to) two shard buffers its single column
+// alternates between (column + relabel scratch) and a mailbox, and hands out their IPC handles and
+// device pointers; group_open(): the peers' buffers and mailboxes are mapped ONCE (IPC handles between
+// processes, plain pointers between states of one process).  After that a qubit remap is three
+// stream-ordered launches -- barrier, swap, barrier -- with no host synchronisation, no handle exchange
+// and no allocation.
+// ---------------------------------------------------------------------------
+int DeviceVectorState::group_export(unsigned char *handles, void **ptrs)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (cols_.size() != 1) return fail(Q1T_ERR_UNSUPPORTED, "group_export: the state must have exactly one column");
+    rc = flush();
+    if (rc) return rc;
+    if (!grp_.exported) {
+        // the column's buffer (or, for a lazy column, the buffer its first sweep will take) and one scratch
+        double2 *b0 = cols_[0].buf;
+        if (!b0) {
+            if (free_bufs_.empty()) {
+                rc = alloc_column(&b0);
+                if (rc) return rc;
+                free_bufs_.push_back(b0);
+            } else b0 = free_bufs_.back();
+        }
+        double2 *b1 = nullptr;
+        for (double2 *p : free_bufs_)
+            if (p != b0) b1 = p;
+        if (!b1 && !want_inplace_relabel()) {
+            std::vector<double2 *> keep;
+            keep.swap(free_bufs_);                       // alloc_column() must not hand b0 out again
+            rc = alloc_column(&b1);
+            free_bufs_.swap(keep);
+            if (rc) return rc;
+            free_bufs_.insert(free_bufs_.begin(), b1);
+        }
+        grp_.bufs[0] = b0;
+        grp_.bufs[1] = b1;
+        // only registered buffers stay in the free list: whatever the column moves into later must be mapped by the peers
+        {
+            std::vector<double2 *> keep;
+            const size_t bytes = sizeof(double2) << n_;
+            for (double2 *p : free_bufs_) {
+                if (p == b0 || p == b1) keep.push_back(p);
+                else if (!pool_give(device_, bytes, p)) cudaFree(p);
+            }
+            free_bufs_.swap(keep);
+        }
+        CK(cudaMalloc(&grp_.mail, 4096));
+        CK(cudaMemsetAsync(grp_.mail, 0, 4096, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        CK(cudaEventCreate(&grp_.ev0));
+        CK(cudaEventCreate(&grp_.ev1));
+        grp_.exported = true;
+    }
+    void *all[3] = { grp_.bufs[0], grp_.bufs[1], grp_.mail };
+    for (int i = 0; i < 3; ++i) {
+        if (ptrs) ptrs[i] = all[i];
+        std::memset(handles + 64 * i, 0, 64);
+        if (!all[i]) continue;
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, all[i]));
+        std::memcpy(handles + 64 * i, &h, 64);
+    }
+    return Q1T_OK;
+}
+
+int DeviceVectorState::group_open(size_t P, size_t rank, const unsigned char *all_handles, void *const *all_ptrs)
+{
+    if (!grp_.exported) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_open: call group_export first");
+    if (grp_.open) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_open: already open");
+    if (P < 2 || P > 32 || rank >= P || (P & (P - 1)) || (!all_handles && !all_ptrs))
+        return fail(Q1T_ERR_INVALID_ARGUMENT, "group_open: bad argument");
+    CK(cudaSetDevice(device_));
+    std::vector<void *> pb(2 * P, nullptr);
+    std::vector<unsigned long long *> pm(P, nullptr);
+    for (size_t r = 0; r < P; ++r) {
+        if (r == rank) {
+            pb[2 * r] = grp_.bufs[0]; pb[2 * r + 1] = grp_.bufs[1]; pm[r] = grp_.mail;
+            continue;
+        }
+        for (int i = 0; i < 3; ++i) {
+            void *p = nullptr;
+            if (all_ptrs) p = all_ptrs[3 * r + i];                     // same process: the pointer itself
+            else {
+                const unsigned char *hb = all_handles + 64 * (3 * r + i);
+                bool zero = true;
+                for (int b = 0; b < 64; ++b) zero = zero && hb[b] == 0;
+                if (!zero) {
+                    cudaIpcMemHandle_t h;
+                    std::memcpy(&h, hb, 64);
+                    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                    grp_.ipc_opened.push_back(p);
+                }
+            }
+            if (i < 2) pb[2 * r + i] = p;
+            else pm[r] = static_cast<unsigned long long *>(p);
+        }
+        if (!pb[2 * r] || !pm[r]) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_open: a peer exported no buffer");
+    }
+    CK(cudaMalloc(&grp_.d_peer_buf, sizeof(void *) * 2 * P));
+    CK(cudaMalloc(&grp_.d_peer_mail, sizeof(void *) * P));
+    CK(cudaMemcpy(grp_.d_peer_buf, pb.data(), sizeof(void *) * 2 * P, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(grp_.d_peer_mail, pm.data(), sizeof(void *) * P, cudaMemcpyHostToDevice));
+    grp_.P = (int)P;
+    grp_.rank = (int)rank;
+    grp_.open = true;
+    return Q1T_OK;
+}
+
+void DeviceVectorState::group_collect_timing()
+{
+    if (!grp_.timing_pending) return;
+    float ms = 0;
+    if (cudaEventSynchronize(grp_.ev1) == cudaSuccess && cudaEventElapsedTime(&ms, grp_.ev0, grp_.ev1) == cudaSuccess) stats.peer_swap_ms += ms;
+    else cudaGetLastError();
+    grp_.timing_pending = false;
+}
+
+int DeviceVectorState::group_barrier()
+{
+    if (!grp_.open) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_barrier: no open peer group");
+    CK(cudaSetDevice(device_));
+    unsigned long long cur = 0;
+    if (cols_.size() == 1 && cols_[0].buf && cols_[0].buf == grp_.bufs[1]) cur = 1;
+    CK(launch_group_barrier(grp_.d_peer_mail, grp_.mail, grp_.P, grp_.rank, ++grp_.epoch, cur, stream_));
+    stats.kernel_launches++;
+    return Q1T_OK;
+}
+
+// rank bits rank_bits[j] trade places with local qubits local_qubits[j] (engine qubit numbering: 0 = top index bit)
+int DeviceVectorState::group_remap(size_t k, const int *rank_bits, const size_t *local_qubits)
+{
+    if (!grp_.open) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: no open peer group");
+    if (k < 1 || k > (size_t)kMaxRemapBits || (int)k + 1 > n_ || !rank_bits || !local_qubits)
+        return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: bad argument");
+    if (cols_.size() != 1) return fail(Q1T_ERR_UNSUPPORTED, "group_remap: the state must have exactly one column");
+    int rc = flush_async();
+    if (rc) return rc;
+    rc = materialize(cols_[0]);
+    if (rc) return rc;
+    if (cols_[0].buf != grp_.bufs[0] && cols_[0].buf != grp_.bufs[1])
+        return fail(Q1T_ERR_UNSUPPORTED, "group_remap: the column does not live in a registered buffer");
+    GroupRemapArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.n = n_; a.k = (int)k; a.P = grp_.P; a.rank = grp_.rank;
+    uint64_t used = 0;
+    for (size_t j = 0; j < k; ++j) {
+        if (rank_bits[j] < 0 || (1 << rank_bits[j]) >= grp_.P || local_qubits[j] >= (size_t)n_)
+            return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: bit out of range");
+        a.gb[j] = rank_bits[j];
+        a.lp[j] = n_ - 1 - (int)local_qubits[j];
+        if ((used >> a.lp[j]) & 1ull) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: duplicate local qubit");
+        used |= 1ull << a.lp[j];
+    }
+    a.split = n_ - 1;
+    while ((used >> a.split) & 1ull) --a.split;                       // the highest index bit that is not traded
+    std::vector<int> ins(a.lp, a.lp + k);
+    ins.push_back(a.split);
+    std::sort(ins.begin(), ins.end());
+    for (size_t i = 0; i <= k; ++i) a.ins[i] = ins[i];
+    group_collect_timing();
+    rc = group_barrier();                                             // every rank has finished what precedes, and published its buffer
+    if (rc) return rc;
+    CK(cudaEventRecord(grp_.ev0, stream_));
+    CK(launch_group_swap(cols_[0].buf, grp_.d_peer_buf, grp_.mail, a, stream_));
+    CK(cudaEventRecord(grp_.ev1, stream_));
+    grp_.timing_pending = true;
+    stats.kernel_launches++;
+    stats.peer_swap_bytes += (((1ull << k) - 1ull) << (n_ - (int)k - 1)) * 32ull;     // remote reads + remote writes of this rank
+    return group_barrier();                                           // nobody touches a shard before every swap has landed
+}
+
+int DeviceVectorState::group_close()
+{
+    if (!grp_.exported) return Q1T_OK;
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    group_collect_timing();
+    for (void *p : grp_.ipc_opened) cudaIpcCloseMemHandle(p);
+    grp_.ipc_opened.clear();
+    if (grp_.d_peer_buf) cudaFree(grp_.d_peer_buf);
+    if (grp_.d_peer_mail) cudaFree(grp_.d_peer_mail);
+    grp_.d_peer_buf = nullptr;
+    grp_.d_peer_mail = nullptr;
+    grp_.open = false;
     return Q1T_OK;
 }
 
@@ -1462,6 +1713,7 @@ int DeviceVectorState::reset_all()
     if (rc) return rc;
     queue_.clear();
     queue_cols_.clear();
+    pending_scale_ = 1.0;
     CK(cudaStreamSynchronize(stream_));
     for (Column &c : cols_)
         if (c.buf) release_column(c.buf);

@@ -29,6 +29,7 @@ public:
     ~DeviceVectorState();
     int init_zero_state();
     int init_from_qubit_coefs(const double *coefs);
+    int set_product_state(const double *coefs);
 
     int apply_gate(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc);
     int apply_unary_gate_all(const double *mat, size_t dim, const char *desc);
@@ -50,6 +51,15 @@ public:
     int column_ptr(size_t col, void **ptr);
     int ipc_export(size_t col, unsigned char *handle64);
     int peer_swap(size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit);
+
+    // peer group (one shard per GPU): two registered shard buffers and a mailbox per rank, mapped by every peer
+    // once; barrier and multi-bit remap are stream-ordered device work (kernels.cu group_*_kernel)
+    int scale_all(double re, double im);          // every column times a scalar (a rank's share of a gate on a pinned rank bit)
+    int group_export(unsigned char *handles3x64, void **ptrs3);
+    int group_open(size_t P, size_t rank, const unsigned char *all_handles, void *const *all_ptrs);
+    int group_barrier();
+    int group_remap(size_t k, const int *rank_bits, const size_t *local_qubits);
+    int group_close();
 
     int counts(size_t *out);
     size_t nr_columns() { return cols_.size(); }
@@ -92,6 +102,8 @@ private:
     bool no_relabel_ = false;                // conditional gates: Swap must move data, not relabel
     long inplace_relabel_ = 0;               // -1 never, 0 when a second column buffer cannot fit, 1 always
     bool want_inplace_relabel();
+    double pending_scale_ = 1.0;             // real factor owed to every column: rides on the next sweep batch's deferred scale
+    int apply_pending_scale();
 
     // device scratch
     double2 **d_colptrs_ = nullptr; size_t colptrs_cap_ = 0;
@@ -104,6 +116,19 @@ private:
     double2 **d_pair_ = nullptr;
     unsigned long long *d_gen_ = nullptr; size_t gen_cap_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    struct PeerGroup {
+        bool exported = false, open = false;
+        int P = 0, rank = 0;
+        double2 *bufs[2] = { nullptr, nullptr };        // this rank's registered shard buffers (never freed while exported)
+        unsigned long long *mail = nullptr;             // this rank's mailbox
+        std::vector<void *> ipc_opened;                 // mappings to close
+        void **d_peer_buf = nullptr;                    // [P][2]
+        unsigned long long **d_peer_mail = nullptr;     // [P]
+        unsigned long long epoch = 0;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        bool timing_pending = false;
+    } grp_;
+    void group_collect_timing();
 
     int fail(int code, const std::string &msg) { err_ = msg; return code; }
     int cuda_fail(cudaError_t e, const char *what);

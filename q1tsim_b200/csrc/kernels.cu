@@ -1592,6 +1592,91 @@ cudaError_t launch_peer_swap(double2 *d_mine, double2 *d_theirs, int n, int L, i
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// peer group (one process per GPU): device-side barrier and the multi-bit qubit remap
+// over NVLink peer memory.
+//
+// Every rank owns a small mailbox in its own HBM that all peers have mapped (CUDA IPC): slot 2r holds the
+// last barrier epoch rank r has reached, slot 2r+1 which of its two registered shard buffers is current.
+// group_barrier_kernel: one lane per peer writes (current buffer, then epoch) into that peer's mailbox with
+// system-scope release stores and then waits, with system-scope acquire loads, until the peer's epoch has
+// arrived in its own mailbox.  Stream-ordered: the host never blocks, and everything enqueued before the
+// barrier on any rank is complete and visible to everything enqueued after it on every rank.
+// ---------------------------------------------------------------------------
+__global__ void group_barrier_kernel(unsigned long long *const *__restrict__ peer_mail, unsigned long long *my_mail, int P, int rank,
+                                     unsigned long long epoch, unsigned long long cur)
+{
+    const int t = threadIdx.x;
+    if (t >= P || t == rank) return;
+    unsigned long long *theirs = peer_mail[t];
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(theirs + 2 * rank + 1), "l"(cur) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(theirs + 2 * rank), "l"(epoch) : "memory");
+    unsigned long long seen = 0;
+    for (unsigned long long spins = 0;; ++spins) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(seen) : "l"(my_mail + 2 * t) : "memory");
+        if (seen >= epoch) break;
+        __nanosleep(100);
+        if (spins > 200000000ull) __trap();      // ~20 s: a peer that died must not hang this device for good
+    }
+}
+cudaError_t launch_group_barrier(unsigned long long *const *d_peer_mail, unsigned long long *d_my_mail, int P, int rank,
+                                 unsigned long long epoch, unsigned long long cur, cudaStream_t stream)
+{
+    group_barrier_kernel<<<1, 32, 0, stream>>>(d_peer_mail, d_my_mail, P, rank, epoch, cur);
+    return cudaGetLastError();
+}
+
+// Multi-bit remap: k rank bits gb[j] and k index bits lp[j] of the shard trade places, in place, in ONE pass.
+// Element (rank r, index l) goes to (r', l'): r' = r with bit gb[j] := l_lp[j], l' = l with bit lp[j] := r_gb[j]
+// -- an involution, so the data moves in pairs between two ranks (or stays, when the two bit patterns agree).
+// Of every pair, one rank does the swap: the lower rank for the pairs whose index bit `split` is 0, the higher
+// one for the others; each rank therefore reads and writes (2^k - 1) 2^(n-k-1) remote amplitudes, spread
+// over its 2^k - 1 partners (blockIdx.y), all NVLink directions busy at once.
+__global__ void __launch_bounds__(256)
+group_swap_kernel(double2 *__restrict__ mine, void *const *__restrict__ peer_buf, const unsigned long long *__restrict__ my_mail, GroupRemapArgs a)
+{
+    unsigned apat = 0;
+    for (int j = 0; j < a.k; ++j) apat |= (unsigned)((a.rank >> a.gb[j]) & 1) << j;
+    const unsigned bpat = blockIdx.y < apat ? blockIdx.y : blockIdx.y + 1;
+    int partner = a.rank;
+    unsigned long long mine_or = 0, theirs_or = 0;
+    for (int j = 0; j < a.k; ++j) {
+        const unsigned bj = (bpat >> j) & 1u, aj = (apat >> j) & 1u;
+        partner = (partner & ~(1 << a.gb[j])) | ((int)bj << a.gb[j]);
+        mine_or |= (unsigned long long)bj << a.lp[j];
+        theirs_or |= (unsigned long long)aj << a.lp[j];
+    }
+    const unsigned long long c = a.rank < partner ? 0ull : 1ull;
+    mine_or |= c << a.split;
+    theirs_or |= c << a.split;
+    const unsigned long long cur = my_mail[2 * partner + 1];          // published by the partner in the barrier before this kernel
+    double2 *__restrict__ theirs = static_cast<double2 *>(peer_buf[2 * partner + (int)(cur & 1ull)]);
+    const unsigned long long npairs = 1ull << (a.n - a.k - 1);
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < npairs;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long base = t;
+        for (int i = 0; i <= a.k; ++i) {                              // open a zero bit at every swapped position (ascending)
+            const int p = a.ins[i];
+            base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
+        }
+        const double2 x = mine[base | mine_or];
+        const double2 y = theirs[base | theirs_or];
+        mine[base | mine_or] = y;
+        theirs[base | theirs_or] = x;
+    }
+}
+cudaError_t launch_group_swap(double2 *d_mine, void *const *d_peer_buf, const unsigned long long *d_my_mail, const GroupRemapArgs &a,
+                              cudaStream_t stream)
+{
+    const unsigned long long npairs = 1ull << (a.n - a.k - 1);
+    unsigned long long blocks = (npairs + 255) / 256;
+    const unsigned long long cap = (148ull * 16ull) / ((1u << a.k) - 1u) + 1;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    group_swap_kernel<<<dim3((unsigned)blocks, (1u << a.k) - 1u), 256, 0, stream>>>(d_mine, d_peer_buf, d_my_mail, a);
+    return cudaGetLastError();
+}
+
 __global__ void set_basis_kernel(double2 *__restrict__ st, unsigned long long idx)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) st[idx] = make_double2(1.0, 0.0);

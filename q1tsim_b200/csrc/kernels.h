@@ -43,6 +43,19 @@ cudaError_t launch_collapse(const double2 *d_in, double2 *d_out0, double2 *d_out
                             double f1, cudaStream_t stream);
 cudaError_t launch_product_state(double2 *d_col, int n, const double2 *d_coefs, cudaStream_t stream);
 cudaError_t launch_peer_swap(double2 *d_mine, double2 *d_theirs, int n, int L, int a, cudaStream_t stream);
+// peer group: device-side barrier over mapped mailboxes, and the multi-bit qubit remap (kernels.cu)
+constexpr int kMaxRemapBits = 4;
+struct GroupRemapArgs {
+    int n, k, P, rank;               // index bits of the shard, bits traded, ranks, this rank
+    int gb[kMaxRemapBits];           // rank bits
+    int lp[kMaxRemapBits];           // index-bit positions of the shard they trade with
+    int split;                       // index bit (not among lp) that splits the pairs between the two ranks of a pair
+    int ins[kMaxRemapBits + 1];      // lp and split, ascending
+};
+cudaError_t launch_group_barrier(unsigned long long *const *d_peer_mail, unsigned long long *d_my_mail, int P, int rank,
+                                 unsigned long long epoch, unsigned long long cur, cudaStream_t stream);
+cudaError_t launch_group_swap(double2 *d_mine, void *const *d_peer_buf, const unsigned long long *d_my_mail, const GroupRemapArgs &a,
+                              cudaStream_t stream);
 cudaError_t launch_set_basis(double2 *d_col, unsigned long long idx, cudaStream_t stream);
 
 }  // namespace q1t

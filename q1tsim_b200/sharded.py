@@ -161,6 +161,78 @@ class EngineLocal:
         self.L.q1t_peer_swap.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_ubyte), C.c_size_t, C.c_int]
         self.st._chk(self.L.q1t_peer_swap(self.st._p, col, buf, local_qubit, my_bit))
 
+    # peer group: buffers and mailboxes mapped once, remaps are stream-ordered device work
+    def group_setup(self, dist, group, rank, P):
+        C = self.C
+        L = self.L
+        L.q1t_group_export.restype = C.c_int
+        L.q1t_group_export.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+        L.q1t_group_open.restype = C.c_int
+        L.q1t_group_open.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+        L.q1t_group_remap.restype = C.c_int
+        L.q1t_group_remap.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+        L.q1t_group_barrier.restype = C.c_int
+        L.q1t_group_barrier.argtypes = [C.c_void_p]
+        L.q1t_group_close.restype = C.c_int
+        L.q1t_group_close.argtypes = [C.c_void_p]
+        mine = (C.c_ubyte * 192)()
+        ptrs = (C.c_void_p * 3)()
+        self.st._chk(L.q1t_group_export(self.st._p, mine, ptrs))
+        allh = [None] * P
+        dist.all_gather_object(allh, bytes(mine), group=group)
+        blob = (C.c_ubyte * (192 * P)).from_buffer_copy(b"".join(allh))
+        self.st._chk(L.q1t_group_open(self.st._p, P, rank, blob, None))
+        self.has_group = True
+
+    def group_remap(self, rank_bits, local_qubits):
+        C = self.C
+        k = len(rank_bits)
+        rb = (C.c_int * k)(*[int(b) for b in rank_bits])
+        lq = (C.c_size_t * k)(*[int(q) for q in local_qubits])
+        self.st._chk(self.L.q1t_group_remap(self.st._p, k, rb, lq))
+
+    def group_barrier(self):
+        self.st._chk(self.L.q1t_group_barrier(self.st._p))
+
+    def pack_gates(self, gates):
+        """[(matrix, bits)] -> argument arrays of q1t_apply_gates (built once per recorded schedule)"""
+        C = self.C
+        mats = np.concatenate([np.ascontiguousarray(np.asarray(m, dtype=np.complex128)).ravel() for m, _ in gates]).view(np.float64).copy()
+        dims = (C.c_size_t * len(gates))(*[int(np.asarray(m).shape[0]) for m, _ in gates])
+        bits = (C.c_size_t * max(1, sum(len(b) for _, b in gates)))(*[int(x) for _, b in gates for x in b])
+        nb = (C.c_size_t * len(gates))(*[len(b) for _, b in gates])
+        self.L.q1t_apply_gates.restype = C.c_int
+        self.L.q1t_apply_gates.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                           C.POINTER(C.c_size_t)]
+        return (len(gates), mats, mats.ctypes.data_as(C.POINTER(C.c_double)), dims, bits, nb)
+
+    def apply_packed(self, packed):
+        n, _keep, mp, dims, bits, nb = packed
+        self.st._chk(self.L.q1t_apply_gates(self.st._p, n, mp, dims, bits, nb))
+
+    def group_close(self):
+        if getattr(self, "has_group", False):
+            self.L.q1t_group_close(self.st._p)
+            self.has_group = False
+
+    def scale(self, s):
+        C = self.C
+        self.L.q1t_scale.restype = C.c_int
+        self.L.q1t_scale.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        s = complex(s)
+        self.st._chk(self.L.q1t_scale(self.st._p, s.real, s.imag))
+
+    def reset_all(self):
+        self.st.reset_all()
+
+    def set_product_state(self, coefs):
+        """replace the state by the product state of per-qubit coefficient pairs (vectorstate.rs:62-83)"""
+        C = self.C
+        c = np.ascontiguousarray(np.asarray(coefs, dtype=np.complex128)).view(np.float64)
+        self.L.q1t_set_product_state.restype = C.c_int
+        self.L.q1t_set_product_state.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self.st._chk(self.L.q1t_set_product_state(self.st._p, c.ctypes.data_as(C.POINTER(C.c_double))))
+
     def draws(self, rng, total, n):
         C = self.C
         out = np.zeros(max(n, 1), dtype=np.float64)
@@ -215,10 +287,40 @@ def select_block(mat, k, fixed):
     return m[np.ix_(keep, keep)]
 
 
+class _Recorder:
+    """Stands in for the local state while ShardedState walks a gate-only prefix of an op list for the first time:
+    what the walk does to the local engine (gates, scalars, Swap relabels, remaps) is data-independent, so it is
+    taped and replayed on later runs of the same op list -- the gates of a segment in ONE call across the C ABI
+    instead of a Python round trip per gate."""
+
+    def __init__(self, local):
+        self.local = local
+        self.tape = []
+        self.valid = True
+
+    def apply_gate(self, mat, qubits):
+        self.tape.append(("g", np.array(mat, dtype=np.complex128), [int(q) for q in qubits]))
+        self.local.apply_gate(mat, qubits)
+
+    def scale(self, s):
+        self.tape.append(("s", complex(s)))
+        self.local.scale(s)
+
+    def group_remap(self, rank_bits, local_qubits):
+        self.tape.append(("r", [int(b) for b in rank_bits], [int(q) for q in local_qubits]))
+        self.local.group_remap(rank_bits, local_qubits)
+
+    def __getattr__(self, name):
+        if name in ("ncols", "counts", "nleaves", "n_local", "shots", "device", "has_group", "stats", "group_setup"):
+            return getattr(self.local, name)
+        self.valid = False              # anything else (collapse, column replacement, host exchange) is not taped
+        return getattr(self.local, name)
+
+
 class ShardedState:
     """`QuState` over a state sharded across the ranks of a process group."""
 
-    def __init__(self, nr_bits, nr_shots, group=None, device=None, local_factory=None, lookahead=None):
+    def __init__(self, nr_bits, nr_shots, group=None, device=None, local_factory=None, lookahead=None, replicate_start=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -233,7 +335,9 @@ class ShardedState:
             raise ValueError("sharded states need at least 10 local qubits per rank (one canonical leaf)")
         factory = local_factory or _engine_factory
         self.device = self.rank if device is None else device
-        self.local = factory(self.n_local, nr_shots, self.device, self.rank != 0)
+        import os as _os
+        _repl = replicate_start if replicate_start is not None else _os.environ.get("Q1T_REPLICATE", "1") != "0"
+        self.local = factory(self.n_local, nr_shots, self.device, self.rank != 0 and not _repl)
         # where[q] = ("g", rank bit) | ("l", local engine qubit); canonical: q < g global
         self.where = [self._canonical(q) for q in range(nr_bits)]
         self.exchanges = 0
@@ -242,6 +346,21 @@ class ShardedState:
         self.lookahead = lookahead        # optional callable(rank bit, keep) -> victim logical qubit
         import os
         self.peer_memory = os.environ.get("Q1T_PEER_MEMORY", "1") != "0"
+        # Replicated start.  |0..0> pins every rank bit to 0: while rank bit i is pinned to v, only the ranks whose bit
+        # equals v hold data -- and what they hold does not depend on the other ranks.  Instead of idling, EVERY rank
+        # runs the same local program (pin[i] = v stands for "my bit is v"); a one-qubit gate on the pinned global
+        # qubit then is a scalar per rank (its matrix entry U[my bit][v]), no exchange, and the bit is free.  Ranks
+        # whose real bit differs from a pin still standing are zeroed before anything observes the state (_depin).
+        self.replicate = replicate_start if replicate_start is not None else os.environ.get("Q1T_REPLICATE", "1") != "0"
+        self.pin = [0 if self.replicate else None] * self.g
+        if not self.replicate and self.rank != 0:
+            pass                          # (the factory was told `empty`: an all-zero shard)
+        self.remaps = 0                   # remap operations (a multi-bit remap counts once)
+        self._start_tag = "zero"          # the state is a fresh |0..0> (run_ops may replay a taped schedule)
+        self.group_ok = False
+        if self.P > 1 and self.peer_memory and getattr(self.local, "group_setup", None) is not None and os.environ.get("Q1T_PEER_GROUP", "1") != "0":
+            self.local.group_setup(dist, group, self.rank, self.P)
+            self.group_ok = True
 
     # ---- layout bookkeeping ------------------------------------------------
     def _canonical(self, q):
@@ -317,22 +436,114 @@ class ShardedState:
                 torch.cuda.synchronize(t.device)
         self.exchange_seconds += time.perf_counter() - t_start
         self.exchanges += 1
+        self.remaps += 1
         qg, ql = self._qubit_at(("g", gbit)), self._qubit_at(("l", j))
         self.where[qg], self.where[ql] = ("l", j), ("g", gbit)
 
-    def _bring_local(self, q, keep=()):
-        """make logical qubit q a local qubit; evict a local qubit not in `keep`"""
-        kind, i = self.where[q]
-        if kind == "l":
+    def _exchange_multi(self, trades):
+        """several rank bits trade places with as many local qubits: trades = [(rank bit, logical qubit that is local)].
+        With a peer group (CUDA engine, one column) that is ONE in-place pass in which every rank exchanges with
+        its 2^k - 1 partners at once (kernels.cu group_swap_kernel); otherwise one pairwise exchange per trade."""
+        k = len(trades)
+        if k == 0:
             return
-        victim = self.lookahead(i, keep) if self.lookahead else None
+        use_group = self.group_ok and self.local.ncols == 1 and k <= 4 and self.n_local >= k + 1
+        if not use_group:
+            for gbit, v in trades:
+                self._exchange(gbit, self.where[v][1])
+            return
+        # the traded index bits should be high ones (long contiguous runs on the wire): relabel victims into the
+        # top-k engine qubits first (a zero-byte Swap relabel inside the engine, undone by its next sweep)
+        free_top = [t for t in range(k) if t not in [self.where[v][1] for _, v in trades]]
+        for gbit, v in trades:
+            j = self.where[v][1]
+            if j >= k:
+                t = free_top.pop(0)
+                qt = self._qubit_at(("l", t))
+                self.local.apply_gate(SWAP, [t, j])
+                self.where[qt], self.where[v] = ("l", j), ("l", t)
+        import time
+        t0 = time.perf_counter()
+        self.local.group_remap([gb for gb, _ in trades], [self.where[v][1] for _, v in trades])
+        self.exchange_seconds += time.perf_counter() - t0          # host time only: the remap itself is stream-ordered
+        self.exchanged_bytes += ((1 << k) - 1) * ((16 << self.n_local) >> k)
+        self.exchanges += k
+        self.remaps += 1
+        for gbit, v in trades:
+            qg = self._qubit_at(("g", gbit))
+            self.where[qg], self.where[v] = self.where[v], ("g", gbit)
+
+    def _pick_victim(self, gbit, keep):
+        victim = self.lookahead(gbit, keep) if self.lookahead else None
         if victim is None or self.where[victim][0] != "l" or victim in keep:
             cands = [self._qubit_at(("l", j)) for j in range(self.n_local)]
             victim = [c for c in cands if c not in keep][0]
-        self._exchange(i, self.where[victim][1])
+        return victim
+
+    def _bring_local(self, q, keep=(), also=()):
+        """make logical qubit q (and the global ones among `also`) local; evict local qubits not in `keep`"""
+        todo = [x for x in [q] + list(also) if self.where[x][0] == "g"]
+        if not todo:
+            return
+        keep = list(keep)
+        pairs = []
+        for x in todo:
+            i = self.where[x][1]
+            if self.pin[i] is not None:
+                self._depin(i)
+            victim = self._pick_victim(i, keep + todo)
+            keep.append(victim)
+            pairs.append((i, victim))
+        self._exchange_multi(pairs)
+
+    # ---- pinned rank bits (replicated start) -----------------------------------------
+    def _depin(self, i):
+        """rank bit i stops being a known basis value: the ranks on the wrong side hold nothing"""
+        v = self.pin[i]
+        if v is None:
+            return
+        self.pin[i] = None
+        if self._rank_bit(i) != v:
+            self.local.replace_columns([ZERO_COLUMN] * self.local.ncols, self.local.counts)
+
+    def _depin_all(self):
+        for i in range(self.g):
+            self._depin(i)
+
+    def reset_all(self):
+        """vectorstate.rs:410-415 on the sharded state: back to |0..0> (every rank bit pinned to 0 again)"""
+        self.where = [self._canonical(q) for q in range(self.n)]
+        self.pin = [0 if self.replicate else None] * self.g
+        self._start_tag = "zero"
+        self.local.reset_all()
+        if not self.replicate and self.rank != 0:
+            self.local.replace_columns([ZERO_COLUMN], [self.shots])
+
+    @classmethod
+    def from_qubit_coefs(cls, coefs, nr_shots, **kw):
+        """vectorstate.rs:62-83 on the sharded state: the product state of per-qubit coefficient pairs.  Rank r holds
+        the product over the local qubits times the coefficients its rank bits select -- no rank bit is pinned."""
+        coefs = [complex(c) for c in coefs]
+        n = len(coefs) // 2
+        st = cls(n, nr_shots, **kw)
+        st.pin = [None] * st.g
+        st.local.set_product_state(coefs[2 * st.g:])
+        s = 1.0 + 0.0j
+        for q in range(st.g):
+            a, b = coefs[2 * q], coefs[2 * q + 1]
+            s *= (a, b)[st._rank_bit(st.g - 1 - q)] / math.sqrt(abs(a) ** 2 + abs(b) ** 2)
+        st.local.scale(s)
+        st._start_tag = "product"
+        return st
 
     def canonicalize(self):
         """restore the canonical layout (qubit q < g at rank bit g-1-q, others in index order)"""
+        self._start_tag = None
+        self._depin_all()
+        # the common case -- every misplaced global qubit sits on chip -- is one multi-bit remap
+        trades = [(self.g - 1 - q, q) for q in range(self.g) if self.where[q] != ("g", self.g - 1 - q)]
+        if trades and all(self.where[q][0] == "l" for q in range(self.g) if self.where[q] != ("g", self.g - 1 - q)):
+            self._exchange_multi(trades)
         for q in range(self.g):
             want = ("g", self.g - 1 - q)
             if self.where[q] == want:
@@ -370,6 +581,7 @@ class ShardedState:
     def apply_gate(self, mat, bits, desc="gate"):
         m = mat if isinstance(mat, np.ndarray) and mat.dtype == np.complex128 else np.asarray(mat, dtype=np.complex128)
         k = len(bits)
+        self._start_tag = None
         if m.shape != (1 << k, 1 << k):
             raise ValueError('Expected %d bits for "%s", got %d' % (int(round(math.log2(m.shape[0]))), desc, k))
         is_swap, diag = self._info(m, k)
@@ -379,24 +591,45 @@ class ShardedState:
             return
         glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
         nondiag = [j for j in glob if not diag[j]]
+        if k == 1 and nondiag and self.pin[self.where[bits[0]][1]] is not None:
+            # a one-qubit gate on a rank bit pinned to v: column v of its matrix.  Two non-zero entries: every rank
+            # takes the entry of its own bit as a scalar and the bit is free; one: the bit stays pinned (X, Y)
+            i = self.where[bits[0]][1]
+            col = m[:, self.pin[i]]
+            nz = [b for b in (0, 1) if col[b] != 0]
+            if len(nz) == 2:
+                s_ = col[self._rank_bit(i)]
+                self.pin[i] = None
+            else:
+                s_ = col[nz[0]]
+                self.pin[i] = nz[0]
+            if s_ != 1:
+                self.local.scale(s_)
+            return
         for j in nondiag:
-            self._bring_local(bits[j], keep=[q for q in bits])
+            self._bring_local(bits[j], keep=[q for q in bits], also=self._also_needed(bits[j]))
         glob = [j for j, q in enumerate(bits) if self.where[q][0] == "g"]
         local_m, local_bits = self._localize(m, bits, glob)
         if local_m is not None:
             self.local.apply_gate(local_m, local_bits)
 
+    def _also_needed(self, q):
+        """other global qubits to bring on chip in the same remap (set by run_ops' look-ahead)"""
+        f = getattr(self, "_also_hook", None)
+        return f(q) if f else ()
+
     def _localize(self, m, bits, glob):
         k = len(bits)
         if glob:
-            fixed = {j: self._rank_bit(self.where[bits[j]][1]) for j in glob}
+            fixed = {j: (self.pin[self.where[bits[j]][1]] if self.pin[self.where[bits[j]][1]] is not None
+                         else self._rank_bit(self.where[bits[j]][1])) for j in glob}
             m = select_block(m, k, fixed)
         lbits = [self.where[q][1] for j, q in enumerate(bits) if j not in glob]
         if not lbits:
             s = m[0, 0]
             if s == 1:
                 return None, None
-            return np.array([[s, 0], [0, s]], dtype=np.complex128), [0]      # a rank-dependent scalar
+            return np.array([[s, 0], [0, s]], dtype=np.complex128), [0]      # a rank-dependent scalar (unit modulus: a phase)
         return m, lbits
 
     def apply_unary_gate_all(self, mat, desc="gate"):
@@ -406,6 +639,8 @@ class ShardedState:
     def apply_conditional_gate(self, control, mat, bits, desc="gate"):
         m = np.asarray(mat, dtype=np.complex128)
         k = len(bits)
+        self._start_tag = None
+        self._depin_all()
         if k == 2 and np.array_equal(m, SWAP):
             # a conditional relabel cannot be virtual: run it as three CX on local qubits
             for q in bits:
@@ -619,10 +854,12 @@ class ShardedState:
         remap evict the local qubit whose data is destined for that rank bit (following the
         remaining `Swap` relabels) and that no later gate touches non-diagonally, so the
         final canonicalisation usually needs no further exchange."""
-        key = (id(ops), len(ops))
+        key = (id(ops), len(ops), self.n, self.g)
+        src_ops = ops
         ops = self._expanded_ops(ops)
         cached = getattr(ShardedState, "_plan_cache", {}).get(key)
-        if cached is not None and cached[0] == (self.n, self.g):
+        # the entry keeps the op list alive and is only valid for that very object (an id can be reused)
+        if cached is not None and cached[0] is src_ops:
             _, mats, dest, busy, nxt = cached
             return self._run_planned(ops, gate_matrix, res, rng, mats, dest, busy, nxt)
         mats = []
@@ -661,10 +898,48 @@ class ShardedState:
             dest[t], busy[t], nxt[t] = d, b, x
         if not hasattr(ShardedState, "_plan_cache"):
             ShardedState._plan_cache = {}
-        ShardedState._plan_cache[key] = ((self.n, self.g), mats, dest, busy, nxt)
+        if len(ShardedState._plan_cache) >= 8:
+            ShardedState._plan_cache.pop(next(iter(ShardedState._plan_cache)))       # oldest entry
+        ShardedState._plan_cache[key] = (src_ops, mats, dest, busy, nxt)
         return self._run_planned(ops, gate_matrix, res, rng, mats, dest, busy, nxt)
 
+    _tapes = {}
+
+    def _replay(self, tape):
+        for kind, payload in tape["segments"]:
+            if kind == "g":
+                self.local.apply_packed(payload)
+            elif kind == "s":
+                self.local.scale(payload)
+            else:
+                self.local.group_remap(payload[0], payload[1])
+        self.where = list(tape["where"])
+        self.pin = list(tape["pin"])
+        self.exchanges += tape["exchanges"]
+        self.remaps += tape["remaps"]
+        self.exchanged_bytes += tape["bytes"]
+
     def _run_planned(self, ops, gate_matrix, res, rng, mats, dest, busy, nxt):
+        # the gate-only prefix of an op list run from a known start (fresh |0..0> or product state) is taped once
+        nprefix = 0
+        while nprefix < len(ops) and ops[nprefix][0] == "gate":
+            nprefix += 1
+        start = getattr(self, "_start_tag", None)
+        can_tape = (start is not None and nprefix >= 8 and hasattr(self.local, "apply_packed") and
+                    self.where == [self._canonical(q) for q in range(self.n)])
+        tkey = (id(ops), len(ops), self.n, self.g, self.rank, start, tuple(self.pin))
+        t_from = 0
+        recorder = None
+        if can_tape:
+            tape = ShardedState._tapes.get(tkey)
+            if tape is not None and tape["ops"] is ops:
+                self._replay(tape)
+                t_from = nprefix
+            else:
+                recorder = _Recorder(self.local)
+                counters = (self.exchanges, self.remaps, self.exchanged_bytes)
+                self.local = recorder
+        self._start_tag = None            # whatever runs now, the state is no longer at its start
         state = {"t": 0}
 
         def policy(gbit, keep):
@@ -679,10 +954,45 @@ class ShardedState:
                     best, far = v, nxt[t + 1][v]
             return best
 
+        INF = 1 << 60
+
+        def also(q):
+            # the other global qubits a later gate needs on chip: they ride along in the same multi-bit remap
+            t = state["t"]
+            return [v for v in range(self.n) if v != q and self.where[v][0] == "g" and self.pin[self.where[v][1]] is None
+                    and nxt[t + 1][v] < INF]
+
+        def finish_recording(rec):
+            self.local = rec.local
+            if not rec.valid:
+                return
+            segs, run = [], []
+            for e in rec.tape:
+                if e[0] == "g":
+                    run.append((e[1], e[2]))
+                    continue
+                if run:
+                    segs.append(("g", self.local.pack_gates(run)))
+                    run = []
+                segs.append(("s", e[1]) if e[0] == "s" else ("r", (e[1], e[2])))
+            if run:
+                segs.append(("g", self.local.pack_gates(run)))
+            if len(ShardedState._tapes) >= 8:
+                ShardedState._tapes.pop(next(iter(ShardedState._tapes)))
+            ShardedState._tapes[tkey] = {"ops": ops, "segments": segs, "where": list(self.where), "pin": list(self.pin),
+                                         "exchanges": self.exchanges - counters[0], "remaps": self.remaps - counters[1],
+                                         "bytes": self.exchanged_bytes - counters[2]}
+
         old = self.lookahead
         self.lookahead = policy
+        self._also_hook = also if self.group_ok else None
         try:
             for t, op in enumerate(ops):
+                if t < t_from:
+                    continue
+                if recorder is not None and t == nprefix:
+                    finish_recording(recorder)
+                    recorder = None
                 state["t"] = t
                 k = op[0]
                 if k == "gate":
@@ -704,8 +1014,14 @@ class ShardedState:
                     pass
                 else:
                     raise NotImplementedError("run_ops: %r" % (op,))
+            if recorder is not None:
+                finish_recording(recorder)
+                recorder = None
         finally:
             self.lookahead = old
+            self._also_hook = None
+            if recorder is not None:
+                self.local = recorder.local
 
     # ---- read-out (tests) ----------------------------------------------------------
     @property

@@ -147,6 +147,59 @@ class NumpyLocal:
     def binomial(self, rng, n, p):
         return rng.binomial(n, p)
 
+    # peer-group emulation (the CUDA engine swaps in place over NVLink peer memory; here every rank gathers all
+    # shards and picks what the multi-bit remap brings it): lets the gloo tests cover ShardedState._exchange_multi
+    def group_setup(self, dist, group, rank, P):
+        self._dist, self._group, self._rank, self._P = dist, group, rank, P
+
+    def group_remap(self, rank_bits, local_qubits):
+        import torch
+        n, r = self.n_local, self._rank
+        l = np.arange(1 << n, dtype=np.int64)
+        src_rank = np.full_like(l, r)
+        src_idx = l.copy()
+        for gb, q in zip(rank_bits, local_qubits):
+            p = n - 1 - q
+            lb = (l >> p) & 1                                     # the element now at (r, l) came from rank bit := l_p, index bit := r_gb
+            src_rank = (src_rank & ~(1 << gb)) | (lb << gb)
+            src_idx = (src_idx & ~(1 << p)) | (((r >> gb) & 1) << p)
+        out = []
+        for c in self.cols:
+            t = torch.from_numpy(np.ascontiguousarray(c).view(np.float64).copy())
+            parts = [torch.empty_like(t) for _ in range(self._P)]
+            self._dist.all_gather(parts, t, group=self._group)
+            allc = np.stack([p_.numpy().view(np.complex128) for p_ in parts])
+            out.append(allc[src_rank, src_idx])
+        self.cols = out
+
+    def pack_gates(self, gates):
+        return [(np.array(m), list(b)) for m, b in gates]
+
+    def apply_packed(self, packed):
+        self.replayed = getattr(self, "replayed", 0) + len(packed)
+        for m, b in packed:
+            self.apply_gate(m, b)
+
+    def scale(self, s):
+        self.cols = [c * complex(s) for c in self.cols]
+
+    def reset_all(self):
+        col = np.zeros(1 << self.n_local, dtype=np.complex128)
+        col[0] = 1.0
+        self.cols, self._counts = [col], [self.shots]
+
+    def set_product_state(self, coefs):
+        self.cols = [O.OracleState.from_qubit_coefs(list(coefs), 1).column(0)]
+        self._counts = [self.shots]
+
 
 def factory(n_local, shots, device, empty):
+    return NumpyLocalNoGroup(n_local, shots, device, empty)
+
+
+class NumpyLocalNoGroup(NumpyLocal):
+    group_setup = None
+
+
+def factory_group(n_local, shots, device, empty):
     return NumpyLocal(n_local, shots, device, empty)

@@ -1,5 +1,11 @@
-"""Multi-GPU parity (needs >= 2 CUDA devices; run with `gpurun --gpus 2 -- python -m pytest
-tests/test_gpu_sharded.py -m gpu`): the sharded engine over NCCL against the oracle."""
+"""Parity of the sharded engine (one process per shard) against the oracle.
+
+* `test_sharded_engine_vs_oracle`: one process per GPU over NCCL (needs >= 2 CUDA devices:
+  `gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`).
+* `test_sharded_engine_on_one_gpu`: the SAME code path -- CUDA IPC peer mappings, mailbox barriers, the in-place
+  multi-bit remap kernel, replicated start -- with 2, 4 and 8 processes that all use device 0 (gloo carries the few
+  host-side messages; the GPU time-slices between the processes), so a 1-GPU box exercises every CUDA kernel of the
+  multi-GPU path."""
 import os
 import socket
 import sys
@@ -90,8 +96,108 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
+def _worker_one_gpu(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from q1tsim_b200 import engine as E
+        from q1tsim_b200 import sharded as S
+        from q1tsim_b200 import workloads as W
+        shots = 500
+        G = O.gate_matrix
+        out = {"rank": rank}
+        O.lib().orc_set_threads(2)
+        ops = W.qft_ops(n, measure=False)
+        cb = list(range(n))
+        # (a) QFT from |0..0>, twice through reset_all: replicated start (no exchange for the gates), one multi-bit
+        #     remap for the canonical layout, sampling bit-exact on identical amplitudes
+        st = S.ShardedState(n, shots, device=0)
+        out["group_ok"] = bool(st.group_ok)
+        for rep in range(2):
+            if rep:
+                st.reset_all()
+            st.run_ops(ops, G)
+            ref = O.OracleState(n, shots, mode=1, order=1)
+            for op in ops:
+                ref.apply_gate(G(op[1], op[2]), op[3])
+            full = st.gather_column(0)
+            out["qft_rel_l2_%d" % rep] = float(np.linalg.norm(full - ref.column(0)) / np.linalg.norm(ref.column(0)))
+            out["remaps_%d" % rep] = st.remaps
+            st.remaps = 0
+        # (b) dense input: product state, QFT with the look-ahead remap planner, against the oracle and the closed form
+        coefs = W.product_state_coefs(n, seed=7)
+        sp = S.ShardedState.from_qubit_coefs(coefs, shots, device=0)
+        rp = O.OracleState.from_qubit_coefs(coefs, shots)
+        sp.run_ops(ops, G)
+        for op in ops:
+            rp.apply_gate(G(op[1], op[2]), op[3])
+        full = sp.gather_column(0)
+        out["product_rel_l2"] = float(np.linalg.norm(full - rp.column(0)) / np.linalg.norm(rp.column(0)))
+        out["product_closed_form"] = float(np.linalg.norm(full - W.qft_of_product_state(n, coefs, np.arange(1 << n))))
+        out["remaps_product"] = sp.remaps
+        # (c) identical amplitudes on both sides -> bit-exact outcomes through the rank-ordered canonical chain
+        psi = rp.column(0)
+        nl = 1 << sp.n_local
+        sp.local.write_column(0, psi[rank * nl:(rank + 1) * nl])
+        words = O.splitmix64_words(33, 4 * shots + 64)
+        rng_s, rng_o = E.Rng(words=words), O.Rng(words=words)
+        rs_, ro = np.zeros(shots, dtype=np.uint64), np.zeros(shots, dtype=np.uint64)
+        sp.measure_into(0, 40, rs_, rng_s); rp.measure_into(0, 40, ro, rng_o)
+        sp.measure_all_into(cb, rs_, rng_s); rp.measure_all_into(cb, ro, rng_o)
+        out["measure_equal"] = bool(np.array_equal(rs_, ro))
+        # (d) random gates on every qubit incl. pinned and unpinned global ones
+        st.reset_all()
+        ref = O.OracleState(n, shots, mode=1, order=1)
+        rs = np.random.default_rng(11)
+        names = [("h", 0), ("x", 0), ("u3", 3), ("cx", 0), ("cu1", 1), ("cs", 0), ("swap", 0), ("rz", 1), ("ccx", 0), ("y", 0), ("t", 0), ("cz", 0)]
+        for rep in range(30):
+            name, npar = names[rep % len(names)]
+            m = G(name, list(rs.uniform(-2, 2, size=npar)))
+            k = int(np.log2(m.shape[0]))
+            bits = [int(b) for b in rs.permutation(n)[:k]]
+            st.apply_gate(m, bits, name); ref.apply_gate(m, bits)
+        out["gates_rel_l2"] = float(np.linalg.norm(st.gather_column(0) - ref.column(0)) / np.linalg.norm(ref.column(0)))
+        dist.barrier()
+        st.local.group_close(); sp.local.group_close()
+        dist.barrier()
+        q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 16), (4, 17), (8, 18)])
+def test_sharded_engine_on_one_gpu(world, n):
+    import torch.multiprocessing as mp
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_one_gpu, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for o in outs:
+        assert o["group_ok"]
+        assert o["qft_rel_l2_0"] < 1e-10 and o["qft_rel_l2_1"] < 1e-10
+        assert o["remaps_0"] == 1 and o["remaps_1"] == 1          # one multi-bit remap, none for the gates
+        assert o["product_rel_l2"] < 1e-10 and o["product_closed_form"] < 1e-10
+        assert o["remaps_product"] <= 2
+        assert o["measure_equal"]
+        assert o["gates_rel_l2"] < 1e-10
+
+
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("world,n", [(2, 16), (2, 21)])
+@pytest.mark.parametrize("world,n", [(2, 16), (2, 21), (4, 20), (8, 21)])
 def test_sharded_engine_vs_oracle(world, n):
     import torch.multiprocessing as mp
     if _ngpu() < world:

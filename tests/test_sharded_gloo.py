@@ -114,6 +114,47 @@ def _worker(rank, world, port, n, case, q):
             oc.execute(shots, rng_o)
             out["cstate_equal"] = bool(np.array_equal(cs, oc.c_state))
             out["consumed"] = (rng_s.consumed, rng_o.consumed)
+        elif case.startswith("replicated"):
+            # replicated start + multi-bit remap (numpy peer-group emulation) + reuse through reset_all: QFT from
+            # |0..0> needs no exchange for its gates; the canonical layout comes back in ONE remap
+            group = case.endswith("group")
+            st = S.ShardedState(n, shots, local_factory=numpy_local.factory if not group else numpy_local.factory_group)
+            ops = W.qft_ops(n, measure=False)
+            for rep in range(2):
+                if rep:
+                    st.reset_all()
+                ref = O.OracleState(n, shots, mode=1, order=1)
+                st.run_ops(ops, G)
+                for op in ops:
+                    ref.apply_gate(G(op[1], op[2]), op[3])
+                out["exchanges_gates_%d" % rep] = st.exchanges
+                out["amp_err_%d" % rep] = float(np.linalg.norm(st.gather_column(0) - ref.column(0)))
+                out["remaps_%d" % rep] = st.remaps
+                out["replayed_%d" % rep] = getattr(st.local, "replayed", 0)
+                st.exchanges = st.remaps = 0
+            # gates on pinned rank bits: X / Y keep the pin, a controlled gate with a pinned target forces the depin
+            st.reset_all()
+            ref = O.OracleState(n, shots, mode=1, order=1)
+            for name, params, bits in (("x", (), [0]), ("h", (), [n - 1]), ("cx", (), [0, n - 2]), ("y", (), [1]), ("u3", (0.3, 0.2, 0.1), [0]),
+                                       ("cz", (), [0, 1]), ("cx", (), [n - 1, 1]), ("h", (), [1]), ("swap", (), [0, n - 3]), ("ry", (0.7,), [0])):
+                both(name, params, bits)
+            out["amp_err_pins"] = float(np.linalg.norm(st.gather_column(0) - ref.column(0)))
+            # dense product-state input (from_qubit_coefs): nothing is pinned, the global H gates need their remap
+            coefs = W.product_state_coefs(n, seed=3)
+            sp = S.ShardedState.from_qubit_coefs(coefs, shots, local_factory=numpy_local.factory if not group else numpy_local.factory_group)
+            rp = O.OracleState.from_qubit_coefs(coefs, shots)
+            sp.run_ops(ops, G)
+            for op in ops:
+                rp.apply_gate(G(op[1], op[2]), op[3])
+            out["amp_err_product"] = float(np.linalg.norm(sp.gather_column(0) - rp.column(0)))
+            out["remaps_product"] = sp.remaps
+            cb = list(range(n))
+            rs_, ro = np.zeros(shots, dtype=np.uint64), np.zeros(shots, dtype=np.uint64)
+            psi = rp.column(0)
+            nl = 1 << sp.n_local
+            sp.local.write_column(0, psi[rank * nl:(rank + 1) * nl])
+            sp.measure_all_into(cb, rs_, rng_s); rp.measure_all_into(cb, ro, rng_o)
+            out["measure_equal"] = bool(np.array_equal(rs_, ro))
         q.put(out)
     finally:
         dist.destroy_process_group()
@@ -167,3 +208,20 @@ def test_sharded_run_ops_basis_changes_and_reset(world, n):
     for o in _run(world, n, "run_ops_basis"):
         assert o["cstate_equal"]
         assert o["consumed"][0] == o["consumed"][1]
+
+
+@pytest.mark.parametrize("world,n,case", [(2, 12, "replicated"), (4, 13, "replicated"), (2, 12, "replicated_group"), (4, 13, "replicated_group"),
+                                          (8, 14, "replicated_group")])
+def test_sharded_replicated_start_and_multi_bit_remap(world, n, case):
+    g = int(np.log2(world))
+    for o in _run(world, n, case):
+        for rep in (0, 1):
+            assert o["amp_err_%d" % rep] < 1e-12
+            # no exchange for the gates of a QFT from |0..0>: only the canonical layout at read-out costs remaps --
+            # one multi-bit remap with a peer group, g pairwise exchanges without
+            assert o["remaps_%d" % rep] == (1 if case.endswith("group") else g)
+        assert o["replayed_0"] == 0 and o["replayed_1"] > 0         # the second run of the op list replays the taped schedule
+        assert o["amp_err_pins"] < 1e-12
+        assert o["amp_err_product"] < 1e-12
+        assert o["remaps_product"] <= (2 if case.endswith("group") else 3 * g)
+        assert o["measure_equal"]
