@@ -154,6 +154,13 @@ int    q1t_peer_swap(q1t_state *st, size_t col, const unsigned char *peer_handle
  * barrier over the group; q1t_group_remap enqueues barrier + swap + barrier: rank bit rank_bits[j] and local
  * qubit local_qubits[j] (j < k <= 4) trade places in one in-place pass, every rank exchanging with its 2^k - 1
  * partners at once.  All ranks must make the same calls in the same order. */
+/* Shards of >= 2^20 amplitudes: q1t_block_totals leaves the canonical leaf totals and their in-block inclusive
+ * prefixes on the device and returns only the block totals (nr_columns x nr_leaves/1024 doubles; qbit as for
+ * q1t_leaf_totals); the host continues the chain over blocks in rank order and hands every column's slice back to
+ * q1t_resolve_draws_blocks: block_prefix[0] = weight in front of this shard, block_prefix[b + 1] = global inclusive
+ * prefix through this shard's block b.  Same fixed geometry as the single-GPU scan. */
+int    q1t_block_totals(q1t_state *st, size_t qbit, double *out);
+int    q1t_resolve_draws_blocks(q1t_state *st, size_t col, const double *block_prefix, const double *chosen, size_t nd, uint64_t *idx);
 /* every column times the scalar re + i*im (a rank's share of a one-qubit gate on a rank bit that is still
  * pinned to a basis value); real factors are deferred into the next fused sweep like the Hadamard normalisations */
 int    q1t_scale(q1t_state *st, double re, double im);
@@ -185,6 +192,8 @@ typedef struct {
     uint64_t peer_swap_bytes;     /* bytes this rank moved over NVLink in q1t_peer_swap (remote reads + remote writes) */
     uint64_t plan_cache_hits;     /* gate batches whose sweep plan came from the process-wide plan cache */
     uint64_t tma_sweeps;          /* sweeps whose tiles were loaded by TMA (cp.async.bulk.tensor), dense ladder sweeps */
+    uint64_t h2d_bytes;           /* bytes copied host -> device by this state (programs, tables, draws, amplitudes written) */
+    uint64_t d2h_bytes;           /* bytes copied device -> host (totals, sampled indices, amplitudes read) */
 } q1t_stats;
 int q1t_get_stats(q1t_state *st, q1t_stats *out);
 int q1t_reset_stats(q1t_state *st);

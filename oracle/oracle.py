@@ -20,7 +20,7 @@ _LIB_PATH = os.path.join(_HERE, "libq1t_oracle.so")
 
 ORC_ERRORS = {
     -1: "InvalidNrBits", -2: "InvalidQBit", -3: "NotEnoughSpace",
-    -4: "InvalidNrMeasurementBits", -5: "InvalidNrControlBits", -6: "RngExhausted",
+    -4: "InvalidNrMeasurementBits", -5: "InvalidNrControlBits", -6: "RngExhausted", -7: "OutOfHostMemory",
 }
 
 
@@ -32,8 +32,8 @@ class OracleError(Exception):
 
 
 def build(force=False):
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    # make decides: the library is rebuilt whenever q1t_oracle.c / .h are newer
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
 
 class _Rng(C.Structure):

@@ -852,8 +852,11 @@ int orc_measure_all_into(orc_state *s, const size_t *cbits, size_t ncbits, uint6
         off += sc_cnt[g];
     }
     if (collapse) {
+        /* vectorstate.rs:150-158 builds a dense (2^n, n_distinct) matrix: 16 B * 2^n * n_distinct, which the host may refuse */
+        orc_cplx *ns = calloc(N * (nsc ? nsc : 1), sizeof(orc_cplx));
+        if (!ns) { free(sc_idx); free(sc_cnt); return ORC_ERR_OUT_OF_MEMORY; }
         free(s->states); free(s->counts);
-        s->states = calloc(N * (nsc ? nsc : 1), sizeof(orc_cplx));
+        s->states = ns;
         s->counts = malloc((nsc ? nsc : 1) * sizeof(size_t));
         for (size_t g = 0; g < nsc; g++) { s->states[sc_idx[g] * nsc + g].re = 1.0; s->counts[g] = sc_cnt[g]; }
         s->ncols = nsc;

@@ -106,6 +106,7 @@ int orc_gate_matrix(const char *name, const double *params, size_t nparams, doub
 #define ORC_ERR_INVALID_NR_MEASUREMENT_BITS (-4)
 #define ORC_ERR_INVALID_NR_CONTROL_BITS (-5)
 #define ORC_ERR_RNG_EXHAUSTED (-6)
+#define ORC_ERR_OUT_OF_MEMORY (-7)     /* the reference's dense collapse matrix (vectorstate.rs:150-158) does not fit into host memory */
 
 #ifdef __cplusplus
 }

@@ -166,6 +166,12 @@ int q1t_replace_columns(q1t_state *st, size_t ncols, const uint64_t *idx, const 
 }
 int q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr) { ST_OR_FAIL; return st->impl->column_ptr(col, ptr); }
 int q1t_ipc_export(q1t_state *st, size_t col, unsigned char *handle64) { ST_OR_FAIL; return st->impl->ipc_export(col, handle64); }
+int q1t_block_totals(q1t_state *st, size_t qbit, double *out) { ST_OR_FAIL; return st->impl->block_totals(qbit, out); }
+int q1t_resolve_draws_blocks(q1t_state *st, size_t col, const double *block_prefix, const double *chosen, size_t nd, uint64_t *idx)
+{
+    ST_OR_FAIL;
+    return st->impl->resolve_draws_blocks(col, block_prefix, chosen, nd, idx);
+}
 int q1t_set_product_state(q1t_state *st, const double *coefs)
 {
     ST_OR_FAIL;

@@ -23,6 +23,16 @@ namespace q1t {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// every host<->device copy of the engine goes through here: q1t_stats::h2d_bytes / d2h_bytes are what bench.py reports
+// as the end-to-end transfer volume
+#define cudaMemcpyAsync(dst, src, nbytes, kind, stream) counted_copy(stats, dst, src, nbytes, kind, stream)
+static inline cudaError_t counted_copy(q1t_stats &st, void *dst, const void *src, size_t nbytes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    if (kind == cudaMemcpyHostToDevice) st.h2d_bytes += nbytes;
+    else if (kind == cudaMemcpyDeviceToHost) st.d2h_bytes += nbytes;
+    return (cudaMemcpyAsync)(dst, src, nbytes, kind, stream);
+}
+
 // ---------------------------------------------------------------------------
 // process-wide cache of column buffers: execute() builds a fresh state every
 // call (circuit.rs:594-600), so without a cache every call would pay
@@ -564,7 +574,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
                 } else hcols.clear();
             }
             time_begin();
-            CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_, nullptr,
+            stats.h2d_bytes += sizeof(SweepProgram); CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_, nullptr,
                             hcols.empty() ? nullptr : hcols.data()));
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
@@ -593,7 +603,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
             time_begin();
             const double2 *hsrc = col.buf;
-            CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, d_gen_ ? d_gen_ + i : nullptr, stream_,
+            stats.h2d_bytes += sizeof(SweepProgram); CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, d_gen_ ? d_gen_ + i : nullptr, stream_,
                             ps.prog.leaf_fuse ? d_leaf_ + (i << (n_ - kCanonLeafBits)) : nullptr, tma_here ? &hsrc : nullptr));
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
@@ -787,7 +797,7 @@ int DeviceVectorState::canonicalize()
                 // d_pair_ is rewritten per launch: stream order keeps the previous launch's copy intact until it has run
                 CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
                 time_begin();
-                CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, nullptr, stream_));
+                stats.h2d_bytes += sizeof(SweepProgram); CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, nullptr, stream_));
                 time_end(stats.sweep_ms);
                 stats.kernel_launches++;
                 stats.sweeps++;
@@ -812,7 +822,7 @@ int DeviceVectorState::canonicalize()
         double2 *h[2] = { col.buf, scratch };
         CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
         time_begin();
-        CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, nullptr, stream_));
+        stats.h2d_bytes += sizeof(SweepProgram); CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_, nullptr, stream_));
         time_end(stats.sweep_ms);
         stats.kernel_launches++;
         stats.sweeps++;
@@ -1212,6 +1222,62 @@ int DeviceVectorState::leaf_totals(size_t qbit, double *out)
     stats.kernel_launches++;
     stats.read_passes += all.size();
     CK(cudaMemcpyAsync(out, d_leaf_, sizeof(double) * all.size() * nr_leaves(), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// canonical block totals of every column (shards of >= 2^20 amplitudes): leaf totals and the in-block inclusive
+// prefixes stay on the device for resolve_draws_blocks(); only ncols * nblocks doubles cross to the host, which
+// continues the chain over blocks in rank order
+int DeviceVectorState::block_totals(size_t qbit, double *out)
+{
+    if (nr_leaves() < kCanonBlock) return fail(Q1T_ERR_UNSUPPORTED, "block_totals: shards below 2^20 amplitudes chain their leaves on the host");
+    int rc = flush_async();
+    if (rc) return rc;
+    for (Column &c : cols_) {
+        rc = materialize(c);
+        if (rc) return rc;
+    }
+    std::vector<int> all;
+    for (size_t c = 0; c < cols_.size(); ++c) all.push_back((int)c);
+    rc = ensure_scratch(all.size());
+    if (rc) return rc;
+    rc = upload_colptrs(all);
+    if (rc) return rc;
+    const uint64_t mask = qbit < (size_t)n_ ? 1ull << (n_ - 1 - (int)qbit) : 0ull;
+    const size_t nb = nr_leaves() / kCanonBlock;
+    time_begin();
+    CK(launch_leaf_totals(d_colptrs_, (int)all.size(), d_leaf_, n_, mask, 0, stream_));
+    CK(launch_block_scan(d_leaf_, d_block_, (int)all.size(), n_, stream_));
+    time_end(stats.read_ms);
+    stats.kernel_launches += 2;
+    stats.read_passes += all.size();
+    CK(cudaMemcpyAsync(out, d_block_, sizeof(double) * all.size() * nb, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return Q1T_OK;
+}
+
+// resolve sorted draws of column `col` after block_totals(): bp[0] = weight in front of this shard, bp[b + 1] = global
+// inclusive prefix through this shard's block b
+int DeviceVectorState::resolve_draws_blocks(size_t col, const double *bp, const double *chosen, size_t nd, uint64_t *idx)
+{
+    if (col >= cols_.size() || !bp) return fail(Q1T_ERR_INVALID_ARGUMENT, "column out of range");
+    if (nd == 0) return Q1T_OK;
+    const size_t nl = nr_leaves(), nb = nl / kCanonBlock;
+    if (nd > draws_cap_) {
+        CK(cudaStreamSynchronize(stream_));
+        scratch_free(device_, d_chosen_, sizeof(double) * draws_cap_);
+        scratch_free(device_, d_idx_, sizeof(uint64_t) * draws_cap_);
+        draws_cap_ = nd;
+        CK(scratch_alloc(device_, (void **)&d_chosen_, sizeof(double) * draws_cap_));
+        CK(scratch_alloc(device_, (void **)&d_idx_, sizeof(uint64_t) * draws_cap_));
+    }
+    CK(cudaMemcpyAsync(d_block_ + col * nb, bp + 1, sizeof(double) * nb, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(d_chosen_, chosen, sizeof(double) * nd, cudaMemcpyHostToDevice, stream_));
+    CK(launch_resolve_draws(cols_[col].buf, d_leaf_ + col * nl, d_block_ + col * nb, n_, d_chosen_, nd,
+                            reinterpret_cast<unsigned long long *>(d_idx_), bp[0], stream_, bp[0]));
+    stats.kernel_launches++;
+    CK(cudaMemcpyAsync(idx, d_idx_, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     return Q1T_OK;
 }

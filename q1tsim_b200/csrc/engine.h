@@ -45,6 +45,8 @@ public:
     size_t nr_leaves() const;
     int leaf_totals(size_t qbit, double *out);
     int resolve_draws(size_t col, const double *P, double base, const double *chosen, size_t nd, uint64_t *idx);
+    int block_totals(size_t qbit, double *out);
+    int resolve_draws_blocks(size_t col, const double *bp, const double *chosen, size_t nd, uint64_t *idx);
     int scale_split_columns(const double *f0, const double *f1, const size_t *n0s);
     int collapse_columns(size_t qbit, const double *w0s, const size_t *n0s);
     int replace_columns(size_t ncols, const uint64_t *idx, const size_t *counts);

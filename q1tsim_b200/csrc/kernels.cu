@@ -1398,11 +1398,13 @@ __global__ void top_chain_kernel(double *__restrict__ block_io, unsigned long lo
     totals_out[c] = run;
 }
 
+// base0: weight in front of this column's first block (0 for a whole state -- x + 0.0 is x --, the weight of the
+// lower ranks for a shard whose block prefixes bpref continue the global chain)
 __device__ __forceinline__ double leaf_prefix(const double *__restrict__ inblock, const double *__restrict__ bpref,
-                                              unsigned long long L)
+                                              unsigned long long L, double base0)
 {
     const unsigned long long b = L / kCanonBlock;
-    return __dadd_rn(b ? bpref[b - 1] : 0.0, inblock[L]);
+    return __dadd_rn(b ? bpref[b - 1] : base0, inblock[L]);
 }
 
 // one thread per draw (draws sorted ascending on the host): leaf by binary
@@ -1410,7 +1412,7 @@ __device__ __forceinline__ double leaf_prefix(const double *__restrict__ inblock
 __global__ void resolve_draws_kernel(const double2 *__restrict__ st, const double *__restrict__ inblock,
                                      const double *__restrict__ bpref, int n, int leaf_bits,
                                      const double *__restrict__ chosen, unsigned long long ndraws,
-                                     unsigned long long *__restrict__ idx_out, double base)
+                                     unsigned long long *__restrict__ idx_out, double base, double base0)
 {
     const unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (j >= ndraws) return;
@@ -1419,9 +1421,9 @@ __global__ void resolve_draws_kernel(const double2 *__restrict__ st, const doubl
     unsigned long long lo = 0, hi = nleaves - 1;
     while (lo < hi) {
         const unsigned long long mid = (lo + hi) >> 1;
-        if (leaf_prefix(inblock, bpref, mid) <= ch) lo = mid + 1; else hi = mid;
+        if (leaf_prefix(inblock, bpref, mid, base0) <= ch) lo = mid + 1; else hi = mid;
     }
-    double run = lo == 0 ? base : leaf_prefix(inblock, bpref, lo - 1);   // base: weight before this shard
+    double run = lo == 0 ? base : leaf_prefix(inblock, bpref, lo - 1, base0);   // base: weight before this shard
     const unsigned leaf = 1u << leaf_bits;
     const double2 *__restrict__ p = st + (lo << leaf_bits);
     unsigned found = 0xffffffffu, last_nz = 0xffffffffu;
@@ -1454,6 +1456,16 @@ cudaError_t launch_leaf_totals(const double2 *const *d_cols, int ncols, double *
     return cudaGetLastError();
 }
 
+// in-block inclusive prefixes (in place) and the raw block totals only: the chain over blocks continues on other ranks
+cudaError_t launch_block_scan(double *d_leaf, double *d_block, int ncols, int n, cudaStream_t stream)
+{
+    const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
+    const unsigned long long nleaves = 1ull << (n - leaf_bits);
+    const unsigned long long nblocks = (nleaves + kCanonBlock - 1) / kCanonBlock;
+    block_scan_kernel<<<dim3((unsigned)((nblocks + 3) / 4), ncols), 128, 0, stream>>>(d_leaf, d_block, nleaves, nblocks);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int ncols, int n, cudaStream_t stream)
 {
     const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
@@ -1468,12 +1480,12 @@ cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int n
 
 cudaError_t launch_resolve_draws(const double2 *d_col, const double *d_leaf, const double *d_block, int n,
                                  const double *d_chosen, unsigned long long ndraws, unsigned long long *d_idx,
-                                 double base, cudaStream_t stream)
+                                 double base, cudaStream_t stream, double base0)
 {
     if (ndraws == 0) return cudaSuccess;
     const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
     resolve_draws_kernel<<<(unsigned)((ndraws + 63) / 64), 64, 0, stream>>>(d_col, d_leaf, d_block, n, leaf_bits, d_chosen,
-                                                                         ndraws, d_idx, base);
+                                                                         ndraws, d_idx, base, base0);
     return cudaGetLastError();
 }
 

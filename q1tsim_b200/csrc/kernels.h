@@ -35,9 +35,10 @@ cudaError_t launch_generic_gate(double2 *const *d_cols, int ncols, int n, int k,
 cudaError_t launch_leaf_totals(const double2 *const *d_cols, int ncols, double *d_leaf, int n,
                                unsigned long long mask, unsigned long long want, cudaStream_t stream);
 cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int ncols, int n, cudaStream_t stream);
+cudaError_t launch_block_scan(double *d_leaf, double *d_block, int ncols, int n, cudaStream_t stream);
 cudaError_t launch_resolve_draws(const double2 *d_col, const double *d_leaf, const double *d_block, int n,
                                  const double *d_chosen, unsigned long long ndraws, unsigned long long *d_idx,
-                                 double base, cudaStream_t stream);
+                                 double base, cudaStream_t stream, double base0 = 0.0);
 cudaError_t launch_scale2(const double2 *d_in, double2 *d_out0, double2 *d_out1, int n, double f0, double f1, cudaStream_t stream);
 cudaError_t launch_collapse(const double2 *d_in, double2 *d_out0, double2 *d_out1, int n, int bitpos, double f0,
                             double f1, cudaStream_t stream);

@@ -113,6 +113,30 @@ class EngineLocal:
                                               idx.ctypes.data_as(C.POINTER(C.c_uint64))))
         return idx[:chosen.size]
 
+    def block_totals(self, qubit):
+        """(ncols, nleaves / 1024) canonical block totals; leaf totals and in-block prefixes stay on the device"""
+        C = self.C
+        nb = self.nleaves // BLOCK
+        out = np.zeros(self.ncols * nb, dtype=np.float64)
+        q = (1 << 64) - 1 if qubit is None else qubit
+        self.L.q1t_block_totals.restype = C.c_int
+        self.L.q1t_block_totals.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]
+        self.st._chk(self.L.q1t_block_totals(self.st._p, q, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.reshape(self.ncols, nb)
+
+    def resolve_draws_blocks(self, col, bp, chosen):
+        C = self.C
+        bp = np.ascontiguousarray(bp, dtype=np.float64)
+        chosen = np.ascontiguousarray(chosen, dtype=np.float64)
+        idx = np.zeros(max(chosen.size, 1), dtype=np.uint64)
+        self.L.q1t_resolve_draws_blocks.restype = C.c_int
+        self.L.q1t_resolve_draws_blocks.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_size_t,
+                                                    C.POINTER(C.c_uint64)]
+        self.st._chk(self.L.q1t_resolve_draws_blocks(self.st._p, col, bp.ctypes.data_as(C.POINTER(C.c_double)),
+                                                     chosen.ctypes.data_as(C.POINTER(C.c_double)), chosen.size,
+                                                     idx.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return idx[:chosen.size]
+
     def collapse_columns(self, qubit, w0, n0):
         C = self.C
         w0 = np.ascontiguousarray(w0, dtype=np.float64)
@@ -697,21 +721,44 @@ class ShardedState:
             ends = Pg[:, nl - 1::nl]
         return Pl, base, np.ascontiguousarray(ends)
 
+    def _on_device_blocks(self):
+        """shards of >= 2^20 amplitudes on the CUDA engine: the leaf level stays on the device"""
+        return self.local.nleaves >= BLOCK and hasattr(self.local, "block_totals")
+
+    def _global_block_prefix(self, btot):
+        """btot: (ncols, nb) block totals of this rank.  Returns (bp, ends): bp[c] = [weight in front of this rank,
+        global inclusive prefixes through this rank's blocks], ends = last prefix of every rank -- the chain over blocks
+        of DESIGN.md 4.2 continued in rank order"""
+        ncols, nb = btot.shape
+        allb = np.concatenate(self._gather(btot), axis=1)                     # (ncols, P * nb) in rank order
+        bpre = np.cumsum(allb, axis=1)
+        first = self.rank * nb
+        front = bpre[:, first - 1] if first else np.zeros(ncols)
+        bp = np.concatenate([front[:, None], bpre[:, first:first + nb]], axis=1)
+        return np.ascontiguousarray(bp), np.ascontiguousarray(bpre[:, nb - 1::nb])
+
+    def _ends(self, qubit_local, zero=False):
+        """last canonical prefix of every rank, per column: (ncols, P)"""
+        if self._on_device_blocks():
+            nb = self.local.nleaves // BLOCK
+            btot = np.zeros((self.local.ncols, nb)) if zero else self.local.block_totals(qubit_local)
+            return self._global_block_prefix(btot)[1]
+        leaf = np.zeros((self.local.ncols, self.local.nleaves)) if zero else self.local.leaf_totals(qubit_local)
+        return self._global_prefix(leaf)[2]
+
     def marginal0(self, qbit):
         """w0 per column in the canonical order (vectorstate.rs:252-261)"""
         self.canonicalize()
         kind, i = self.where[qbit]
         if kind == "l":
-            leaf = self.local.leaf_totals(i)
+            ends = self._ends(i)
         else:
-            leaf = self.local.leaf_totals(None) if self._rank_bit(i) == 0 else np.zeros((self.local.ncols, self.local.nleaves))
-        _, _, ends = self._global_prefix(leaf)
+            ends = self._ends(None, zero=self._rank_bit(i) != 0)
         return ends[:, -1].copy()
 
     def column_totals(self):
         self.canonicalize()
-        _, _, ends = self._global_prefix(self.local.leaf_totals(None))
-        return ends[:, -1].copy()
+        return self._ends(None)[:, -1].copy()
 
     # ---- measurement ---------------------------------------------------------------
     def _measure(self, qbit, cbit, res, rng, collapse):
@@ -756,7 +803,11 @@ class ShardedState:
         if len(cbits) != self.n:
             raise ValueError("Expected %d measurement bits, but got %d" % (self.n, len(cbits)))
         self.canonicalize()
-        Pl, base, ends = self._global_prefix(self.local.leaf_totals(None))
+        blocks = self._on_device_blocks()
+        if blocks:
+            bp, ends = self._global_block_prefix(self.local.block_totals(None))
+        else:
+            Pl, base, ends = self._global_prefix(self.local.leaf_totals(None))
         counts = self.local.counts
         groups = []                                   # (global basis index, multiplicity) per column, ascending
         for c, cnt in enumerate(counts):
@@ -765,7 +816,8 @@ class ShardedState:
             # owner rank of a draw: number of rank-end prefixes (all but the last) that are <= chosen
             owner = np.searchsorted(ends[c, :-1], chosen, side="right")
             mine = chosen[owner == self.rank]
-            idx = self.local.resolve_draws(c, Pl[c], base[c], mine).astype(np.uint64) | (np.uint64(self.rank) << np.uint64(self.n_local))
+            idx = self.local.resolve_draws_blocks(c, bp[c], mine) if blocks else self.local.resolve_draws(c, Pl[c], base[c], mine)
+            idx = idx.astype(np.uint64) | (np.uint64(self.rank) << np.uint64(self.n_local))
             per_rank = np.bincount(owner, minlength=self.P)
             allidx = self._gather_var(idx, per_rank)
             vals, mult = np.unique(allidx, return_counts=True)
