@@ -549,17 +549,39 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
         ps.prog.generate = (generate && si == 0) ? 1 : 0;
         const bool last = si + 1 == sweeps.size();
         bool relabel = false;
-        if (last && final_relabel && !ident && which.size() == cols_.size() && !want_inplace_relabel()) {
+        const bool try_leaf = last && final_relabel && want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(ps.prog);
+        // with the layout already canonical the last sweep is still sent through the (out-of-place) staged store when a
+        // measurement follows: its store pass then delivers the canonical leaf totals, which saves the read pass
+        if (last && final_relabel && (!ident || try_leaf) && which.size() == cols_.size() && !want_inplace_relabel()) {
             std::vector<int> dstpos(n_);
             for (int l = 0; l < n_; ++l) dstpos[perm_[l]] = l;
             if (can_fuse_relabel(ps.prog, dstpos)) {
-                const bool try_leaf = want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(ps.prog);
+                const SweepProgram before = ps.prog;
                 set_relabel(ps.prog, dstpos, try_leaf);
                 relabel = true;
                 if (ps.prog.leaf_fuse) {
-                    if (ps.prog.direct_store || ensure_scratch(which.size())) ps.prog.leaf_fuse = 0;   // needs the staged store pass
+                    if (ensure_scratch(which.size())) ps.prog.leaf_fuse = 0;
+                    else ps.prog.direct_store = 0;                    // the totals come out of the staged store pass
+                }
+                if (ident && !ps.prog.leaf_fuse) { ps.prog = before; relabel = false; }     // nothing gained: run in place
+            }
+        }
+        // a tracked sweep whose steps all act on bits still pinned to 0 is a pure broadcast (kernels.cu
+        // ladder_broadcast_tiles), which lives in the staged store pass: give up the direct store for it
+        if (!relabel && ps.prog.sup_mode && !ps.prog.generate && ps.prog.direct_store && ps.prog.nrounds > 0) {
+            bool ok = true;
+            uint32_t tgt = 0;
+            for (int r = 0; r < ps.prog.nrounds && ok; ++r) {
+                const RoundDesc &R = ps.prog.rounds[r];
+                for (int j = kRegBits - R.nsteps; j < kRegBits; ++j) {
+                    const unsigned tb = R.reg_tb[j];
+                    if (!((R.smask >> j) & 1u) || ((tgt >> tb) & 1u)) ok = false;
+                    for (unsigned long long g : gen)
+                        if ((g >> ps.prog.tsrc[tb]) & 1ull) ok = false;
+                    tgt |= 1u << tb;
                 }
             }
+            if (ok && __builtin_popcount(tgt) >= 2) ps.prog.direct_store = 0;
         }
         // dense ladder sweeps take their tiles by TMA (planner.cpp apply_tma_layout, kernels.cu ladder_kernel)
         const bool tma_ok = tma_ && !ps.prog.generate && ps.prog.sup_mode == 0 && sweep_uses_ladder_kernel(ps.prog) && tma_available();
@@ -1232,7 +1254,12 @@ int DeviceVectorState::leaf_totals(size_t qbit, double *out)
 int DeviceVectorState::block_totals(size_t qbit, double *out)
 {
     if (nr_leaves() < kCanonBlock) return fail(Q1T_ERR_UNSUPPORTED, "block_totals: shards below 2^20 amplitudes chain their leaves on the host");
+    // as in measure_all_into: the last queued sweep may produce the leaf totals in its store pass
+    want_leaf_fusion_ = fuse_leaf_totals_ && qbit >= (size_t)n_ && cols_.size() == 1;
+    leaf_fused_ = false;
     int rc = flush_async();
+    const bool leaf_ready = leaf_fused_;
+    want_leaf_fusion_ = leaf_fused_ = false;
     if (rc) return rc;
     for (Column &c : cols_) {
         rc = materialize(c);
@@ -1247,11 +1274,14 @@ int DeviceVectorState::block_totals(size_t qbit, double *out)
     const uint64_t mask = qbit < (size_t)n_ ? 1ull << (n_ - 1 - (int)qbit) : 0ull;
     const size_t nb = nr_leaves() / kCanonBlock;
     time_begin();
-    CK(launch_leaf_totals(d_colptrs_, (int)all.size(), d_leaf_, n_, mask, 0, stream_));
+    if (!leaf_ready) {
+        CK(launch_leaf_totals(d_colptrs_, (int)all.size(), d_leaf_, n_, mask, 0, stream_));
+        stats.kernel_launches++;
+        stats.read_passes += all.size();
+    }
     CK(launch_block_scan(d_leaf_, d_block_, (int)all.size(), n_, stream_));
     time_end(stats.read_ms);
-    stats.kernel_launches += 2;
-    stats.read_passes += all.size();
+    stats.kernel_launches++;
     CK(cudaMemcpyAsync(out, d_block_, sizeof(double) * all.size() * nb, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     return Q1T_OK;

@@ -341,6 +341,29 @@ class _Recorder:
         return getattr(self.local, name)
 
 
+class _NullLocal:
+    """No data: lets ShardedState walk an op list and count what it would cost (remaps, local relabels)"""
+    ncols = 1
+    has_group = True
+
+    def __init__(self, n_local, shots):
+        self.n_local, self.shots, self.counts = n_local, shots, [shots]
+        self.relabels = 0
+
+    def apply_gate(self, mat, qubits):
+        if len(qubits) == 2 and mat is SWAP:
+            self.relabels += 1
+
+    def scale(self, s):
+        pass
+
+    def group_remap(self, rank_bits, local_qubits):
+        pass
+
+    def replace_columns(self, idx, counts):
+        pass
+
+
 class ShardedState:
     """`QuState` over a state sharded across the ranks of a process group."""
 
@@ -957,6 +980,22 @@ class ShardedState:
 
     _tapes = {}
 
+    def _dry_run_cost(self, ops, nprefix, mats, dest, busy, nxt, where0):
+        """remaps (and local relabels) the gate prefix of `ops` plus the canonical read-out would cost from the layout
+        where0 on a fresh |0..0>: the same code path on a data-less stand-in"""
+        sim = object.__new__(ShardedState)
+        sim.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("local", "where", "pin")})
+        sim.local = _NullLocal(self.n_local, self.shots)
+        sim.where = list(where0)
+        sim.pin = [0] * self.g
+        sim.group_ok = True
+        sim.exchanges = sim.remaps = sim.exchanged_bytes = 0
+        sim.exchange_seconds = 0.0
+        sim._start_tag = None
+        sim._walk(ops[:nprefix], None, None, None, mats, dest, busy, nxt, 0)
+        sim.canonicalize()
+        return sim.remaps * 1000 + sim.local.relabels
+
     def _replay(self, tape):
         for kind, payload in tape["segments"]:
             if kind == "g":
@@ -971,17 +1010,38 @@ class ShardedState:
         self.remaps += tape["remaps"]
         self.exchanged_bytes += tape["bytes"]
 
+    _layouts = {}
+
     def _run_planned(self, ops, gate_matrix, res, rng, mats, dest, busy, nxt):
-        # the gate-only prefix of an op list run from a known start (fresh |0..0> or product state) is taped once
         nprefix = 0
         while nprefix < len(ops) and ops[nprefix][0] == "gate":
             nprefix += 1
         start = getattr(self, "_start_tag", None)
-        can_tape = (start is not None and nprefix >= 8 and hasattr(self.local, "apply_packed") and
-                    self.where == [self._canonical(q) for q in range(self.n)])
+        canonical = [self._canonical(q) for q in range(self.n)]
+        at_start = start is not None and self.where == canonical
+        # Initial layout.  |0..0> is symmetric under qubit permutations, so a run that starts from it may start from ANY
+        # layout.  Two candidates: the canonical one, and the one the remaining Swap relabels turn INTO the canonical
+        # one (label q starts where the qubit its data ends as belongs); a data-less walk of the op list counts what
+        # each costs in remaps and local relabels.  A QFT from |0..0> ends canonical without a single exchange.
+        if at_start and start == "zero" and self.replicate and self.g > 0 and nprefix > 0 and all(v == 0 for v in self.pin):
+            lkey = (id(ops), len(ops), self.n, self.g)
+            hit = ShardedState._layouts.get(lkey)
+            if hit is None or hit[0] is not ops:
+                cand = [self._canonical(dest[0][q]) for q in range(self.n)]
+                pick = canonical
+                if cand != canonical and self._dry_run_cost(ops, nprefix, mats, dest, busy, nxt, cand) < \
+                        self._dry_run_cost(ops, nprefix, mats, dest, busy, nxt, canonical):
+                    pick = cand
+                if len(ShardedState._layouts) >= 8:
+                    ShardedState._layouts.pop(next(iter(ShardedState._layouts)))
+                hit = ShardedState._layouts[lkey] = (ops, pick)
+            self.where = list(hit[1])
+        # the gate-only prefix of an op list run from a known start (fresh |0..0> or product state) is taped once
+        can_tape = at_start and nprefix >= 8 and hasattr(self.local, "apply_packed")
         tkey = (id(ops), len(ops), self.n, self.g, self.rank, start, tuple(self.pin))
         t_from = 0
         recorder = None
+        counters = (self.exchanges, self.remaps, self.exchanged_bytes)
         if can_tape:
             tape = ShardedState._tapes.get(tkey)
             if tape is not None and tape["ops"] is ops:
@@ -989,9 +1049,39 @@ class ShardedState:
                 t_from = nprefix
             else:
                 recorder = _Recorder(self.local)
-                counters = (self.exchanges, self.remaps, self.exchanged_bytes)
                 self.local = recorder
+
+        def finish_recording():
+            rec = recorder
+            self.local = rec.local
+            if not rec.valid:
+                return
+            segs, run = [], []
+            for e in rec.tape:
+                if e[0] == "g":
+                    run.append((e[1], e[2]))
+                    continue
+                if run:
+                    segs.append(("g", self.local.pack_gates(run)))
+                    run = []
+                segs.append(("s", e[1]) if e[0] == "s" else ("r", (e[1], e[2])))
+            if run:
+                segs.append(("g", self.local.pack_gates(run)))
+            if len(ShardedState._tapes) >= 8:
+                ShardedState._tapes.pop(next(iter(ShardedState._tapes)))
+            ShardedState._tapes[tkey] = {"ops": ops, "segments": segs, "where": list(self.where), "pin": list(self.pin),
+                                         "exchanges": self.exchanges - counters[0], "remaps": self.remaps - counters[1],
+                                         "bytes": self.exchanged_bytes - counters[2]}
+
         self._start_tag = None            # whatever runs now, the state is no longer at its start
+        try:
+            self._walk(ops, gate_matrix, res, rng, mats, dest, busy, nxt, t_from, nprefix=nprefix,
+                       on_prefix_end=finish_recording if recorder is not None else None)
+        finally:
+            if recorder is not None and self.local is recorder:
+                self.local = recorder.local
+
+    def _walk(self, ops, gate_matrix, res, rng, mats, dest, busy, nxt, t_from, nprefix=None, on_prefix_end=None):
         state = {"t": 0}
 
         def policy(gbit, keep):
@@ -1014,37 +1104,17 @@ class ShardedState:
             return [v for v in range(self.n) if v != q and self.where[v][0] == "g" and self.pin[self.where[v][1]] is None
                     and nxt[t + 1][v] < INF]
 
-        def finish_recording(rec):
-            self.local = rec.local
-            if not rec.valid:
-                return
-            segs, run = [], []
-            for e in rec.tape:
-                if e[0] == "g":
-                    run.append((e[1], e[2]))
-                    continue
-                if run:
-                    segs.append(("g", self.local.pack_gates(run)))
-                    run = []
-                segs.append(("s", e[1]) if e[0] == "s" else ("r", (e[1], e[2])))
-            if run:
-                segs.append(("g", self.local.pack_gates(run)))
-            if len(ShardedState._tapes) >= 8:
-                ShardedState._tapes.pop(next(iter(ShardedState._tapes)))
-            ShardedState._tapes[tkey] = {"ops": ops, "segments": segs, "where": list(self.where), "pin": list(self.pin),
-                                         "exchanges": self.exchanges - counters[0], "remaps": self.remaps - counters[1],
-                                         "bytes": self.exchanged_bytes - counters[2]}
-
         old = self.lookahead
         self.lookahead = policy
         self._also_hook = also if self.group_ok else None
+        pending_end = on_prefix_end
         try:
             for t, op in enumerate(ops):
                 if t < t_from:
                     continue
-                if recorder is not None and t == nprefix:
-                    finish_recording(recorder)
-                    recorder = None
+                if pending_end is not None and t == nprefix:
+                    pending_end()
+                    pending_end = None
                 state["t"] = t
                 k = op[0]
                 if k == "gate":
@@ -1066,14 +1136,11 @@ class ShardedState:
                     pass
                 else:
                     raise NotImplementedError("run_ops: %r" % (op,))
-            if recorder is not None:
-                finish_recording(recorder)
-                recorder = None
+            if pending_end is not None:
+                pending_end()
         finally:
             self.lookahead = old
             self._also_hook = None
-            if recorder is not None:
-                self.local = recorder.local
 
     # ---- read-out (tests) ----------------------------------------------------------
     @property

@@ -217,11 +217,12 @@ def test_sharded_replicated_start_and_multi_bit_remap(world, n, case):
     for o in _run(world, n, case):
         for rep in (0, 1):
             assert o["amp_err_%d" % rep] < 1e-12
-            # no exchange for the gates of a QFT from |0..0>: only the canonical layout at read-out costs remaps --
-            # one multi-bit remap with a peer group, g pairwise exchanges without
-            assert o["remaps_%d" % rep] == (1 if case.endswith("group") else g)
+            # a QFT from |0..0> costs no exchange at all: replicated start for its gates, and the run starts from the
+            # layout that its Swap relabels turn into the canonical one (|0..0> is symmetric)
+            assert o["remaps_%d" % rep] == 0
         assert o["replayed_0"] == 0 and o["replayed_1"] > 0         # the second run of the op list replays the taped schedule
         assert o["amp_err_pins"] < 1e-12
         assert o["amp_err_product"] < 1e-12
-        assert o["remaps_product"] <= (2 if case.endswith("group") else 3 * g)
+        # a dense input has nothing pinned: the global qubits come on chip in one multi-bit remap (peer group)
+        assert 1 <= o["remaps_product"] <= (2 if case.endswith("group") else 3 * g)
         assert o["measure_equal"]
