@@ -192,6 +192,8 @@ typedef struct {
     uint64_t peer_swap_bytes;     /* bytes this rank moved over NVLink in q1t_peer_swap (remote reads + remote writes) */
     uint64_t plan_cache_hits;     /* gate batches whose sweep plan came from the process-wide plan cache */
     uint64_t tma_sweeps;          /* sweeps whose tiles were loaded by TMA (cp.async.bulk.tensor), dense ladder sweeps */
+    uint64_t graph_captures;      /* launch-bound sweep batches captured into a CUDA graph */
+    uint64_t graph_replays;       /* ... and batches executed by replaying a cached graph (one launch for the whole batch) */
     uint64_t h2d_bytes;           /* bytes copied host -> device by this state (programs, tables, draws, amplitudes written) */
     uint64_t d2h_bytes;           /* bytes copied device -> host (totals, sampled indices, amplitudes read) */
 } q1t_stats;
@@ -199,7 +201,7 @@ int q1t_get_stats(q1t_state *st, q1t_stats *out);
 int q1t_reset_stats(q1t_state *st);
 /* enable per-kernel CUDA-event timing (bench only; serialises the stream) */
 int q1t_set_timing(q1t_state *st, int enabled);
-/* engine knobs: "tile_bits" (8..13), "fuse" (0/1), "coalesce_bits" (2/3), "balance" (-1/0/1), "track_support" (0/1), "tma" (0/1),
+/* engine knobs: "tile_bits" (8..13), "fuse" (0/1), "coalesce_bits" (2/3), "balance" (-1/0/1), "track_support" (0/1), "tma" (0/1), "graphs" (0/1),
  * "inplace_relabel" (-1 never, 0 only when no second column buffer fits into device memory, 1 always).
  * Returns Q1T_ERR_INVALID_ARGUMENT for unknown keys. */
 int q1t_set_option(q1t_state *st, const char *key, long value);

@@ -25,11 +25,35 @@ namespace q1t {
 
 // every host<->device copy of the engine goes through here: q1t_stats::h2d_bytes / d2h_bytes are what bench.py reports
 // as the end-to-end transfer volume
+// While a sweep batch is being captured into a CUDA graph, the host sources of its copies are moved into pinned
+// memory owned by the graph: a replay re-reads them from there, so they must neither move nor change.
+struct GraphArena {
+    std::vector<void *> chunks;
+    void *stage(const void *src, size_t nbytes)
+    {
+        void *p = nullptr;
+        if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        std::memcpy(p, src, nbytes);
+        chunks.push_back(p);
+        return p;
+    }
+    void release()
+    {
+        for (void *p : chunks) cudaFreeHost(p);
+        chunks.clear();
+    }
+};
+static thread_local GraphArena *g_capture_arena = nullptr;      // non-null while this thread captures a sweep batch
+
 #define cudaMemcpyAsync(dst, src, nbytes, kind, stream) counted_copy(stats, dst, src, nbytes, kind, stream)
 static inline cudaError_t counted_copy(q1t_stats &st, void *dst, const void *src, size_t nbytes, cudaMemcpyKind kind, cudaStream_t stream)
 {
     if (kind == cudaMemcpyHostToDevice) st.h2d_bytes += nbytes;
     else if (kind == cudaMemcpyDeviceToHost) st.d2h_bytes += nbytes;
+    if (g_capture_arena && kind == cudaMemcpyHostToDevice) {
+        src = g_capture_arena->stage(src, nbytes);
+        if (!src) return cudaErrorMemoryAllocation;
+    }
     return (cudaMemcpyAsync)(dst, src, nbytes, kind, stream);
 }
 
@@ -105,6 +129,15 @@ uint64_t g_plan_clock = 0;
 const size_t kPlanCacheMax = 16;
 }  // namespace
 
+// process-wide cache of captured sweep batches (launch-bound circuits: a hundred 10-microsecond sweeps per execute())
+namespace {
+struct GraphEntry { uint64_t key; cudaGraphExec_t exec; GraphArena arena; uint64_t stamp; uint64_t launches, sweeps, col_passes, bytes, h2d; };
+std::mutex g_graph_mu;
+std::vector<GraphEntry> g_graphs;
+uint64_t g_graph_clock = 0;
+const size_t kGraphCacheMax = 12;
+}  // namespace
+
 int DeviceVectorState::cuda_fail(cudaError_t e, const char *what)
 {
     char buf[512];
@@ -126,6 +159,7 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
     if (const char *e = std::getenv("Q1T_FUSE_LEAF")) fuse_leaf_totals_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_INPLACE_RELABEL")) inplace_relabel_ = std::atol(e);
     if (const char *e = std::getenv("Q1T_TMA")) tma_ = std::atol(e) != 0;
+    if (const char *e = std::getenv("Q1T_GRAPHS")) graphs_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_PREFETCH_AHEAD")) prefetch_ahead_ = std::atol(e);
     if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
 }
@@ -302,14 +336,21 @@ int DeviceVectorState::materialize(Column &c)
     return Q1T_OK;
 }
 
-int DeviceVectorState::upload_colptrs(const std::vector<int> &which)
+int DeviceVectorState::reserve_colptrs(size_t need)
 {
-    const size_t need = which.size();
     if (need > colptrs_cap_) {
         if (d_colptrs_) { CK(cudaStreamSynchronize(stream_)); scratch_free(device_, d_colptrs_, sizeof(double2 *) * colptrs_cap_); }
         colptrs_cap_ = std::max<size_t>(need * 2, 16);
         CK(scratch_alloc(device_, (void **)&d_colptrs_, sizeof(double2 *) * colptrs_cap_));
     }
+    return Q1T_OK;
+}
+
+int DeviceVectorState::upload_colptrs(const std::vector<int> &which)
+{
+    const size_t need = which.size();
+    int rc0 = reserve_colptrs(need);
+    if (rc0) return rc0;
     std::vector<double2 *> h(need);
     for (size_t i = 0; i < need; ++i) h[i] = cols_[which[i]].buf;
     CK(cudaMemcpyAsync(d_colptrs_, h.data(), sizeof(double2 *) * need, cudaMemcpyHostToDevice, stream_));
@@ -458,10 +499,10 @@ static unsigned long long physical_index(uint64_t logical, const std::vector<int
 int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel)
 {
     if (sweeps.empty()) return Q1T_OK;
-    bool all_basis = true;
-    for (int c : which) all_basis = all_basis && cols_[c].basis;
+    bool all_basis = true, any_basis = false;
+    for (int c : which) { all_basis = all_basis && cols_[c].basis; any_basis = any_basis || cols_[c].basis; }
     std::vector<unsigned long long> gen(which.size());
-    bool generate = all_basis;
+    const bool generate = all_basis;
     if (generate) {
         for (size_t i = 0; i < which.size(); ++i) {
             Column &c = cols_[which[i]];
@@ -475,18 +516,114 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
             gen_cap_ = std::max<size_t>(which.size() * 2, 16);
             CK(scratch_alloc(device_, (void **)&d_gen_, sizeof(unsigned long long) * gen_cap_));
         }
-        CK(cudaMemcpyAsync(d_gen_, gen.data(), sizeof(unsigned long long) * gen.size(), cudaMemcpyHostToDevice, stream_));
     } else {
         for (int c : which) {
             int rc = materialize(cols_[c]);
             if (rc) return rc;
         }
     }
-    int rc = upload_colptrs(which);
+    int rc = reserve_colptrs(which.size());
     if (rc) return rc;
     bool ident = true;
     for (int l = 0; l < n_; ++l)
         if (perm_[l] != l) ident = false;
+    // Launch-bound batches (small states, many sweeps) are captured into a CUDA graph once and replayed: a sweep of a
+    // 2^20 state runs for ~10 us, its launch plus the upload of its program costs ~40 us of host time.  A batch qualifies
+    // if it comes from the plan cache (the key names the gate list), touches no lazy column half-way, and restores no
+    // layout (the relabelling path allocates).  The graph is keyed by everything the issued work depends on.
+    const bool graph_try = graphs_ && !timing && cur_plan_key_ != 0 && sweeps.size() >= 8 && n_ <= 26 && !tma_ &&
+                           (generate || !any_basis) && !(final_relabel && (!ident || want_leaf_fusion_));
+    uint64_t gkey = 0;
+    if (graph_try) {
+        gkey = 1469598103934665603ull;
+        auto mix = [&](const void *p, size_t nbytes) {
+            const unsigned char *b = static_cast<const unsigned char *>(p);
+            for (size_t i = 0; i < nbytes; ++i) { gkey ^= b[i]; gkey *= 1099511628211ull; }
+        };
+        const uint64_t hdr[8] = { cur_plan_key_, (uint64_t)sweeps.size(), (uint64_t)generate, (uint64_t)track_support_, (uint64_t)which.size(),
+                                  (uint64_t)n_, (uint64_t)device_, (uint64_t)direct_ };
+        mix(hdr, sizeof hdr);
+        const void *ptrs[3] = { d_ptabs_, d_colptrs_, d_gen_ };
+        mix(ptrs, sizeof ptrs);
+        for (int c : which) { const void *b = cols_[c].buf; mix(&b, sizeof b); }
+        if (generate) mix(gen.data(), sizeof(unsigned long long) * gen.size());
+        const double ps = which.size() == cols_.size() ? pending_scale_ : 1.0;
+        mix(&ps, sizeof ps);
+        cudaGraphExec_t exec = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_graph_mu);
+            for (GraphEntry &ge : g_graphs)
+                if (ge.key == gkey) {
+                    exec = ge.exec;
+                    ge.stamp = ++g_graph_clock;
+                    stats.kernel_launches += ge.launches;
+                    stats.sweeps += ge.sweeps;
+                    stats.sweep_column_passes += ge.col_passes;
+                    stats.sweep_bytes += ge.bytes;
+                    stats.h2d_bytes += ge.h2d;
+                }
+        }
+        if (exec) {
+            if (which.size() == cols_.size()) pending_scale_ = 1.0;
+            CK(cudaGraphLaunch(exec, stream_));
+            stats.graph_replays++;
+            sweeps.clear();
+            return Q1T_OK;
+        }
+    }
+    if (!graph_try) return issue_sweeps(sweeps, which, final_relabel, generate, gen, ident);
+    // capture, instantiate, launch, remember
+    GraphEntry ge;
+    ge.key = gkey;
+    ge.exec = nullptr;
+    const q1t_stats before = stats;
+    CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeRelaxed));   // relaxed: the pinned staging chunks are allocated while capturing
+    g_capture_arena = &ge.arena;
+    rc = issue_sweeps(sweeps, which, final_relabel, generate, gen, ident);
+    g_capture_arena = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        ge.arena.release();
+        if (rc) return rc;
+        return cuda_fail(ce, "cudaStreamEndCapture");
+    }
+    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { ge.arena.release(); return cuda_fail(ce, "cudaGraphInstantiate"); }
+    CK(cudaGraphLaunch(ge.exec, stream_));
+    stats.graph_captures++;
+    ge.launches = stats.kernel_launches - before.kernel_launches;
+    ge.sweeps = stats.sweeps - before.sweeps;
+    ge.col_passes = stats.sweep_column_passes - before.sweep_column_passes;
+    ge.bytes = stats.sweep_bytes - before.sweep_bytes;
+    ge.h2d = stats.h2d_bytes - before.h2d_bytes;
+    {
+        std::lock_guard<std::mutex> lk(g_graph_mu);
+        if (g_graphs.size() >= kGraphCacheMax) {
+            size_t lru = 0;
+            for (size_t i = 1; i < g_graphs.size(); ++i)
+                if (g_graphs[i].stamp < g_graphs[lru].stamp) lru = i;
+            // (an evicted graph may still be running on some stream: let everything drain before it goes)
+            cudaDeviceSynchronize();
+            cudaGraphExecDestroy(g_graphs[lru].exec);
+            g_graphs[lru].arena.release();
+            g_graphs.erase(g_graphs.begin() + lru);
+        }
+        ge.stamp = ++g_graph_clock;
+        g_graphs.push_back(ge);
+    }
+    return Q1T_OK;
+}
+
+// the stream work of a sweep batch (immediately, or into the graph being captured)
+int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel, bool generate,
+                                    const std::vector<unsigned long long> &gen, bool ident)
+{
+    if (generate) CK(cudaMemcpyAsync(d_gen_, gen.data(), sizeof(unsigned long long) * gen.size(), cudaMemcpyHostToDevice, stream_));
+    int rc = upload_colptrs(which);
+    if (rc) return rc;
     // the deferred Hadamard normalisations of the whole batch are applied once: for free in the
     // generated basis element, otherwise at the store of the last sweep
     {
@@ -596,7 +733,13 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
                 } else hcols.clear();
             }
             time_begin();
-            stats.h2d_bytes += sizeof(SweepProgram); CK(launch_sweep(ps.prog, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_, nullptr,
+            // (captured into a graph, the program upload re-reads its source at every replay: pinned copy owned by the graph)
+            const SweepProgram *prog_src = &ps.prog;
+            if (g_capture_arena) {
+                prog_src = static_cast<const SweepProgram *>(g_capture_arena->stage(&ps.prog, sizeof(SweepProgram)));
+                if (!prog_src) return fail(Q1T_ERR_CUDA, "out of pinned host memory while capturing a sweep batch");
+            }
+            stats.h2d_bytes += sizeof(SweepProgram); CK(launch_sweep(*prog_src, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_, nullptr,
                             hcols.empty() ? nullptr : hcols.data()));
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
@@ -717,7 +860,10 @@ int DeviceVectorState::run_queue(bool final_relabel)
                         std::vector<PlannedSweep> plan = pc.sweeps;
                         pc.stamp = ++g_plan_clock;
                         stats.plan_cache_hits++;
-                        return run_sweeps(plan, which, final_relabel);
+                        cur_plan_key_ = key ? key : 1;
+                        const int rcs = run_sweeps(plan, which, final_relabel);
+                        cur_plan_key_ = 0;
+                        return rcs;
                     }
             }
             std::vector<PlannedSweep> plan[2];
@@ -748,7 +894,10 @@ int DeviceVectorState::run_queue(bool final_relabel)
                 }
                 g_plan_cache.push_back({ key, q.size(), ++g_plan_clock, plan[pick] });
             }
-            return run_sweeps(plan[pick], which, final_relabel);
+            cur_plan_key_ = q.size() >= 16 ? (key ? key : 1) : 0;
+            const int rcs = run_sweeps(plan[pick], which, final_relabel);
+            cur_plan_key_ = 0;
+            return rcs;
         }
     }
     Planner pl(n_, (int)tile_bits_, (int)coalesce_bits_, balance);
@@ -1894,6 +2043,10 @@ int DeviceVectorState::set_option(const char *key, long value)
     }
     if (!std::strcmp(key, "tma")) {
         tma_ = value != 0;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "graphs")) {
+        graphs_ = value != 0;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "direct")) {

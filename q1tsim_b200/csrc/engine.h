@@ -99,6 +99,8 @@ private:
     long balance_ = -1;                      // sweep packing: -1 try both, 0 greedy, 1 balanced
     long prefetch_ahead_ = 0;
     bool direct_ = true;
+    bool graphs_ = true;                     // launch-bound sweep batches are captured into CUDA graphs and replayed
+    uint64_t cur_plan_key_ = 0;              // plan-cache key of the batch run_queue is handing to run_sweeps (0: none)
     bool tma_ = false;                       // dense ladder sweeps load their tiles by TMA (cp.async.bulk.tensor): measured slower than cp.async (profiles/r2_ladder_tma.md), off
     bool fuse_ = true;
     bool no_relabel_ = false;                // conditional gates: Swap must move data, not relabel
@@ -139,6 +141,9 @@ private:
     void release_column(double2 *p);
     int materialize(Column &c);
     int upload_colptrs(const std::vector<int> &which);
+    int reserve_colptrs(size_t need);
+    int issue_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel, bool generate,
+                     const std::vector<unsigned long long> &gen, bool ident);
     int run_queue(bool final_relabel = false);   // queue -> planner -> sweep launches
     int run_sweeps(std::vector<PlannedSweep> &sweeps, const std::vector<int> &which, bool final_relabel);
     int run_generic(const LoweredGate &g, const std::vector<int> &which);

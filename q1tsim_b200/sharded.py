@@ -153,9 +153,12 @@ class EngineLocal:
 
     def replace_columns(self, idx, counts):
         C = self.C
-        ia = (C.c_uint64 * max(len(idx), 1))(*[int(v) for v in idx])
-        ca = (C.c_size_t * max(len(counts), 1))(*[int(v) for v in counts])
-        self.st._chk(self.L.q1t_replace_columns(self.st._p, len(idx), ia, ca))
+        ia = np.ascontiguousarray(np.asarray(idx, dtype=np.uint64))
+        ca = np.ascontiguousarray(np.asarray(counts, dtype=np.uint64))          # size_t
+        if ia.size == 0:
+            ia, ca = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+        self.st._chk(self.L.q1t_replace_columns(self.st._p, len(idx), ia.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                ca.ctypes.data_as(C.POINTER(C.c_size_t))))
 
     def column_tensor(self, col):
         """zero-copy torch view (2^n_local * 2,) float64 of a flushed column on the device"""
@@ -855,10 +858,10 @@ class ShardedState:
             words |= ((vals >> np.uint64(self.n - 1 - q)) & np.uint64(1)) << np.uint64(cbits[q])
         tot = int(mult.sum())
         res[:tot] = (res[:tot] & ~mask) | np.repeat(words, mult)
-        new_idx, new_cnt = [int(v) for v in vals], [int(m_) for m_ in mult]
         if collapse:
-            lm = (1 << self.n_local) - 1
-            self.local.replace_columns([(v & lm) if (v >> self.n_local) == self.rank else ZERO_COLUMN for v in new_idx], new_cnt)
+            lm = np.uint64((1 << self.n_local) - 1)
+            mine = (vals >> np.uint64(self.n_local)) == np.uint64(self.rank)
+            self.local.replace_columns(np.where(mine, vals & lm, np.uint64(ZERO_COLUMN)), mult.astype(np.uint64))
 
     def _gather_var(self, idx, per_rank):
         import torch

@@ -122,10 +122,10 @@ class NumpyLocal:
         self.cols = []
         for v in idx:
             col = np.zeros(1 << self.n_local, dtype=np.complex128)
-            if v != ZERO_COLUMN:
-                col[v] = 1.0
+            if int(v) != ZERO_COLUMN:
+                col[int(v)] = 1.0
             self.cols.append(col)
-        self._counts = list(counts)
+        self._counts = [int(c) for c in counts]
 
     def column_tensor(self, col):
         import torch

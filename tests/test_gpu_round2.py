@@ -147,3 +147,33 @@ def test_measure_all_bit_exact_n24():
     e.measure_all_into(list(range(n)), re_, E.Rng(words=words))
     o.measure_all_into(list(range(n)), ro, O.Rng(words=words))
     assert np.array_equal(re_, ro)
+
+
+@pytest.mark.parametrize("n,depth", [(12, 40), (20, 100)])
+def test_launch_bound_batches_replayed_as_cuda_graphs(n, depth):
+    """cfg2 shape (random H/U3/CX/CS/CT layers): a hundred short sweeps per run.  From the second run of the same gate list
+    on, the whole batch is ONE cudaGraphLaunch of the captured sweeps; results are identical to issuing them one by one"""
+    ops = W.random_circuit_ops(n, depth, measure=False)
+    gates = [(E.gate_matrix(o[1], o[2]), o[3], o[1]) for o in ops]
+    cols = {}
+    for graphs in (1, 0):
+        st = E.VectorState(n, 16)
+        st.set_option("graphs", graphs)
+        for rep in range(3):
+            st.reset_all()
+            for m, b, name in gates:
+                st.apply_gate(m, b, name)
+            st.flush()
+        s = st.stats()
+        if graphs:
+            assert s["graph_captures"] + s["graph_replays"] >= 3 and s["graph_replays"] >= 1, s
+        else:
+            assert s["graph_captures"] == 0 and s["graph_replays"] == 0
+        cols[graphs] = st.column(0)
+        st.close()
+    assert np.array_equal(cols[0], cols[1])
+    if n <= 12:
+        o = O.OracleState(n, 16, mode=1, order=1)
+        for m, b, _ in gates:
+            o.apply_gate(m, b)
+        assert rel_l2(cols[1], o.column(0)) < 1e-10
