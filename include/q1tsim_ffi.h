@@ -41,26 +41,26 @@ typedef struct { void *data; size_t length; size_t size; uint32_t restype; } res
 #define RESULT_CSTATE 5u
 
 void       result_free(result_t res);                                        /* ffi.rs:165-169 */
-circuit_t *circuit_new(size_t nr_qbits, size_t nr_cbits);                    /* ffi.rs:172-176 */
-void       circuit_free(circuit_t *ptr);                                     /* ffi.rs:179-186 */
-size_t     circuit_nr_qbits(const circuit_t *ptr);                           /* ffi.rs:189-194 */
-size_t     circuit_nr_cbits(const circuit_t *ptr);                           /* ffi.rs:197-202 */
-result_t   circuit_cstate(const circuit_t *ptr);                             /* ffi.rs:205-214 */
+circuit_t *circuit_new(size_t nr_qbits, size_t nr_cbits);                    /* ffi.rs:171-176 */
+void       circuit_free(circuit_t *ptr);                                     /* ffi.rs:178-186 */
+size_t     circuit_nr_qbits(const circuit_t *ptr);                           /* ffi.rs:188-194 */
+size_t     circuit_nr_cbits(const circuit_t *ptr);                           /* ffi.rs:196-202 */
+result_t   circuit_cstate(const circuit_t *ptr);                             /* ffi.rs:204-214 */
 result_t   circuit_add_gate(circuit_t *ptr, const char *gate, const size_t *qbits, size_t nr_qbits,
-                            const parameter_t *param_ptr, size_t nr_params);  /* ffi.rs:307-384 */
+                            const parameter_t *param_ptr, size_t nr_params);  /* ffi.rs:307-380 */
 result_t   circuit_add_conditional_gate(circuit_t *ptr, const size_t *control_ptr, size_t nr_control,
                                         uint64_t target, const char *gate, const size_t *qbits_ptr, size_t nr_qbits,
-                                        const parameter_t *param_ptr, size_t nr_params);   /* ffi.rs:387-464 */
-result_t   circuit_measure(circuit_t *ptr, size_t qbit, size_t cbit, char dir, uint8_t collapse);        /* ffi.rs:501-530 */
-result_t   circuit_measure_all(circuit_t *ptr, const size_t *cbits, size_t nr_cbits, char dir, uint8_t collapse); /* ffi.rs:533-567 */
-result_t   circuit_reset(circuit_t *ptr, size_t qbit);                       /* ffi.rs:467-483 */
-result_t   circuit_reset_all(circuit_t *ptr);                                /* ffi.rs:486-498 */
-result_t   circuit_execute(circuit_t *ptr, size_t nr_shots);                 /* ffi.rs:570-585 */
-result_t   circuit_reexecute(circuit_t *ptr);                                /* ffi.rs:588-603 */
-result_t   circuit_histogram(const circuit_t *ptr);                          /* ffi.rs:606-621 */
-result_t   circuit_latex(const circuit_t *ptr);                              /* ffi.rs:624-639; circuit.rs:1148-1231 */
-result_t   circuit_open_qasm(const circuit_t *ptr);                          /* ffi.rs:643-658; circuit.rs:877-1017 */
-result_t   circuit_c_qasm(const circuit_t *ptr);                             /* ffi.rs:661-676; circuit.rs:1019-1146 */
+                                        const parameter_t *param_ptr, size_t nr_params);   /* ffi.rs:382-459 */
+result_t   circuit_measure(circuit_t *ptr, size_t qbit, size_t cbit, char dir, uint8_t collapse);        /* ffi.rs:494-522 */
+result_t   circuit_measure_all(circuit_t *ptr, const size_t *cbits, size_t nr_cbits, char dir, uint8_t collapse); /* ffi.rs:524-557 */
+result_t   circuit_reset(circuit_t *ptr, size_t qbit);                       /* ffi.rs:461-477 */
+result_t   circuit_reset_all(circuit_t *ptr);                                /* ffi.rs:479-492 */
+result_t   circuit_execute(circuit_t *ptr, size_t nr_shots);                 /* ffi.rs:559-575 */
+result_t   circuit_reexecute(circuit_t *ptr);                                /* ffi.rs:577-593 */
+result_t   circuit_histogram(const circuit_t *ptr);                          /* ffi.rs:595-611 */
+result_t   circuit_latex(const circuit_t *ptr);                              /* ffi.rs:613-629; circuit.rs:1148-1231 */
+result_t   circuit_open_qasm(const circuit_t *ptr);                          /* ffi.rs:632-648; circuit.rs:877-1017 */
+result_t   circuit_c_qasm(const circuit_t *ptr);                             /* ffi.rs:650-666; circuit.rs:1019-1146 */
 
 /* ---- additive entry points ---- */
 /* arbitrary user gate given by its matrix() (gates.rs:174), row-major (re,im) */

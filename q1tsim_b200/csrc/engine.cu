@@ -531,8 +531,9 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     // 2^20 state runs for ~10 us, its launch plus the upload of its program costs ~40 us of host time.  A batch qualifies
     // if it comes from the plan cache (the key names the gate list), touches no lazy column half-way, and restores no
     // layout (the relabelling path allocates).  The graph is keyed by everything the issued work depends on.
-    const bool graph_try = graphs_ && !timing && cur_plan_key_ != 0 && sweeps.size() >= 8 && n_ <= 26 && !tma_ &&
-                           (generate || !any_basis) && !(final_relabel && (!ident || want_leaf_fusion_));
+    const bool may_relabel = final_relabel && (!ident || (want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(sweeps.back().prog)));
+    const bool graph_try = graphs_ && !timing && cur_plan_key_ != 0 && sweeps.size() >= 4 && n_ <= 26 && !tma_ &&
+                           (generate || !any_basis) && !may_relabel;
     uint64_t gkey = 0;
     if (graph_try) {
         gkey = 1469598103934665603ull;

@@ -1383,23 +1383,34 @@ block_scan_kernel(double *__restrict__ leaf_io, double *__restrict__ block_total
     }
 }
 
-// one thread per column: inclusive chain over block totals (in place)
-__global__ void top_chain_kernel(double *__restrict__ block_io, unsigned long long nblocks, int ncols,
-                                 double *__restrict__ totals_out)
+// one CTA per column: inclusive chain over block totals (in place).  The totals are staged through shared memory
+// with coalesced loads (a thread chaining straight from global memory pays a DRAM round trip per block), thread 0
+// chains them sequentially -- the canonical order -- and the CTA writes the prefixes back.
+__global__ void __launch_bounds__(256)
+top_chain_kernel(double *__restrict__ block_io, unsigned long long nblocks, int ncols, double *__restrict__ totals_out)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s[2048];
+    const int c = blockIdx.x;
     if (c >= ncols) return;
     double *__restrict__ bt = block_io + (unsigned long long)c * nblocks;
     double run = 0.0;
-    for (unsigned long long b = 0; b < nblocks; ++b) {
-        run = __dadd_rn(run, bt[b]);
-        bt[b] = run;
+    for (unsigned long long first = 0; first < nblocks; first += 2048) {
+        const unsigned cnt = (unsigned)((nblocks - first) < 2048ull ? (nblocks - first) : 2048ull);
+        for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) s[i] = bt[first + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (unsigned i = 0; i < cnt; ++i) {
+                run = __dadd_rn(run, s[i]);
+                s[i] = run;
+            }
+        }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) bt[first + i] = s[i];
+        __syncthreads();
     }
-    totals_out[c] = run;
+    if (threadIdx.x == 0) totals_out[c] = run;
 }
 
-// base0: weight in front of this column's first block (0 for a whole state -- x + 0.0 is x --, the weight of the
-// lower ranks for a shard whose block prefixes bpref continue the global chain)
 __device__ __forceinline__ double leaf_prefix(const double *__restrict__ inblock, const double *__restrict__ bpref,
                                               unsigned long long L, double base0)
 {
@@ -1407,19 +1418,23 @@ __device__ __forceinline__ double leaf_prefix(const double *__restrict__ inblock
     return __dadd_rn(b ? bpref[b - 1] : base0, inblock[L]);
 }
 
-// one thread per draw (draws sorted ascending on the host): leaf by binary
-// search over the canonical leaf prefixes, then a sequential in-leaf scan.
-__global__ void resolve_draws_kernel(const double2 *__restrict__ st, const double *__restrict__ inblock,
-                                     const double *__restrict__ bpref, int n, int leaf_bits,
-                                     const double *__restrict__ chosen, unsigned long long ndraws,
-                                     unsigned long long *__restrict__ idx_out, double base, double base0)
+// one warp per draw (draws sorted ascending on the host): leaf by binary search over the canonical leaf prefixes
+// (lane 0's result broadcast), then the in-leaf scan: the warp loads 32 consecutive amplitudes at a time (512 B,
+// coalesced, the next chunk already in flight) and lane 0's running sum visits them in index order through shuffles --
+// the same sequential chain as before, without a dependent DRAM round trip per 8 elements.
+__global__ void __launch_bounds__(256)
+resolve_draws_kernel(const double2 *__restrict__ st, const double *__restrict__ inblock,
+                     const double *__restrict__ bpref, int n, int leaf_bits,
+                     const double *__restrict__ chosen, unsigned long long ndraws,
+                     unsigned long long *__restrict__ idx_out, double base, double base0)
 {
-    const unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long j = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
     if (j >= ndraws) return;
     const double ch = chosen[j];
     const unsigned long long nleaves = 1ull << (n - leaf_bits);
     unsigned long long lo = 0, hi = nleaves - 1;
-    while (lo < hi) {
+    while (lo < hi) {                                   // (every lane runs the same search: uniform loads)
         const unsigned long long mid = (lo + hi) >> 1;
         if (leaf_prefix(inblock, bpref, mid, base0) <= ch) lo = mid + 1; else hi = mid;
     }
@@ -1427,22 +1442,24 @@ __global__ void resolve_draws_kernel(const double2 *__restrict__ st, const doubl
     const unsigned leaf = 1u << leaf_bits;
     const double2 *__restrict__ p = st + (lo << leaf_bits);
     unsigned found = 0xffffffffu, last_nz = 0xffffffffu;
-    for (unsigned e0 = 0; e0 < leaf && found == 0xffffffffu; e0 += 8) {
-        double w[8];
-        const unsigned m = (leaf - e0) < 8u ? (leaf - e0) : 8u;
-#pragma unroll
-        for (unsigned q = 0; q < 8; ++q) w[q] = q < m ? norm_sqr_rn(p[e0 + q]) : 0.0;
-#pragma unroll
-        for (unsigned q = 0; q < 8; ++q) {
+    double w_next = (unsigned)lane < leaf ? norm_sqr_rn(p[lane]) : 0.0;
+    for (unsigned e0 = 0; e0 < leaf && found == 0xffffffffu; e0 += 32) {
+        const double w = w_next;
+        if (e0 + 32 < leaf) w_next = e0 + 32 + lane < leaf ? norm_sqr_rn(p[e0 + 32 + lane]) : 0.0;
+        const unsigned m = (leaf - e0) < 32u ? (leaf - e0) : 32u;
+        // the chain runs redundantly in every lane on shuffled values: no divergence, same order
+#pragma unroll 8
+        for (unsigned q = 0; q < 32; ++q) {
+            const double wq = __shfl_sync(0xffffffffu, w, q);
             if (q < m && found == 0xffffffffu) {
-                if (w[q] > 0.0) last_nz = e0 + q;
-                run = __dadd_rn(run, w[q]);
+                if (wq > 0.0) last_nz = e0 + q;
+                run = __dadd_rn(run, wq);
                 if (ch < run) found = e0 + q;
             }
         }
     }
     if (found == 0xffffffffu) found = last_nz == 0xffffffffu ? leaf - 1 : last_nz;
-    idx_out[j] = (lo << leaf_bits) + found;
+    if (lane == 0) idx_out[j] = (lo << leaf_bits) + found;
 }
 
 cudaError_t launch_leaf_totals(const double2 *const *d_cols, int ncols, double *d_leaf, int n,
@@ -1474,7 +1491,7 @@ cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int n
     block_scan_kernel<<<dim3((unsigned)((nblocks + 3) / 4), ncols), 128, 0, stream>>>(d_leaf, d_block, nleaves, nblocks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    top_chain_kernel<<<(ncols + 63) / 64, 64, 0, stream>>>(d_block, nblocks, ncols, d_totals);
+    top_chain_kernel<<<ncols, 256, 0, stream>>>(d_block, nblocks, ncols, d_totals);
     return cudaGetLastError();
 }
 
@@ -1484,8 +1501,8 @@ cudaError_t launch_resolve_draws(const double2 *d_col, const double *d_leaf, con
 {
     if (ndraws == 0) return cudaSuccess;
     const int leaf_bits = n < kCanonLeafBits ? n : kCanonLeafBits;
-    resolve_draws_kernel<<<(unsigned)((ndraws + 63) / 64), 64, 0, stream>>>(d_col, d_leaf, d_block, n, leaf_bits, d_chosen,
-                                                                         ndraws, d_idx, base, base0);
+    resolve_draws_kernel<<<(unsigned)((ndraws + 7) / 8), 256, 0, stream>>>(d_col, d_leaf, d_block, n, leaf_bits, d_chosen,
+                                                                        ndraws, d_idx, base, base0);
     return cudaGetLastError();
 }
 
