@@ -37,10 +37,34 @@ struct GraphArena {
         chunks.push_back(p);
         return p;
     }
+    // programs and phase tables of the captured sweeps live in ONE device blob that stays resident as long as the
+    // graph does (uploaded once, after the capture): the kernels read them from there, a replay uploads nothing
+    char *d_blob = nullptr, *h_blob = nullptr;
+    size_t blob_cap = 0, blob_used = 0;
+    bool reserve_blob(size_t nbytes)
+    {
+        if (cudaMalloc(&d_blob, nbytes) != cudaSuccess) { cudaGetLastError(); d_blob = nullptr; return false; }
+        if (cudaMallocHost(&h_blob, nbytes) != cudaSuccess) { cudaGetLastError(); cudaFree(d_blob); d_blob = nullptr; h_blob = nullptr; return false; }
+        blob_cap = nbytes;
+        blob_used = 0;
+        return true;
+    }
+    // returns the DEVICE address the bytes will have once the blob is uploaded
+    const void *put(const void *src, size_t nbytes)
+    {
+        const size_t at = (blob_used + 255) & ~(size_t)255;
+        if (!d_blob || at + nbytes > blob_cap) return nullptr;
+        std::memcpy(h_blob + at, src, nbytes);
+        blob_used = at + nbytes;
+        return d_blob + at;
+    }
     void release()
     {
         for (void *p : chunks) cudaFreeHost(p);
         chunks.clear();
+        if (h_blob) cudaFreeHost(h_blob);
+        if (d_blob) cudaFree(d_blob);
+        h_blob = d_blob = nullptr;
     }
 };
 static thread_local GraphArena *g_capture_arena = nullptr;      // non-null while this thread captures a sweep batch
@@ -578,6 +602,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     ge.key = gkey;
     ge.exec = nullptr;
     const q1t_stats before = stats;
+    ge.arena.reserve_blob(sweeps.size() * (sizeof(SweepProgram) + 512 + (sizeof(PhaseTab) + 16) * kMaxPhase));    // (without it: uploads stay in the graph)
     CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeRelaxed));   // relaxed: the pinned staging chunks are allocated while capturing
     g_capture_arena = &ge.arena;
     rc = issue_sweeps(sweeps, which, final_relabel, generate, gen, ident);
@@ -593,13 +618,23 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     ce = cudaGraphInstantiate(&ge.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { ge.arena.release(); return cuda_fail(ce, "cudaGraphInstantiate"); }
+    if (ge.arena.blob_used) {
+        // the one upload of the batch's programs and phase tables (not part of the graph)
+        stats.h2d_bytes += ge.arena.blob_used;
+        CK((cudaMemcpyAsync)(ge.arena.d_blob, ge.arena.h_blob, ge.arena.blob_used, cudaMemcpyHostToDevice, stream_));
+    }
     CK(cudaGraphLaunch(ge.exec, stream_));
+    if (ge.arena.h_blob) {
+        CK(cudaStreamSynchronize(stream_));
+        cudaFreeHost(ge.arena.h_blob);
+        ge.arena.h_blob = nullptr;
+    }
     stats.graph_captures++;
     ge.launches = stats.kernel_launches - before.kernel_launches;
     ge.sweeps = stats.sweeps - before.sweeps;
     ge.col_passes = stats.sweep_column_passes - before.sweep_column_passes;
     ge.bytes = stats.sweep_bytes - before.sweep_bytes;
-    ge.h2d = stats.h2d_bytes - before.h2d_bytes;
+    ge.h2d = stats.h2d_bytes - before.h2d_bytes - ge.arena.blob_used;      // a replay does not upload the resident blob again
     {
         std::lock_guard<std::mutex> lk(g_graph_mu);
         if (g_graphs.size() >= kGraphCacheMax) {
@@ -682,8 +717,18 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
     }
     for (size_t si = 0; si < sweeps.size(); ++si) {
         PlannedSweep &ps = sweeps[si];
-        if (!ps.ptabs.empty())
-            CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
+        const PhaseTab *d_ptabs_here = d_ptabs_;
+        bool ptabs_resident = false;
+        if (!ps.ptabs.empty()) {
+            if (g_capture_arena && g_capture_arena->d_blob) {
+                if (const void *dp = g_capture_arena->put(ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size())) {
+                    d_ptabs_here = static_cast<const PhaseTab *>(dp);
+                    ptabs_resident = true;
+                }
+            }
+            if (!ptabs_resident)
+                CK(cudaMemcpyAsync(d_ptabs_, ps.ptabs.data(), sizeof(PhaseTab) * ps.ptabs.size(), cudaMemcpyHostToDevice, stream_));
+        }
         ps.prog.generate = (generate && si == 0) ? 1 : 0;
         const bool last = si + 1 == sweeps.size();
         bool relabel = false;
@@ -735,13 +780,18 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
             }
             time_begin();
             // (captured into a graph, the program upload re-reads its source at every replay: pinned copy owned by the graph)
-            const SweepProgram *prog_src = &ps.prog;
+            const SweepProgram *prog_src = &ps.prog, *d_prog = nullptr;
             if (g_capture_arena) {
-                prog_src = static_cast<const SweepProgram *>(g_capture_arena->stage(&ps.prog, sizeof(SweepProgram)));
-                if (!prog_src) return fail(Q1T_ERR_CUDA, "out of pinned host memory while capturing a sweep batch");
+                if (!sweep_uses_ladder_kernel(ps.prog) && g_capture_arena->d_blob)
+                    d_prog = static_cast<const SweepProgram *>(g_capture_arena->put(&ps.prog, sizeof(SweepProgram)));     // device-resident
+                if (!d_prog) {
+                    prog_src = static_cast<const SweepProgram *>(g_capture_arena->stage(&ps.prog, sizeof(SweepProgram)));
+                    if (!prog_src) return fail(Q1T_ERR_CUDA, "out of pinned host memory while capturing a sweep batch");
+                }
             }
-            stats.h2d_bytes += sizeof(SweepProgram); CK(launch_sweep(*prog_src, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_, d_gen_, stream_, nullptr,
-                            hcols.empty() ? nullptr : hcols.data()));
+            if (!d_prog) stats.h2d_bytes += sizeof(SweepProgram);
+            CK(launch_sweep(*prog_src, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_here, d_gen_, stream_, nullptr,
+                            hcols.empty() ? nullptr : hcols.data(), d_prog));
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
             stats.sweeps++;
@@ -1770,6 +1820,8 @@ int DeviceVectorState::group_remap(size_t k, const int *rank_bits, const size_t 
     ins.push_back(a.split);
     std::sort(ins.begin(), ins.end());
     for (size_t i = 0; i <= k; ++i) a.ins[i] = ins[i];
+    static const int interleave = std::getenv("Q1T_SWAP_INTERLEAVE") ? std::atoi(std::getenv("Q1T_SWAP_INTERLEAVE")) : 1;
+    a.interleave = interleave;
     group_collect_timing();
     rc = group_barrier();                                             // every rank has finished what precedes, and published its buffer
     if (rc) return rc;

@@ -406,14 +406,16 @@ __device__ __forceinline__ unsigned long long outer_base(const uint64_t (&tab)[k
 // ---------------------------------------------------------------------------
 // INTERP = false: programs whose rounds are all ROUND_PH ladders (or that have no rounds at all):
 // the op interpreter is compiled out, which leaves a small straight-line kernel.
-template <bool INTERP, int MAXT, int MINB>
+// GPROG: the program is read from global memory (gprog) instead of the constant bank.  A batch replayed as a CUDA
+// graph keeps its programs device-resident, so a replay consists of kernel nodes only -- no 33 KB upload per sweep.
+template <bool INTERP, int MAXT, int MINB, bool GPROG>
 __global__ void __launch_bounds__(MAXT, MINB)
 sweep_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
-             const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx)
+             const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx, const SweepProgram *__restrict__ gprog)
 {
     extern __shared__ double2 tile[];
 
-    const SweepProgram &P = c_prog;
+    const SweepProgram &P = *(GPROG ? gprog : &c_prog);
     const int T = P.T, TB = P.TB;
     const unsigned tid = threadIdx.x;
     const unsigned long long o = blockIdx.x;
@@ -1199,7 +1201,7 @@ bool tma_can_encode(const SweepProgram &prog, const double2 *const *h_src_cols, 
 
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
-                         double *d_leaf_out, const double2 *const *h_src_cols)
+                         double *d_leaf_out, const double2 *const *h_src_cols, const SweepProgram *d_prog)
 {
     TmaMaps tmaps;
     if (prog.tma_nreq > 0) {
@@ -1207,35 +1209,45 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         if (!sweep_uses_ladder_kernel(prog) || prog.generate || prog.sup_mode || !tma_make_maps(prog, h_src_cols, ncols, tmaps))
             return cudaErrorInvalidValue;
     } else std::memset(&tmaps, 0, sizeof tmaps);
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
+    const bool ladder = sweep_uses_ladder_kernel(prog);
+    const bool gprog = d_prog != nullptr && !ladder;          // (the ladder kernel keeps its program in the constant bank)
+    cudaError_t e = cudaSuccess;
+    if (!gprog) {
+        e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+    }
     const int he_bits = prog.TB > kThrLoBits ? prog.TB - kThrLoBits : 0;
     const size_t smem = (sizeof(double2) << prog.T) + (sizeof(double2) * (size_t)prog.nphase << he_bits);
-    static bool smem_set = false;
-    if (!smem_set) {
+    typedef void (*SweepFn)(const double2 *const *, double2 *const *, const PhaseTab *, const unsigned long long *, const SweepProgram *);
+    static const SweepFn sfn[6] = { sweep_kernel<true, kMaxThreads, 1, false>, sweep_kernel<false, kMaxThreads, 1, false>,
+                                    sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS, false>,
+                                    sweep_kernel<true, kMaxThreads, 1, true>, sweep_kernel<false, kMaxThreads, 1, true>,
+                                    sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS, true> };
+    static int sattr_dev_mask = 0;             // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((sattr_dev_mask >> (dev & 31)) & 1)) {
         const int max_smem = (int)((sizeof(double2) << kMaxTileBits) + sizeof(double2) * kMaxPhase * kHiEntries);
-        e = cudaFuncSetAttribute(sweep_kernel<true, kMaxThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(sweep_kernel<false, kMaxThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * kHiEntries));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        smem_set = true;
+        const int small_smem = (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * kHiEntries);
+        for (int v = 0; v < 6; ++v) {
+            e = cudaFuncSetAttribute(sfn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (v % 3) == 2 ? small_smem : max_smem);
+            if (e != cudaSuccess) return e;
+        }
+        for (int v = 2; v < 6; v += 3) {
+            e = cudaFuncSetAttribute(sfn[v], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
+        sattr_dev_mask |= 1 << (dev & 31);
     }
     bool ladders_only = true;
     for (int r = 0; r < prog.nrounds; ++r) ladders_only = ladders_only && prog.rounds[r].kind == ROUND_PH;
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
-    if (sweep_uses_ladder_kernel(prog)) {
+    if (ladder) {
         typedef void (*LadderFn)(const double2 *const *, double2 *const *, const PhaseTab *, const unsigned long long *, double *, const TmaMaps);
         static const LadderFn fns[2] = { ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true> };
         static int attr_dev_mask[2] = { 0, 0 };            // function attributes are per device
-        int dev = 0, nsm = 148, occ = 0;
-        cudaGetDevice(&dev);
+        int nsm = 148, occ = 0;
         const int variant = prog.tma_nreq > 0 ? 1 : 0;
         const LadderFn fn = fns[variant];
         if (!((attr_dev_mask[variant] >> (dev & 31)) & 1)) {
@@ -1261,10 +1273,8 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         fn<<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
         return cudaGetLastError();
     }
-    if (ladders_only && (int)block.x <= kSmallThreads)
-        sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
-    else if (ladders_only) sweep_kernel<false, kMaxThreads, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
-    else sweep_kernel<true, kMaxThreads, 1><<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx);
+    const int v = (ladders_only && (int)block.x <= kSmallThreads ? 2 : ladders_only ? 1 : 0) + (gprog ? 3 : 0);
+    sfn[v]<<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_prog);
     return cudaGetLastError();
 }
 
@@ -1666,7 +1676,13 @@ group_swap_kernel(double2 *__restrict__ mine, void *const *__restrict__ peer_buf
 {
     unsigned apat = 0;
     for (int j = 0; j < a.k; ++j) apat |= (unsigned)((a.rank >> a.gb[j]) & 1) << j;
-    const unsigned bpat = blockIdx.y < apat ? blockIdx.y : blockIdx.y + 1;
+    // interleave: consecutive CTAs serve different partners (all of them busy from the first wave on); else the
+    // partners are served one after the other (blockIdx.y), each as one perfect matching of the ranks
+    const unsigned npartners = (1u << a.k) - 1u;
+    const unsigned py = a.interleave ? blockIdx.x % npartners : blockIdx.y;
+    const unsigned long long bx = a.interleave ? blockIdx.x / npartners : blockIdx.x;
+    const unsigned long long gx = a.interleave ? gridDim.x / npartners : gridDim.x;
+    const unsigned bpat = py < apat ? py : py + 1;
     int partner = a.rank;
     unsigned long long mine_or = 0, theirs_or = 0;
     for (int j = 0; j < a.k; ++j) {
@@ -1681,8 +1697,8 @@ group_swap_kernel(double2 *__restrict__ mine, void *const *__restrict__ peer_buf
     const unsigned long long cur = my_mail[2 * partner + 1];          // published by the partner in the barrier before this kernel
     double2 *__restrict__ theirs = static_cast<double2 *>(peer_buf[2 * partner + (int)(cur & 1ull)]);
     const unsigned long long npairs = 1ull << (a.n - a.k - 1);
-    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < npairs;
-         t += (unsigned long long)gridDim.x * blockDim.x) {
+    for (unsigned long long t = bx * (unsigned long long)blockDim.x + threadIdx.x; t < npairs;
+         t += gx * blockDim.x) {
         unsigned long long base = t;
         for (int i = 0; i <= a.k; ++i) {                              // open a zero bit at every swapped position (ascending)
             const int p = a.ins[i];
@@ -1702,7 +1718,9 @@ cudaError_t launch_group_swap(double2 *d_mine, void *const *d_peer_buf, const un
     const unsigned long long cap = (148ull * 16ull) / ((1u << a.k) - 1u) + 1;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
-    group_swap_kernel<<<dim3((unsigned)blocks, (1u << a.k) - 1u), 256, 0, stream>>>(d_mine, d_peer_buf, d_my_mail, a);
+    const unsigned np = (1u << a.k) - 1u;
+    if (a.interleave) group_swap_kernel<<<dim3((unsigned)blocks * np, 1), 256, 0, stream>>>(d_mine, d_peer_buf, d_my_mail, a);
+    else group_swap_kernel<<<dim3((unsigned)blocks, np), 256, 0, stream>>>(d_mine, d_peer_buf, d_my_mail, a);
     return cudaGetLastError();
 }
 

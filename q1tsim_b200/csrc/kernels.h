@@ -21,7 +21,10 @@ struct GenericGateArgs {
 // of the written column(s), 2^(n-10) doubles per column (what launch_leaf_totals would compute afterwards)
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
-                         double *d_leaf_out = nullptr, const double2 *const *h_src_cols = nullptr);
+                         double *d_leaf_out = nullptr, const double2 *const *h_src_cols = nullptr,
+                         const SweepProgram *d_prog = nullptr);
+// d_prog: device-resident copy of `prog` (the caller keeps it alive and in sync): kernels other than the ladder
+// kernel then read the program from there and nothing is uploaded -- batches replayed as CUDA graphs
 // h_src_cols: host copy of the source column pointers, needed (only) by programs in TMA layout (prog.tma_nreq > 0)
 // to encode the tensor maps; true if the driver offers cuTensorMapEncodeTiled
 bool tma_available();
@@ -52,6 +55,7 @@ struct GroupRemapArgs {
     int lp[kMaxRemapBits];           // index-bit positions of the shard they trade with
     int split;                       // index bit (not among lp) that splits the pairs between the two ranks of a pair
     int ins[kMaxRemapBits + 1];      // lp and split, ascending
+    int interleave;                  // 1: consecutive CTAs serve different partners; 0: one partner after the other
 };
 cudaError_t launch_group_barrier(unsigned long long *const *d_peer_mail, unsigned long long *d_my_mail, int P, int rank,
                                  unsigned long long epoch, unsigned long long cur, cudaStream_t stream);
