@@ -246,8 +246,11 @@ CircuitError Circuit::execute(size_t nr_shots, q1t_rng rng, const double *qubit_
     }
     c_state_.assign(nr_shots, 0);
     has_cstate_ = true;
+    fresh_state_ = true;               // identity layout: a cached lowering of the leading gate run may be replayed
     if (host_profile_on()) std::fprintf(stderr, "q1t host profile: new state + init %.0f us\n", now_us() - t0);
-    return do_execute(rng);
+    const CircuitError ce = do_execute(rng);
+    if (q_state_) q_state_->record_lowered(nullptr);
+    return ce;
 }
 
 // circuit.rs:618-641
@@ -282,7 +285,35 @@ CircuitError Circuit::do_execute(q1t_rng rng)
 #define TRY(expr) do { const int rc__ = (expr); if (rc__) return state_err(rc__); } while (0)
     const bool prof = host_profile_on();
     double t_kind[2] = { 0.0, 0.0 }, t_eval = 0.0;          // [0] gates (evaluate + lower + queue), [1] everything that observes the state
+    // The leading run of plain gates of a circuit whose parameters are all values (no pointer read at execute time,
+    // gates/parameter.rs:21-50) lowers to the same list every time it starts from a fresh state: it is lowered once
+    // and replayed (execute() of a built circuit: 480 x matrix() + classification per call otherwise).
+    size_t skip = 0;
+    std::vector<LoweredGate> *recording = nullptr;
+    if (fresh_state_) {
+        size_t run = 0;
+        bool constant = true;
+        while (run < ops_.size() && ops_[run].kind == CircuitOp::Gate) {
+            for (const Param &pr : ops_[run].gate.params) constant = constant && pr.ptr == nullptr;
+            ++run;
+        }
+        if (constant && run >= 16) {
+            if (lowered_valid_ && lowered_len_ == run) {
+                TRY(q.apply_lowered(lowered_));
+                skip = run;
+            } else {
+                lowered_.clear();
+                lowered_len_ = run;
+                recording = &lowered_;
+                q.record_lowered(recording);
+            }
+        }
+    }
+    fresh_state_ = false;
+    size_t op_index = 0;
     for (const CircuitOp &op : ops_) {
+        if (recording && op_index == lowered_len_) { q.record_lowered(nullptr); recording = nullptr; lowered_valid_ = true; }
+        if (op_index++ < skip) continue;
         const double t_op = prof ? now_us() : 0.0;
         struct Tick {
             bool on; double t0; double &acc;
@@ -343,6 +374,7 @@ CircuitError Circuit::do_execute(q1t_rng rng)
         }
     }
 #undef TRY
+    if (recording) { q.record_lowered(nullptr); lowered_valid_ = true; }        // (the circuit is gates only)
     // the reference's execute() returns with the state fully evolved; queued gates after the
     // last measurement are run here so that errors surface now
     const double t_fl = prof ? now_us() : 0.0;

@@ -98,6 +98,10 @@ private:
     bool has_cstate_ = false;
     std::vector<uint64_t> c_state_;
     std::vector<CircuitOp> ops_;
+    // lowering of the leading run of constant-parameter gates, recorded at the first execute() (do_execute)
+    std::vector<LoweredGate> lowered_;
+    size_t lowered_len_ = 0;
+    bool lowered_valid_ = false, fresh_state_ = false;
     size_t next_group_ = 0;
     size_t export_group(size_t at, const std::vector<std::string> &names, bool cq, std::string &out, CircuitError &err) const;
     CircuitError state_err(int rc);

@@ -426,6 +426,13 @@ int DeviceVectorState::lower_and_queue(const double *mat, size_t dim, const size
     std::string e;
     if (!lower_gate(reinterpret_cast<const cplx *>(mat), (int)k, phys, lg, e))
         return fail(e.find("duplicate") != std::string::npos ? Q1T_ERR_INVALID_ARGUMENT : Q1T_ERR_UNSUPPORTED, e);
+    if (lowered_rec_) lowered_rec_->push_back(lg);
+    return enqueue_lowered(lg);
+}
+
+// a gate already lowered onto physical positions: relabel (Swap), drop (identity) or queue
+int DeviceVectorState::enqueue_lowered(const LoweredGate &lg)
+{
     stats.gates_queued++;
     if (lg.kind == LoweredGate::POLY && lg.nb == 0) return Q1T_OK;          // identity
     if (lg.kind == LoweredGate::SWAP && n_ >= 5 && fuse_ && !no_relabel_) {
@@ -1112,6 +1119,22 @@ int DeviceVectorState::flush()
     return Q1T_OK;
 }
 
+// Replay of a gate run that was lowered before FROM THE IDENTITY LAYOUT (Circuit::execute on a fresh state: the
+// lowering of a gate depends on the qubit relabelling in force, and the same run from the same start reproduces
+// the same sequence of relabellings).  Skips matrix(), classification and control extraction of every gate.
+int DeviceVectorState::apply_lowered(const std::vector<LoweredGate> &lgs)
+{
+    if (!queue_cols_.empty()) { int rc = run_queue(); if (rc) return rc; }
+    for (int l = 0; l < n_; ++l)
+        if (perm_[l] != l) return fail(Q1T_ERR_INVALID_ARGUMENT, "apply_lowered: the state is not in the identity layout");
+    for (const LoweredGate &lg : lgs) {
+        int rc = enqueue_lowered(lg);
+        if (rc) return rc;
+        if (queue_.size() >= 8192) { rc = run_queue(); if (rc) return rc; }
+    }
+    return Q1T_OK;
+}
+
 // vectorstate.rs:166-178
 int DeviceVectorState::apply_gate(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc)
 {
@@ -1687,7 +1710,12 @@ int DeviceVectorState::group_export(unsigned char *handles, void **ptrs)
         double2 *b1 = nullptr;
         for (double2 *p : free_bufs_)
             if (p != b0) b1 = p;
-        if (!b1 && !want_inplace_relabel()) {
+        // a second buffer only if two shards fit (128 GiB shards relabel in place and swap in place: one buffer)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+        static const bool force_single = std::getenv("Q1T_GROUP_SINGLE_BUFFER") && std::atoi(std::getenv("Q1T_GROUP_SINGLE_BUFFER")) != 0;
+        const bool two_fit = !force_single && inplace_relabel_ <= 0 && (total_b == 0 || 2 * (sizeof(double2) << n_) <= total_b / 100 * 90);
+        if (!b1 && two_fit) {
             std::vector<double2 *> keep;
             keep.swap(free_bufs_);                       // alloc_column() must not hand b0 out again
             rc = alloc_column(&b1);

@@ -33,6 +33,8 @@ public:
 
     int apply_gate(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc);
     int apply_unary_gate_all(const double *mat, size_t dim, const char *desc);
+    int apply_lowered(const std::vector<LoweredGate> &lgs);
+    void record_lowered(std::vector<LoweredGate> *rec) { lowered_rec_ = rec; }
     int apply_conditional_gate(const uint8_t *control, size_t ncontrol, const double *mat, size_t dim,
                                const size_t *bits, size_t k, const char *desc);
     int measure_into(size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng, bool collapse);
@@ -154,6 +156,8 @@ private:
                        bool leaf_totals_ready = false);
     int ensure_scratch(size_t ncols);
     int lower_and_queue(const double *mat, size_t dim, const size_t *bits, size_t k, const char *desc);
+    int enqueue_lowered(const LoweredGate &lg);
+    std::vector<LoweredGate> *lowered_rec_ = nullptr;
     void time_begin();
     void time_end(double &acc);
 };
