@@ -1,4 +1,5 @@
 // capi.cpp -- extern "C" inner ABI (include/q1t_engine.h) over DeviceVectorState.
+#include <mutex>
 #include <cstring>
 #include <new>
 #include <string>
@@ -66,14 +67,57 @@ int q1t_apply_gates(q1t_state *st, size_t ngates, const double *mats, const size
 {
     ST_OR_FAIL;
     if (ngates && (!mats || !dims || !bits || !nbits)) return Q1T_ERR_INVALID_ARGUMENT;
+    // A batch applied to a state in the identity layout lowers to the same list every time (the lowering of a gate depends
+    // only on its matrix, its bits and the relabelling in force): batches of >= 16 gates are lowered once and replayed,
+    // keyed by a hash of everything the caller passed (the taped schedules of the sharded runs come back every step).
+    struct Cached { uint64_t key; size_t n, ngates; std::vector<q1t::LoweredGate> lowered; uint64_t stamp; };
+    static std::mutex mu;
+    static std::vector<Cached> cache;
+    static uint64_t clock = 0;
+    const bool cacheable = ngates >= 16 && st->impl->layout_is_identity();
+    uint64_t key = 1469598103934665603ull;
+    if (cacheable) {
+        auto mix = [&](const void *p, size_t nbytes) {
+            const unsigned char *b = static_cast<const unsigned char *>(p);
+            for (size_t i = 0; i < nbytes; ++i) { key ^= b[i]; key *= 1099511628211ull; }
+        };
+        size_t nm = 0, nb = 0;
+        for (size_t g = 0; g < ngates; ++g) { nm += 2 * dims[g] * dims[g]; nb += nbits[g]; }
+        mix(dims, sizeof(size_t) * ngates);
+        mix(nbits, sizeof(size_t) * ngates);
+        mix(bits, sizeof(size_t) * nb);
+        mix(mats, sizeof(double) * nm);
+        std::vector<q1t::LoweredGate> hit;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (Cached &c : cache)
+                if (c.key == key && c.ngates == ngates && c.n == st->impl->nr_bits()) { hit = c.lowered; c.stamp = ++clock; break; }
+        }
+        if (!hit.empty()) return st->impl->apply_lowered(hit);
+    }
+    std::vector<q1t::LoweredGate> rec;
+    if (cacheable) st->impl->record_lowered(&rec);
     size_t moff = 0, boff = 0;
-    for (size_t g = 0; g < ngates; ++g) {
-        const int rc = st->impl->apply_gate(mats + moff, dims[g], bits + boff, nbits[g], "gate");
-        if (rc) return rc;
+    int rc = Q1T_OK;
+    for (size_t g = 0; g < ngates && !rc; ++g) {
+        rc = st->impl->apply_gate(mats + moff, dims[g], bits + boff, nbits[g], "gate");
         moff += 2 * dims[g] * dims[g];
         boff += nbits[g];
     }
-    return Q1T_OK;
+    if (cacheable) {
+        st->impl->record_lowered(nullptr);
+        if (!rc && rec.size() == ngates) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (cache.size() >= 16) {
+                size_t lru = 0;
+                for (size_t i = 1; i < cache.size(); ++i)
+                    if (cache[i].stamp < cache[lru].stamp) lru = i;
+                cache.erase(cache.begin() + lru);
+            }
+            cache.push_back({ key, st->impl->nr_bits(), ngates, rec, ++clock });
+        }
+    }
+    return rc;
 }
 int q1t_apply_unary_gate_all(q1t_state *st, const double *m, size_t dim, const char *desc)
 {

@@ -742,6 +742,17 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
         const bool try_leaf = last && final_relabel && want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(ps.prog);
         // with the layout already canonical the last sweep is still sent through the (out-of-place) staged store when a
         // measurement follows: its store pass then delivers the canonical leaf totals, which saves the read pass
+        bool leaf_inplace = false;
+        if (last && final_relabel && ident && try_leaf && which.size() == cols_.size() && want_inplace_relabel()) {
+            // no room for a second buffer (128 GiB shards): the same fused store pass, launched in place -- a tile is read
+            // completely before its CTA stores it, and with the layout unchanged it stores exactly what it has read
+            std::vector<int> dstpos(n_);
+            for (int l = 0; l < n_; ++l) dstpos[l] = l;
+            const SweepProgram before = ps.prog;
+            set_relabel(ps.prog, dstpos, true);
+            if (ps.prog.leaf_fuse && !ensure_scratch(which.size())) { ps.prog.direct_store = 0; leaf_inplace = true; }
+            else ps.prog = before;
+        }
         if (last && final_relabel && (!ident || try_leaf) && which.size() == cols_.size() && !want_inplace_relabel()) {
             std::vector<int> dstpos(n_);
             for (int l = 0; l < n_; ++l) dstpos[perm_[l]] = l;
@@ -772,7 +783,12 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
                 }
             }
             if (ok && __builtin_popcount(tgt) >= 2) ps.prog.direct_store = 0;
-        }
+            if (std::getenv("Q1T_DEBUG_BCAST"))
+                std::fprintf(stderr, "q1t bcast check: sweep %zu ok %d tgt %x direct_store %d nrounds %d smask0 %x nsteps0 %d\n", si, (int)ok, tgt,
+                             ps.prog.direct_store, ps.prog.nrounds, ps.prog.rounds[0].smask, ps.prog.rounds[0].nsteps);
+        } else if (std::getenv("Q1T_DEBUG_BCAST"))
+            std::fprintf(stderr, "q1t bcast skip: sweep %zu relabel %d sup_mode %d generate %d direct_store %d nrounds %d\n", si, (int)relabel,
+                         ps.prog.sup_mode, ps.prog.generate, ps.prog.direct_store, ps.prog.nrounds);
         // dense ladder sweeps take their tiles by TMA (planner.cpp apply_tma_layout, kernels.cu ladder_kernel)
         const bool tma_ok = tma_ && !ps.prog.generate && ps.prog.sup_mode == 0 && sweep_uses_ladder_kernel(ps.prog) && tma_available();
         if (!relabel) {
@@ -797,8 +813,9 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
                 }
             }
             if (!d_prog) stats.h2d_bytes += sizeof(SweepProgram);
-            CK(launch_sweep(*prog_src, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_here, d_gen_, stream_, nullptr,
+            CK(launch_sweep(*prog_src, d_colptrs_, d_colptrs_, (int)which.size(), d_ptabs_here, d_gen_, stream_, leaf_inplace ? d_leaf_ : nullptr,
                             hcols.empty() ? nullptr : hcols.data(), d_prog));
+            if (leaf_inplace) leaf_fused_ = true;
             time_end(stats.sweep_ms);
             stats.kernel_launches++;
             stats.sweeps++;
@@ -924,24 +941,50 @@ int DeviceVectorState::run_queue(bool final_relabel)
                         return rcs;
                     }
             }
+            // Candidates: {64-byte, 128-byte tiles} x {greedy, balanced packing}.  A dense batch is judged by sweeps, then
+            // rounds.  A batch that starts from basis states and runs tracked (every sweep in the ladder kernel) moves only
+            // the support of the state, so it is judged by the BYTES its sweeps will move: the packing decides how much of
+            // the growth of the support falls into the last sweeps (a plan that leaves three low bits for a last small
+            // sweep reads and writes the whole state once more).
             std::vector<PlannedSweep> plan[2];
-            uint64_t cost[2][2];
-            int pick = 0;
+            std::vector<PlannedSweep> best;
+            uint64_t best_cost[3] = { ~0ull, ~0ull, ~0ull };
+            auto tracked_bytes = [&](const std::vector<PlannedSweep> &pl) {
+                uint64_t pinned = n_ >= 64 ? ~0ull : ((1ull << n_) - 1ull), total = 0;
+                for (size_t si = 0; si < pl.size(); ++si) {
+                    const SweepProgram &P = pl[si].prog;
+                    int pinned_outer = 0, pinned_all = 0;
+                    for (int i = 0; i < P.n_outer; ++i) pinned_outer += (int)((pinned >> P.osrc[i]) & 1ull);
+                    for (int b = 0; b < n_; ++b) pinned_all += (int)((pinned >> b) & 1ull);
+                    const bool last = si + 1 == pl.size();
+                    const uint64_t tiles_written = last ? (1ull << P.n_outer) : (1ull << (P.n_outer - pinned_outer));
+                    // a live element whose lowest index bits are still pinned sits alone in its 32-byte sector / 64-byte burst
+                    const uint64_t per_read = (pinned & 1ull) ? ((pinned & 2ull) ? 64 : 32) : 16;
+                    total += (tiles_written << P.T) * 16ull + (si == 0 ? 0ull : (1ull << (n_ - pinned_all)) * per_read);
+                    pinned &= ~pl[si].touched;
+                }
+                return total;
+            };
             for (int attempt = sparse_start ? 0 : 1; attempt < 2; ++attempt) {
                 const int cbits = attempt == 0 ? 2 : (int)coalesce_bits_;
                 for (int b = 0; b < 2; ++b) {
                     Planner trial(n_, (int)tile_bits_, cbits, b != 0);
                     for (const LoweredGate &g : q) trial.add(g);
                     trial.finish();
-                    cost[b][0] = trial.stats.sweeps;
-                    cost[b][1] = trial.stats.rounds;
                     plan[b] = trial.take();
+                    bool all_ladder = true;
+                    for (const PlannedSweep &ps : plan[b]) all_ladder = all_ladder && sweep_uses_ladder_kernel(ps.prog);
+                    if (attempt == 0 && !all_ladder) continue;        // a 64-byte plan only pays when it runs tracked
+                    const bool tracked = sparse_start && all_ladder;
+                    const uint64_t c[3] = { tracked ? tracked_bytes(plan[b]) : ~0ull - 1, trial.stats.sweeps, trial.stats.rounds };
+                    if (c[0] < best_cost[0] || (c[0] == best_cost[0] && (c[1] < best_cost[1] || (c[1] == best_cost[1] && c[2] < best_cost[2])))) {
+                        best_cost[0] = c[0]; best_cost[1] = c[1]; best_cost[2] = c[2];
+                        best = plan[b];
+                    }
                 }
-                pick = (cost[1][0] < cost[0][0] || (cost[1][0] == cost[0][0] && cost[1][1] < cost[0][1])) ? 1 : 0;
-                bool all_ladder = true;
-                for (const PlannedSweep &ps : plan[pick]) all_ladder = all_ladder && sweep_uses_ladder_kernel(ps.prog);
-                if (attempt == 0 && all_ladder) break;            // the 64-byte plan will be tracked
             }
+            plan[0].swap(best);
+            const int pick = 0;
             if (q.size() >= 16) {
                 std::lock_guard<std::mutex> lk(g_plan_mu);
                 if (g_plan_cache.size() >= kPlanCacheMax) {       // evict the least recently used plan

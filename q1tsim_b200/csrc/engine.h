@@ -35,6 +35,12 @@ public:
     int apply_unary_gate_all(const double *mat, size_t dim, const char *desc);
     int apply_lowered(const std::vector<LoweredGate> &lgs);
     void record_lowered(std::vector<LoweredGate> *rec) { lowered_rec_ = rec; }
+    bool layout_is_identity() const
+    {
+        for (int l = 0; l < n_; ++l)
+            if (perm_[l] != l) return false;
+        return queue_cols_.empty();
+    }
     int apply_conditional_gate(const uint8_t *control, size_t ncontrol, const double *mat, size_t dim,
                                const size_t *bits, size_t k, const char *desc);
     int measure_into(size_t qbit, size_t cbit, uint64_t *res, size_t res_len, q1t_rng rng, bool collapse);
