@@ -315,10 +315,12 @@ struct LadderStep<J, -1> {
         for (int h = 0; h < (kSlots >> (J + 1)); ++h) {
             const int s0 = (h << (J + 1)) | u, s1 = s0 | (1 << J);
             const double2 x = a[s0], y = a[s1];
-            const double tr = fma(y.x, f.x, -(y.y * f.y));
-            const double ti = fma(y.x, f.y, y.y * f.x);
-            a[s0] = make_double2(x.x + tr, x.y + ti);
-            a[s1] = make_double2(x.x - tr, x.y - ti);
+            // (x + f y, x - f y) in six FMAs instead of 2 mul + 2 fma + 4 add: the sum by two chained FMAs per
+            // component, the difference as 2 x - sum (one FMA).  The FP64 pipe is the busiest unit of the kernel.
+            const double pr = fma(y.x, f.x, fma(-y.y, f.y, x.x));
+            const double pi = fma(y.x, f.y, fma(y.y, f.x, x.y));
+            a[s0] = make_double2(pr, pi);
+            a[s1] = make_double2(fma(2.0, x.x, -pr), fma(2.0, x.y, -pi));
         }
     }
 };
