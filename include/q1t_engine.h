@@ -171,6 +171,23 @@ int    q1t_group_open(q1t_state *st, size_t nranks, size_t rank, const unsigned 
 int    q1t_group_barrier(q1t_state *st);
 int    q1t_group_remap(q1t_state *st, size_t k, const int *rank_bits, const size_t *local_qubits);
 int    q1t_group_close(q1t_state *st);
+/* ---- a state sharded over the devices of ONE process (csrc/sharded.h): the QuState calls a circuit beyond one GPU needs ----
+ * `devices`: nr_devices = 2^g entries, they may repeat (several shards on one GPU).  Shard r holds the amplitudes whose
+ * top g index bits equal r.  Starts as |0..0> (VectorState::new, vectorstate.rs:41-53).  q1t_sharded_set_initial_layout
+ * (only on the fresh state): dest[q] = the qubit the data labelled q ends as after the Swap relabels of the run to come;
+ * the run then ends in the canonical layout (|0..0> is symmetric, any layout is a legal start). */
+typedef struct q1t_sharded q1t_sharded;
+int    q1t_sharded_new(size_t nr_bits, size_t nr_shots, size_t nr_devices, const int *devices, q1t_sharded **out);
+void   q1t_sharded_free(q1t_sharded *h);
+int    q1t_sharded_apply_gate(q1t_sharded *h, const double *matrix, size_t matrix_dim, const size_t *bits, size_t nr_bits, const char *desc);
+int    q1t_sharded_set_initial_layout(q1t_sharded *h, const int *dest, size_t n);
+int    q1t_sharded_measure_all_into(q1t_sharded *h, const size_t *cbits, size_t n, uint64_t *res, size_t res_len, q1t_rng rng);
+int    q1t_sharded_peek_all_into(q1t_sharded *h, const size_t *cbits, size_t n, uint64_t *res, size_t res_len, q1t_rng rng);
+int    q1t_sharded_reset_all(q1t_sharded *h);
+int    q1t_sharded_read_amplitudes(q1t_sharded *h, size_t offset, size_t len, double *out);   /* canonical index order */
+int    q1t_sharded_column_total(q1t_sharded *h, double *out);
+int    q1t_sharded_counters(q1t_sharded *h, uint64_t *out3);       /* remaps, exchanged qubits, local relabels */
+const char *q1t_sharded_last_error(q1t_sharded *h);               /* h = NULL: error of the last failed q1t_sharded_new on this thread */
 /* rand 0.7 Uniform(0,total) draws as WeightedIndex::sample makes them (vectorstate.rs:126) */
 double q1t_uniform_draw(q1t_rng rng, double total);
 void   q1t_uniform_draws(q1t_rng rng, double total, size_t n, double *out);

@@ -13,7 +13,7 @@
  *   - extra entry points: circuit_add_matrix_gate, circuit_add_composite_gate, circuit_add_loop_gate,
  *     circuit_execute_with_rng,
  *     circuit_reexecute_with_rng, circuit_histogram_u64, circuit_engine_stats,
- *     circuit_set_device, circuit_state.
+ *     circuit_set_device, circuit_set_devices (+ circuit_sharded_*), circuit_state.
  * Ownership (ffi.rs:139-169): every result_t is returned by value and owns
  * `data`; the caller passes it to result_free exactly once.
  */
@@ -96,6 +96,12 @@ size_t     circuit_cstate_into(const circuit_t *ptr, uint64_t *out, size_t out_l
 /* preset the classical register (tests of circuit.rs:1628-1650 set c_state directly) */
 result_t   circuit_set_cstate(circuit_t *ptr, const uint64_t *words, size_t n);
 int        circuit_set_device(circuit_t *ptr, int device);
+/* execute() on a state sharded over n devices of this process (power of two >= 2, devices may repeat; n = 0: back to one
+ * device): gates, measure_all / peek_all in any basis, barriers -- the circuits of BASELINE config 5 (34-36 qubits on
+ * 8 B200).  The reference has no analogue (its VectorState is one host array, vectorstate.rs:25-35). */
+int        circuit_set_devices(circuit_t *ptr, const int *devices, size_t n);
+int        circuit_sharded_amplitudes(circuit_t *ptr, size_t offset, size_t len, double *out);   /* canonical order, re/im pairs */
+int        circuit_sharded_counters(circuit_t *ptr, uint64_t *out3);   /* remaps, exchanged qubits, local relabels of the last run */
 q1t_state *circuit_state(circuit_t *ptr);          /* borrowed: the live q_state, NULL before execute */
 int        circuit_engine_stats(circuit_t *ptr, q1t_stats *out);
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libq1tsim.so")
-SOURCES = ["kernels.cu", "engine.cu", "planner.cpp", "sampling.cpp", "gates.cpp", "capi.cpp", "circuit.cpp", "composite.cpp", "export.cpp", "latex.cpp", "ffi_compat.cpp"]
+SOURCES = ["kernels.cu", "engine.cu", "planner.cpp", "sampling.cpp", "gates.cpp", "capi.cpp", "circuit.cpp", "sharded.cpp", "composite.cpp", "export.cpp", "latex.cpp", "ffi_compat.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ccbin", "g++",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-cudart", "static"]
 

@@ -352,6 +352,34 @@ class Circuit:
     def latex(self):
         return _unpack(self._L.circuit_latex(self._p))
 
+    def set_devices(self, devices):
+        """execute() on a state sharded over these devices of this process (power of two >= 2; may repeat a device)"""
+        L = self._L
+        L.circuit_set_devices.restype = C.c_int
+        L.circuit_set_devices.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_size_t]
+        arr = (C.c_int * max(len(devices), 1))(*[int(d) for d in devices])
+        if L.circuit_set_devices(self._p, arr, len(devices)):
+            raise CircuitError("set_devices: the number of devices must be 0 or a power of two >= 2")
+
+    def sharded_amplitudes(self, offset=0, length=None):
+        L = self._L
+        L.circuit_sharded_amplitudes.restype = C.c_int
+        L.circuit_sharded_amplitudes.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_double)]
+        n = int(self._L.circuit_nr_qbits(self._p))
+        length = (1 << n) - offset if length is None else length
+        out = np.zeros(2 * length, dtype=np.float64)
+        if L.circuit_sharded_amplitudes(self._p, offset, length, out.ctypes.data_as(C.POINTER(C.c_double))):
+            raise CircuitError("no sharded state (set_devices + execute first)")
+        return out.view(np.complex128)
+
+    def sharded_counters(self):
+        L = self._L
+        L.circuit_sharded_counters.restype = C.c_int
+        L.circuit_sharded_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        out = (C.c_uint64 * 3)()
+        L.circuit_sharded_counters(self._p, out)
+        return {"remaps": int(out[0]), "exchanged_qubits": int(out[1]), "local_relabels": int(out[2])}
+
     def engine_stats(self):
         s = E.Stats()
         rc = self._L.circuit_engine_stats(self._p, C.byref(s))

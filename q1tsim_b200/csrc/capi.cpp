@@ -10,6 +10,7 @@
 using q1t::DeviceVectorState;
 
 #include "capi_internal.h"
+#include "sharded.h"
 
 static thread_local std::string g_ctor_error;
 
@@ -444,6 +445,59 @@ int q1t_plan_layout(size_t *out, size_t n)
     for (size_t i = 0; i < n && i < 10; ++i) out[i] = v[i];
     return Q1T_OK;
 }
+
+// ---- sharded state: P shards on the devices of one process (sharded.h) ----
+struct q1t_sharded { std::unique_ptr<q1t::ShardedVectorState> impl; };
+static thread_local std::string g_sharded_err;
+int q1t_sharded_new(size_t nr_bits, size_t nr_shots, size_t nr_devices, const int *devices, q1t_sharded **out)
+{
+    if (!out || !devices || nr_devices < 2) { g_sharded_err = "q1t_sharded_new: at least two devices (they may repeat)"; return Q1T_ERR_INVALID_ARGUMENT; }
+    q1t_sharded *h = new q1t_sharded;
+    h->impl.reset(new q1t::ShardedVectorState(nr_bits, nr_shots, std::vector<int>(devices, devices + nr_devices)));
+    const int rc = h->impl->init_zero_state();
+    if (rc) { g_sharded_err = h->impl->last_error(); delete h; return rc; }
+    *out = h;
+    return Q1T_OK;
+}
+void q1t_sharded_free(q1t_sharded *h) { delete h; }
+#define SH_OR_FAIL if (!h) return Q1T_ERR_INVALID_ARGUMENT
+int q1t_sharded_apply_gate(q1t_sharded *h, const double *m, size_t dim, const size_t *bits, size_t k, const char *desc)
+{
+    SH_OR_FAIL;
+    return h->impl->apply_gate(m, dim, bits, k, desc);
+}
+int q1t_sharded_set_initial_layout(q1t_sharded *h, const int *dest, size_t n)
+{
+    SH_OR_FAIL;
+    if (!dest) return Q1T_ERR_INVALID_ARGUMENT;
+    return h->impl->set_initial_layout(std::vector<int>(dest, dest + n));
+}
+int q1t_sharded_measure_all_into(q1t_sharded *h, const size_t *cbits, size_t n, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    SH_OR_FAIL;
+    return h->impl->measure_all_into(cbits, n, res, res_len, rng, true);
+}
+int q1t_sharded_peek_all_into(q1t_sharded *h, const size_t *cbits, size_t n, uint64_t *res, size_t res_len, q1t_rng rng)
+{
+    SH_OR_FAIL;
+    return h->impl->measure_all_into(cbits, n, res, res_len, rng, false);
+}
+int q1t_sharded_reset_all(q1t_sharded *h) { SH_OR_FAIL; return h->impl->reset_all(); }
+int q1t_sharded_read_amplitudes(q1t_sharded *h, size_t offset, size_t len, double *out)
+{
+    SH_OR_FAIL;
+    if (!out) return Q1T_ERR_INVALID_ARGUMENT;
+    return h->impl->read_amplitudes(offset, len, out);
+}
+int q1t_sharded_column_total(q1t_sharded *h, double *out) { SH_OR_FAIL; return out ? h->impl->column_total(out) : Q1T_ERR_INVALID_ARGUMENT; }
+int q1t_sharded_counters(q1t_sharded *h, uint64_t *out3)
+{
+    SH_OR_FAIL;
+    if (!out3) return Q1T_ERR_INVALID_ARGUMENT;
+    out3[0] = h->impl->remaps; out3[1] = h->impl->exchanges; out3[2] = h->impl->local_relabels;
+    return Q1T_OK;
+}
+const char *q1t_sharded_last_error(q1t_sharded *h) { return h ? h->impl->last_error() : g_sharded_err.c_str(); }
 
 int q1t_device_count(void)
 {

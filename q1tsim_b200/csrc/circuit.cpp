@@ -233,8 +233,115 @@ static double now_us()
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// execute() on a state sharded over several devices (circuit.rs:562-600 for circuits beyond one GPU).  The op list is known
+// in full: it is walked on a data-less ShardedVectorState from two initial layouts -- |0..0> is symmetric, so any layout
+// is a legal start -- and run from the cheaper one (see q1tsim_b200/sharded.py run_ops; a QFT ends canonical without a
+// single exchange).
+CircuitError Circuit::execute_sharded(size_t nr_shots, q1t_rng rng)
+{
+    static const double H[8] = { 0.70710678118654752440, 0, 0.70710678118654752440, 0, 0.70710678118654752440, 0, -0.70710678118654752440, -0.0 };
+    static const double S[8] = { 1, 0, 0, 0, 0, 0, 0, 1 };
+    static const double SDG[8] = { 1, 0, 0, 0, 0, 0, -0.0, -1 };
+    static const double SWAPM[32] = { 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0 };
+    for (const CircuitOp &op : ops_)
+        if (op.kind != CircuitOp::Gate && op.kind != CircuitOp::MeasureAll && op.kind != CircuitOp::PeekAll && op.kind != CircuitOp::Barrier)
+            return mkerr(Q1T_ERR_UNSUPPORTED, "a circuit on a sharded state may hold gates, measure_all / peek_all and barriers");
+    // a collapsing measure_all leaves one basis-state column per outcome; the gates that restore an X or Y basis afterwards
+    // (circuit.rs:705-735) would have to remap a multi-column state, which the peer group does not do
+    for (const CircuitOp &op : ops_)
+        if (op.kind == CircuitOp::MeasureAll && op.basis != Basis::Z)
+            return mkerr(Q1T_ERR_UNSUPPORTED, "measure_all in the X or Y basis is not available on a sharded state (peek_all is; measure_all in the Z basis is)");
+    q_state_.reset();
+    // matrices of the gates (parameters are read now, at execution time)
+    std::vector<std::vector<std::complex<double>>> mats(ops_.size());
+    size_t nprefix = 0;
+    bool in_prefix = true;
+    for (size_t t = 0; t < ops_.size(); ++t) {
+        if (ops_[t].kind != CircuitOp::Gate) { in_prefix = false; continue; }
+        if (ops_[t].gate.evaluate(mats[t]) < 0) return mkerr(Q1T_ERR_PARSE, "invalid gate");
+        if (in_prefix) nprefix = t + 1;
+    }
+    // dest[q]: the logical qubit the data labelled q ends as after the Swap relabels of the leading gate run
+    std::vector<int> dest(nr_qbits_);
+    for (size_t q = 0; q < nr_qbits_; ++q) dest[q] = (int)q;
+    for (size_t t = nprefix; t-- > 0;) {
+        const CircuitOp &op = ops_[t];
+        if (op.bits.size() == 2 && mats[t].size() == 16 && std::memcmp(mats[t].data(), SWAPM, sizeof SWAPM) == 0)
+            std::swap(dest[op.bits[0]], dest[op.bits[1]]);
+    }
+    auto walk = [&](ShardedVectorState &st, size_t upto, uint64_t *res, size_t nres) -> int {
+        for (size_t t = 0; t < upto; ++t) {
+            const CircuitOp &op = ops_[t];
+            int rc = Q1T_OK;
+            if (op.kind == CircuitOp::Gate)
+                rc = st.apply_gate(reinterpret_cast<const double *>(mats[t].data()), (size_t)1 << op.bits.size(), op.bits.data(), op.bits.size(),
+                                   op.gate.description().c_str());
+            else if (op.kind == CircuitOp::MeasureAll || op.kind == CircuitOp::PeekAll) {
+                if (op.basis == Basis::X) rc = st.apply_unary_gate_all(H, 2, "H");
+                if (op.basis == Basis::Y) { rc = st.apply_unary_gate_all(SDG, 2, "Sdg"); if (!rc) rc = st.apply_unary_gate_all(H, 2, "H"); }
+                if (!rc) rc = st.measure_all_into(op.bits.data(), op.bits.size(), res, nres, rng, op.kind == CircuitOp::MeasureAll);
+                if (!rc && op.basis == Basis::X) rc = st.apply_unary_gate_all(H, 2, "H");
+                if (!rc && op.basis == Basis::Y) { rc = st.apply_unary_gate_all(H, 2, "H"); if (!rc) rc = st.apply_unary_gate_all(S, 2, "S"); }
+            }
+            if (rc) return rc;
+        }
+        return Q1T_OK;
+    };
+    bool use_dest = false;
+    {
+        bool ident = true;
+        for (size_t q = 0; q < nr_qbits_; ++q) ident = ident && dest[q] == (int)q;
+        if (!ident && nprefix > 0) {
+            uint64_t cost[2] = { 0, 0 };
+            for (int c = 0; c < 2; ++c) {
+                ShardedVectorState dry(nr_qbits_, nr_shots, devices, true);
+                if (dry.init_zero_state()) return mkerr(Q1T_ERR_INVALID_ARGUMENT, dry.last_error());
+                if (c == 1 && dry.set_initial_layout(dest)) return mkerr(Q1T_ERR_INVALID_ARGUMENT, dry.last_error());
+                const int rc = walk(dry, nprefix, nullptr, 0);
+                if (rc) return mkerr(rc, dry.last_error());
+                if (dry.canonicalize()) return mkerr(Q1T_ERR_INVALID_ARGUMENT, dry.last_error());
+                cost[c] = dry.remaps * 1000 + dry.local_relabels;
+            }
+            use_dest = cost[1] < cost[0];
+        }
+    }
+    // the shards, their registered buffers and the peer mappings are kept from one execute() to the next (a fresh
+    // state is |0..0> either way: reset_all)
+    int rc;
+    if (s_state_ && s_state_->nr_shots() == nr_shots && s_state_->nr_shards() == devices.size() && s_devices_ == devices)
+        rc = s_state_->reset_all();
+    else {
+        s_state_.reset();
+        s_state_.reset(new ShardedVectorState(nr_qbits_, nr_shots, devices));
+        s_devices_ = devices;
+        rc = s_state_->init_zero_state();
+    }
+    if (!rc && use_dest) rc = s_state_->set_initial_layout(dest);
+    if (rc) {
+        CircuitError e = mkerr(rc, s_state_->last_error());
+        s_state_.reset();
+        has_cstate_ = false;
+        return e;
+    }
+    c_state_.assign(nr_shots, 0);
+    has_cstate_ = true;
+    rc = walk(*s_state_, ops_.size(), c_state_.data(), c_state_.size());
+    if (!rc) rc = s_state_->canonicalize();         // the reference's execute() returns with the state fully evolved
+    sharded_counters[0] = s_state_->remaps;
+    sharded_counters[1] = s_state_->exchanges;
+    sharded_counters[2] = s_state_->local_relabels;
+    if (rc) return mkerr(rc, s_state_->last_error());
+    return ok();
+}
+
 CircuitError Circuit::execute(size_t nr_shots, q1t_rng rng, const double *qubit_coefs)
 {
+    if (devices.size() >= 2) {
+        if (qubit_coefs) return mkerr(Q1T_ERR_UNSUPPORTED, "execute_with a product state is not available on a sharded state");
+        return execute_sharded(nr_shots, rng);
+    }
+    s_state_.reset();
+    s_devices_.clear();
     const double t0 = host_profile_on() ? now_us() : 0.0;
     q_state_.reset(new DeviceVectorState(nr_qbits_, nr_shots, device));
     const int rc = qubit_coefs ? q_state_->init_from_qubit_coefs(qubit_coefs) : q_state_->init_zero_state();

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "sharded.h"
 
 namespace q1t {
 
@@ -82,6 +83,7 @@ public:
 
     bool executed() const { return has_cstate_; }
     const std::vector<uint64_t> &cstate() const { return c_state_; }
+    ShardedVectorState *sharded_state() { return s_state_.get(); }
     CircuitError set_cstate(const uint64_t *w, size_t n);
     std::map<uint64_t, size_t> histogram() const;
     std::map<std::string, size_t> histogram_string() const;
@@ -91,6 +93,10 @@ public:
     CircuitError latex(std::string &out) const;          // latex.cpp: circuit.rs:1148-1231
     DeviceVectorState *state() { return q_state_.get(); }
     int device = 0;
+    // >= 2 entries (they may repeat): execute() runs on a state sharded over these devices of this process
+    // (ShardedVectorState): gates, measure_all / peek_all in any basis, barriers
+    std::vector<int> devices;
+    uint64_t sharded_counters[3] = { 0, 0, 0 };      // remaps, exchanged qubits, local relabels of the last sharded run
 
 private:
     size_t nr_qbits_, nr_cbits_;
@@ -98,6 +104,9 @@ private:
     bool has_cstate_ = false;
     std::vector<uint64_t> c_state_;
     std::vector<CircuitOp> ops_;
+    std::unique_ptr<ShardedVectorState> s_state_;
+    std::vector<int> s_devices_;
+    CircuitError execute_sharded(size_t nr_shots, q1t_rng rng);
     // lowering of the leading run of constant-parameter gates, recorded at the first execute() (do_execute)
     std::vector<LoweredGate> lowered_;
     size_t lowered_len_ = 0;

@@ -563,7 +563,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     // if it comes from the plan cache (the key names the gate list), touches no lazy column half-way, and restores no
     // layout (the relabelling path allocates).  The graph is keyed by everything the issued work depends on.
     const bool may_relabel = final_relabel && (!ident || (want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(sweeps.back().prog)));
-    const bool graph_try = graphs_ && !timing && cur_plan_key_ != 0 && sweeps.size() >= 4 && n_ <= 26 && !tma_ &&
+    const bool graph_try = graphs_ && !timing && cur_plan_key_ != 0 && sweeps.size() >= 4 && n_ <= 26 && !tma_ && !cprog_device_shared(device_) &&
                            (generate || !any_basis) && !may_relabel;
     uint64_t gkey = 0;
     if (graph_try) {
@@ -1519,6 +1519,15 @@ int DeviceVectorState::leaf_totals(size_t qbit, double *out)
 // continues the chain over blocks in rank order
 int DeviceVectorState::block_totals(size_t qbit, double *out)
 {
+    int rc = block_totals_launch(qbit);
+    if (rc) return rc;
+    return block_totals_fetch(out);
+}
+
+// the two halves of block_totals(): everything enqueued / the copy to the host and the wait.  A host layer that drives
+// several shards from one thread launches on all of them before it waits for any.
+int DeviceVectorState::block_totals_launch(size_t qbit)
+{
     if (nr_leaves() < kCanonBlock) return fail(Q1T_ERR_UNSUPPORTED, "block_totals: shards below 2^20 amplitudes chain their leaves on the host");
     // as in measure_all_into: the last queued sweep may produce the leaf totals in its store pass
     want_leaf_fusion_ = fuse_leaf_totals_ && qbit >= (size_t)n_ && cols_.size() == 1;
@@ -1538,7 +1547,6 @@ int DeviceVectorState::block_totals(size_t qbit, double *out)
     rc = upload_colptrs(all);
     if (rc) return rc;
     const uint64_t mask = qbit < (size_t)n_ ? 1ull << (n_ - 1 - (int)qbit) : 0ull;
-    const size_t nb = nr_leaves() / kCanonBlock;
     time_begin();
     if (!leaf_ready) {
         CK(launch_leaf_totals(d_colptrs_, (int)all.size(), d_leaf_, n_, mask, 0, stream_));
@@ -1548,7 +1556,14 @@ int DeviceVectorState::block_totals(size_t qbit, double *out)
     CK(launch_block_scan(d_leaf_, d_block_, (int)all.size(), n_, stream_));
     time_end(stats.read_ms);
     stats.kernel_launches++;
-    CK(cudaMemcpyAsync(out, d_block_, sizeof(double) * all.size() * nb, cudaMemcpyDeviceToHost, stream_));
+    return Q1T_OK;
+}
+
+int DeviceVectorState::block_totals_fetch(double *out)
+{
+    const size_t nb = nr_leaves() / kCanonBlock;
+    CK(cudaSetDevice(device_));
+    CK(cudaMemcpyAsync(out, d_block_, sizeof(double) * cols_.size() * nb, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     return Q1T_OK;
 }
@@ -1559,6 +1574,7 @@ int DeviceVectorState::resolve_draws_blocks(size_t col, const double *bp, const 
 {
     if (col >= cols_.size() || !bp) return fail(Q1T_ERR_INVALID_ARGUMENT, "column out of range");
     if (nd == 0) return Q1T_OK;
+    CK(cudaSetDevice(device_));
     const size_t nl = nr_leaves(), nb = nl / kCanonBlock;
     if (nd > draws_cap_) {
         CK(cudaStreamSynchronize(stream_));
@@ -1866,6 +1882,18 @@ int DeviceVectorState::group_remap(size_t k, const int *rank_bits, const size_t 
     if (!grp_.open) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: no open peer group");
     if (k < 1 || k > (size_t)kMaxRemapBits || (int)k + 1 > n_ || !rank_bits || !local_qubits)
         return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: bad argument");
+    int rc = group_remap_prepare();
+    if (rc) return rc;
+    return group_remap_issue(k, rank_bits, local_qubits);
+}
+
+// The two halves of group_remap().  prepare: everything that may allocate, free or wait (queued sweeps, relabels, the
+// materialisation of a lazy column).  issue: barrier + swap + barrier, launches only.  A host thread that drives several
+// shards ON ONE DEVICE must prepare all of them before it issues any: a cudaFree between two shards' barrier launches
+// would wait for the first shard's barrier kernel, which waits for the second's.
+int DeviceVectorState::group_remap_prepare()
+{
+    if (!grp_.open) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: no open peer group");
     if (cols_.size() != 1) return fail(Q1T_ERR_UNSUPPORTED, "group_remap: the state must have exactly one column");
     int rc = flush_async();
     if (rc) return rc;
@@ -1873,6 +1901,18 @@ int DeviceVectorState::group_remap(size_t k, const int *rank_bits, const size_t 
     if (rc) return rc;
     if (cols_[0].buf != grp_.bufs[0] && cols_[0].buf != grp_.bufs[1])
         return fail(Q1T_ERR_UNSUPPORTED, "group_remap: the column does not live in a registered buffer");
+    group_collect_timing();
+    return Q1T_OK;
+}
+
+int DeviceVectorState::group_remap_issue(size_t k, const int *rank_bits, const size_t *local_qubits)
+{
+    if (!grp_.open) return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: no open peer group");
+    if (k < 1 || k > (size_t)kMaxRemapBits || (int)k + 1 > n_ || !rank_bits || !local_qubits)
+        return fail(Q1T_ERR_INVALID_ARGUMENT, "group_remap: bad argument");
+    if (cols_.size() != 1 || !cols_[0].buf) return fail(Q1T_ERR_UNSUPPORTED, "group_remap: call group_remap_prepare first");
+    int rc = Q1T_OK;
+    CK(cudaSetDevice(device_));
     GroupRemapArgs a;
     std::memset(&a, 0, sizeof a);
     a.n = n_; a.k = (int)k; a.P = grp_.P; a.rank = grp_.rank;
@@ -1893,7 +1933,6 @@ int DeviceVectorState::group_remap(size_t k, const int *rank_bits, const size_t 
     for (size_t i = 0; i <= k; ++i) a.ins[i] = ins[i];
     static const int interleave = std::getenv("Q1T_SWAP_INTERLEAVE") ? std::atoi(std::getenv("Q1T_SWAP_INTERLEAVE")) : 1;
     a.interleave = interleave;
-    group_collect_timing();
     rc = group_barrier();                                             // every rank has finished what precedes, and published its buffer
     if (rc) return rc;
     CK(cudaEventRecord(grp_.ev0, stream_));

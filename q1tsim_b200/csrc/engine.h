@@ -54,6 +54,9 @@ public:
     int leaf_totals(size_t qbit, double *out);
     int resolve_draws(size_t col, const double *P, double base, const double *chosen, size_t nd, uint64_t *idx);
     int block_totals(size_t qbit, double *out);
+    int block_totals_launch(size_t qbit);
+    int block_totals_fetch(double *out);
+    int device() const { return device_; }
     int resolve_draws_blocks(size_t col, const double *bp, const double *chosen, size_t nd, uint64_t *idx);
     int scale_split_columns(const double *f0, const double *f1, const size_t *n0s);
     int collapse_columns(size_t qbit, const double *w0s, const size_t *n0s);
@@ -69,6 +72,8 @@ public:
     int group_open(size_t P, size_t rank, const unsigned char *all_handles, void *const *all_ptrs);
     int group_barrier();
     int group_remap(size_t k, const int *rank_bits, const size_t *local_qubits);
+    int group_remap_prepare();
+    int group_remap_issue(size_t k, const int *rank_bits, const size_t *local_qubits);
     int group_close();
 
     int counts(size_t *out);

@@ -327,6 +327,28 @@ int circuit_set_device(circuit_t *ptr, int device)
     return Q1T_OK;
 }
 
+// extension: execute() on a state sharded over `n` devices of this process (a power of two >= 2; the list may repeat a
+// device: several shards on one GPU); n = 0 goes back to one device.  The circuit may then hold gates, measure_all /
+// peek_all and barriers, and reaches 34-36 qubits on 8 B200.
+int circuit_set_devices(circuit_t *ptr, const int *devices, size_t n)
+{
+    if (!ptr || (n && !devices) || n == 1 || (n & (n - 1))) return Q1T_ERR_INVALID_ARGUMENT;
+    ptr->impl.devices.assign(devices, devices + n);
+    return Q1T_OK;
+}
+// amplitudes of the last sharded run in canonical index order; remaps / exchanged qubits / local relabels it cost
+int circuit_sharded_amplitudes(circuit_t *ptr, size_t offset, size_t len, double *out)
+{
+    if (!ptr || !out || !ptr->impl.sharded_state()) return Q1T_ERR_INVALID_ARGUMENT;
+    return ptr->impl.sharded_state()->read_amplitudes(offset, len, out);
+}
+int circuit_sharded_counters(circuit_t *ptr, uint64_t *out3)
+{
+    if (!ptr || !out3) return Q1T_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < 3; ++i) out3[i] = ptr->impl.sharded_counters[i];
+    return Q1T_OK;
+}
+
 q1t_state *circuit_state(circuit_t *ptr)
 {
     if (!ptr || !ptr->impl.state()) return nullptr;

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace q1t {
 
@@ -1201,6 +1202,44 @@ bool tma_can_encode(const SweepProgram &prog, const double2 *const *h_src_cols, 
     return ok;
 }
 
+// c_prog is ONE constant bank per device and process.  States of one process that share a device (several shards on one
+// GPU: how the single-process sharded state is tested on a one-GPU box) launch from different streams, so the upload of
+// one's program must not overtake the other's running sweep: from the moment a second stream shows up on a device, every
+// (upload, kernel) pair waits for the previous one on that device.  The usual case -- one stream per device -- pays one
+// relaxed load.
+namespace {
+struct CprogGuard {
+    std::mutex mu;
+    cudaStream_t first[64] = {};
+    bool seen[64] = {};
+    bool shared[64] = {};
+    cudaEvent_t evt[64] = {};
+} g_cprog;
+}  // namespace
+bool cprog_device_shared(int dev) { return dev >= 0 && dev < 64 && g_cprog.shared[dev]; }
+static cudaError_t cprog_acquire(int dev, cudaStream_t stream)
+{
+    if (dev < 0 || dev >= 64) return cudaSuccess;
+    if (!g_cprog.shared[dev]) {
+        std::lock_guard<std::mutex> lk(g_cprog.mu);
+        if (!g_cprog.seen[dev]) { g_cprog.seen[dev] = true; g_cprog.first[dev] = stream; return cudaSuccess; }
+        if (g_cprog.first[dev] == stream) return cudaSuccess;
+        // a second stream on this device: let what is in flight finish once, serialise through an event from now on
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&g_cprog.evt[dev], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(g_cprog.evt[dev], stream);
+        if (e != cudaSuccess) return e;
+        g_cprog.shared[dev] = true;
+    }
+    return cudaStreamWaitEvent(stream, g_cprog.evt[dev], 0);
+}
+static void cprog_release(int dev, cudaStream_t stream)
+{
+    if (dev >= 0 && dev < 64 && g_cprog.shared[dev]) cudaEventRecord(g_cprog.evt[dev], stream);
+}
+
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
                          double *d_leaf_out, const double2 *const *h_src_cols, const SweepProgram *d_prog)
@@ -1214,7 +1253,11 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
     const bool ladder = sweep_uses_ladder_kernel(prog);
     const bool gprog = d_prog != nullptr && !ladder;          // (the ladder kernel keeps its program in the constant bank)
     cudaError_t e = cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
     if (!gprog) {
+        e = cprog_acquire(dev, stream);
+        if (e != cudaSuccess) return e;
         e = cudaMemcpyToSymbolAsync(c_prog, &prog, sizeof(SweepProgram), 0, cudaMemcpyHostToDevice, stream);
         if (e != cudaSuccess) return e;
     }
@@ -1226,8 +1269,6 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
                                     sweep_kernel<true, kMaxThreads, 1, true>, sweep_kernel<false, kMaxThreads, 1, true>,
                                     sweep_kernel<false, kSmallThreads, Q1T_LADDER_MIN_CTAS, true> };
     static int sattr_dev_mask = 0;             // function attributes are per device
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (!((sattr_dev_mask >> (dev & 31)) & 1)) {
         const int max_smem = (int)((sizeof(double2) << kMaxTileBits) + sizeof(double2) * kMaxPhase * kHiEntries);
         const int small_smem = (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * kHiEntries);
@@ -1273,11 +1314,15 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         if (per_col > (1ull << prog.n_outer)) per_col = 1ull << prog.n_outer;
         dim3 pgrid((unsigned)per_col, (unsigned)ncols, 1);
         fn<<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
-        return cudaGetLastError();
+        e = cudaGetLastError();
+        cprog_release(dev, stream);
+        return e;
     }
     const int v = (ladders_only && (int)block.x <= kSmallThreads ? 2 : ladders_only ? 1 : 0) + (gprog ? 3 : 0);
     sfn[v]<<<grid, block, smem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_prog);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (!gprog) cprog_release(dev, stream);
+    return e;
 }
 
 // ---------------------------------------------------------------------------
@@ -1644,6 +1689,7 @@ cudaError_t launch_peer_swap(double2 *d_mine, double2 *d_theirs, int n, int L, i
 // arrived in its own mailbox.  Stream-ordered: the host never blocks, and everything enqueued before the
 // barrier on any rank is complete and visible to everything enqueued after it on every rank.
 // ---------------------------------------------------------------------------
+void group_kernels_preload();
 __global__ void group_barrier_kernel(unsigned long long *const *__restrict__ peer_mail, unsigned long long *my_mail, int P, int rank,
                                      unsigned long long epoch, unsigned long long cur)
 {
@@ -1663,6 +1709,7 @@ __global__ void group_barrier_kernel(unsigned long long *const *__restrict__ pee
 cudaError_t launch_group_barrier(unsigned long long *const *d_peer_mail, unsigned long long *d_my_mail, int P, int rank,
                                  unsigned long long epoch, unsigned long long cur, cudaStream_t stream)
 {
+    group_kernels_preload();
     group_barrier_kernel<<<1, 32, 0, stream>>>(d_peer_mail, d_my_mail, P, rank, epoch, cur);
     return cudaGetLastError();
 }
@@ -1724,6 +1771,23 @@ cudaError_t launch_group_swap(double2 *d_mine, void *const *d_peer_buf, const un
     if (a.interleave) group_swap_kernel<<<dim3((unsigned)blocks * np, 1), 256, 0, stream>>>(d_mine, d_peer_buf, d_my_mail, a);
     else group_swap_kernel<<<dim3((unsigned)blocks, np), 256, 0, stream>>>(d_mine, d_peer_buf, d_my_mail, a);
     return cudaGetLastError();
+}
+
+// CUDA loads a kernel at its first launch (lazy module loading), and loading may synchronise the context: a swap kernel
+// launched for the first time while a barrier kernel of ANOTHER shard of this process spins on the same device would wait
+// for that barrier, which waits for a barrier this thread has not launched yet.  Both kernels are loaded before the first
+// barrier goes out (per device).
+void group_kernels_preload()
+{
+    static int done_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((done_mask >> (dev & 31)) & 1) return;
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, group_barrier_kernel);
+    cudaFuncGetAttributes(&fa, group_swap_kernel);
+    cudaGetLastError();
+    done_mask |= 1 << (dev & 31);
 }
 
 __global__ void set_basis_kernel(double2 *__restrict__ st, unsigned long long idx)

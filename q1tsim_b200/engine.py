@@ -355,3 +355,86 @@ class VectorState:
 
     def set_option(self, key, value):
         self._chk(lib().q1t_set_option(self._p, key.encode(), int(value)))
+
+
+class ShardedProcessState:
+    """A state sharded over the devices of THIS process (csrc/sharded.h, q1t_sharded_* of include/q1t_engine.h): the C++
+    form of q1tsim_b200.sharded.ShardedState for gates, measure_all / peek_all and read-out.  `devices` may repeat a
+    device (several shards on one GPU)."""
+
+    def __init__(self, nr_bits, nr_shots, devices):
+        L = lib()
+        vp, sz = C.c_void_p, C.c_size_t
+        L.q1t_sharded_new.restype = C.c_int
+        L.q1t_sharded_new.argtypes = [sz, sz, sz, C.POINTER(C.c_int), C.POINTER(vp)]
+        L.q1t_sharded_free.restype = None
+        L.q1t_sharded_free.argtypes = [vp]
+        L.q1t_sharded_apply_gate.restype = C.c_int
+        L.q1t_sharded_apply_gate.argtypes = [vp, C.POINTER(C.c_double), sz, C.POINTER(sz), sz, C.c_char_p]
+        L.q1t_sharded_set_initial_layout.restype = C.c_int
+        L.q1t_sharded_set_initial_layout.argtypes = [vp, C.POINTER(C.c_int), sz]
+        for f in (L.q1t_sharded_measure_all_into, L.q1t_sharded_peek_all_into):
+            f.restype = C.c_int
+            f.argtypes = [vp, C.POINTER(sz), sz, C.POINTER(C.c_uint64), sz, _RngHandle]
+        L.q1t_sharded_reset_all.restype = C.c_int
+        L.q1t_sharded_reset_all.argtypes = [vp]
+        L.q1t_sharded_read_amplitudes.restype = C.c_int
+        L.q1t_sharded_read_amplitudes.argtypes = [vp, sz, sz, C.POINTER(C.c_double)]
+        L.q1t_sharded_column_total.restype = C.c_int
+        L.q1t_sharded_column_total.argtypes = [vp, C.POINTER(C.c_double)]
+        L.q1t_sharded_counters.restype = C.c_int
+        L.q1t_sharded_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.q1t_sharded_last_error.restype = C.c_char_p
+        L.q1t_sharded_last_error.argtypes = [vp]
+        self._L, self.nr_bits, self.nr_shots = L, nr_bits, nr_shots
+        p = vp()
+        dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = L.q1t_sharded_new(nr_bits, nr_shots, len(devices), dv, C.byref(p))
+        if rc:
+            raise EngineError(rc, L.q1t_sharded_last_error(None).decode())
+        self._p = p
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._L.q1t_sharded_free(self._p)
+            self._p = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc:
+            raise EngineError(rc, self._L.q1t_sharded_last_error(self._p).decode())
+
+    def apply_gate(self, mat, bits, desc="gate"):
+        m = np.ascontiguousarray(np.asarray(mat, dtype=np.complex128))
+        self._chk(self._L.q1t_sharded_apply_gate(self._p, _dptr(m.view(np.float64)), m.shape[0], _szarr(bits), len(bits), desc.encode()))
+
+    def set_initial_layout(self, dest):
+        arr = (C.c_int * len(dest))(*[int(d) for d in dest])
+        self._chk(self._L.q1t_sharded_set_initial_layout(self._p, arr, len(dest)))
+
+    def measure_all_into(self, cbits, res, rng, collapse=True):
+        f = self._L.q1t_sharded_measure_all_into if collapse else self._L.q1t_sharded_peek_all_into
+        self._chk(f(self._p, _szarr(cbits), len(cbits), res.ctypes.data_as(C.POINTER(C.c_uint64)), res.size, rng.handle))
+
+    def peek_all_into(self, cbits, res, rng):
+        self.measure_all_into(cbits, res, rng, collapse=False)
+
+    def reset_all(self):
+        self._chk(self._L.q1t_sharded_reset_all(self._p))
+
+    def amplitudes(self, offset=0, length=None):
+        length = (1 << self.nr_bits) - offset if length is None else length
+        out = np.zeros(2 * length, dtype=np.float64)
+        self._chk(self._L.q1t_sharded_read_amplitudes(self._p, offset, length, _dptr(out)))
+        return out.view(np.complex128)
+
+    def column_total(self):
+        v = C.c_double()
+        self._chk(self._L.q1t_sharded_column_total(self._p, C.byref(v)))
+        return v.value
+
+    def counters(self):
+        out = (C.c_uint64 * 3)()
+        self._chk(self._L.q1t_sharded_counters(self._p, out))
+        return {"remaps": int(out[0]), "exchanged_qubits": int(out[1]), "local_relabels": int(out[2])}
