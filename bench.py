@@ -64,27 +64,39 @@ class ClockSampler:
         self.err = None
 
     def _run(self):
+        N, h, mx = self.N, self.h, self.mx
         try:
-            import pynvml as N
-            N.nvmlInit()
-            h = N.nvmlDeviceGetHandleByIndex(self.idx)
-            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
             while not self.stop_flag:
                 sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
                 rs = N.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 try:
                     pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
-                except Exception:
+                except Exception:      # noqa: BLE001
                     pw = 0.0
                 self.rows.append((sm, mx, rs, pw))
+                self.first.set()
                 time.sleep(0.005)
         except Exception as e:            # noqa: BLE001
             self.err = repr(e)
+            self.first.set()
 
     def start(self):
+        # NVML is initialised here, before the timed region, and start() returns once the first sample is in
+        self.first = threading.Event()
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+        except Exception as e:            # noqa: BLE001
+            self.err = repr(e)
+            return
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
+        self.first.wait(timeout=2.0)
+        self.rows = []                    # (the sample taken before the region starts does not count)
 
     def stop(self):
         self.stop_flag = True

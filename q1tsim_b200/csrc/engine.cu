@@ -218,6 +218,7 @@ DeviceVectorState::~DeviceVectorState()
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
         cudaStreamDestroy(stream_);
+        cprog_stream_unregister(device_);
     }
 }
 
@@ -233,6 +234,7 @@ int DeviceVectorState::ensure_device()
     if (device_ < 0 || device_ >= cnt) return fail(Q1T_ERR_CUDA, "invalid CUDA device ordinal");
     CK(cudaSetDevice(device_));
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    cprog_stream_register(device_);
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
     CK(scratch_alloc(device_, (void **)&d_ptabs_, sizeof(PhaseTab) * kMaxPhase));

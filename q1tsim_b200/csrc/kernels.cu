@@ -1204,40 +1204,42 @@ bool tma_can_encode(const SweepProgram &prog, const double2 *const *h_src_cols, 
 
 // c_prog is ONE constant bank per device and process.  States of one process that share a device (several shards on one
 // GPU: how the single-process sharded state is tested on a one-GPU box) launch from different streams, so the upload of
-// one's program must not overtake the other's running sweep: from the moment a second stream shows up on a device, every
-// (upload, kernel) pair waits for the previous one on that device.  The usual case -- one stream per device -- pays one
-// relaxed load.
+// one's program must not overtake the other's running sweep: while more than one state is alive on a device, every
+// (upload, kernel) pair waits for the previous one on that device.  The usual case -- one state per device -- pays one
+// load.
 namespace {
 struct CprogGuard {
     std::mutex mu;
-    cudaStream_t first[64] = {};
-    bool seen[64] = {};
-    bool shared[64] = {};
+    int live[64] = {};            // states (streams) alive on the device
     cudaEvent_t evt[64] = {};
 } g_cprog;
 }  // namespace
-bool cprog_device_shared(int dev) { return dev >= 0 && dev < 64 && g_cprog.shared[dev]; }
+bool cprog_device_shared(int dev) { return dev >= 0 && dev < 64 && g_cprog.live[dev] > 1; }
+// a state (one stream) appears on / leaves a device.  The second one to appear waits for what the first has in flight.
+void cprog_stream_register(int dev)
+{
+    if (dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(g_cprog.mu);
+    if (++g_cprog.live[dev] == 2) {
+        cudaDeviceSynchronize();
+        if (!g_cprog.evt[dev]) cudaEventCreateWithFlags(&g_cprog.evt[dev], cudaEventDisableTiming);
+        cudaGetLastError();
+    }
+}
+void cprog_stream_unregister(int dev)
+{
+    if (dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(g_cprog.mu);
+    if (g_cprog.live[dev] > 0) --g_cprog.live[dev];
+}
 static cudaError_t cprog_acquire(int dev, cudaStream_t stream)
 {
-    if (dev < 0 || dev >= 64) return cudaSuccess;
-    if (!g_cprog.shared[dev]) {
-        std::lock_guard<std::mutex> lk(g_cprog.mu);
-        if (!g_cprog.seen[dev]) { g_cprog.seen[dev] = true; g_cprog.first[dev] = stream; return cudaSuccess; }
-        if (g_cprog.first[dev] == stream) return cudaSuccess;
-        // a second stream on this device: let what is in flight finish once, serialise through an event from now on
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) return e;
-        e = cudaEventCreateWithFlags(&g_cprog.evt[dev], cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-        e = cudaEventRecord(g_cprog.evt[dev], stream);
-        if (e != cudaSuccess) return e;
-        g_cprog.shared[dev] = true;
-    }
-    return cudaStreamWaitEvent(stream, g_cprog.evt[dev], 0);
+    if (!cprog_device_shared(dev) || !g_cprog.evt[dev]) return cudaSuccess;
+    return cudaStreamWaitEvent(stream, g_cprog.evt[dev], 0);       // (an event never recorded yet does not block)
 }
 static void cprog_release(int dev, cudaStream_t stream)
 {
-    if (dev >= 0 && dev < 64 && g_cprog.shared[dev]) cudaEventRecord(g_cprog.evt[dev], stream);
+    if (cprog_device_shared(dev) && g_cprog.evt[dev]) cudaEventRecord(g_cprog.evt[dev], stream);
 }
 
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,

@@ -28,9 +28,11 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
 // h_src_cols: host copy of the source column pointers, needed (only) by programs in TMA layout (prog.tma_nreq > 0)
 // to encode the tensor maps; true if the driver offers cuTensorMapEncodeTiled
 bool tma_available();
-// true once two streams of this process have launched sweeps on the device (several states on one GPU): their program
-// uploads into the one constant bank are serialised, and graph capture of sweep batches is off there
+// true while more than one state of this process is alive on the device: their program uploads into the one constant
+// bank are serialised, and graph capture of sweep batches is off there.  States register / unregister their stream.
 bool cprog_device_shared(int dev);
+void cprog_stream_register(int dev);
+void cprog_stream_unregister(int dev);
 // can the tile description of a program in TMA layout be encoded for these source columns?
 bool tma_can_encode(const SweepProgram &prog, const double2 *const *h_src_cols, int ncols);
 // true if launch_sweep() runs this program in the persistent ladder kernel (the one that honours

@@ -153,6 +153,8 @@ def test_measure_all_bit_exact_n24():
 def test_launch_bound_batches_replayed_as_cuda_graphs(n, depth):
     """cfg2 shape (random H/U3/CX/CS/CT layers): a hundred short sweeps per run.  From the second run of the same gate list
     on, the whole batch is ONE cudaGraphLaunch of the captured sweeps; results are identical to issuing them one by one"""
+    import gc
+    gc.collect()                 # (graphs are off while another state is alive on the device: let earlier tests' states go)
     ops = W.random_circuit_ops(n, depth, measure=False)
     gates = [(E.gate_matrix(o[1], o[2]), o[3], o[1]) for o in ops]
     cols = {}
