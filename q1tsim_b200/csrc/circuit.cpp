@@ -342,6 +342,8 @@ CircuitError Circuit::execute(size_t nr_shots, q1t_rng rng, const double *qubit_
     }
     s_state_.reset();
     s_devices_.clear();
+    // one device holds 1..34 qubits (capi.cpp make_state checks the same for the inner ABI)
+    if (nr_qbits_ < 1 || nr_qbits_ > 34) return mkerr(Q1T_ERR_INVALID_ARGUMENT, "the number of qubits must be in 1..34 for one device");
     const double t0 = host_profile_on() ? now_us() : 0.0;
     q_state_.reset(new DeviceVectorState(nr_qbits_, nr_shots, device));
     const int rc = qubit_coefs ? q_state_->init_from_qubit_coefs(qubit_coefs) : q_state_->init_zero_state();
@@ -370,6 +372,7 @@ CircuitError Circuit::reexecute(q1t_rng rng)
 CircuitError Circuit::set_cstate(const uint64_t *w, size_t n)
 {
     if (!q_state_) {
+        if (nr_qbits_ < 1 || nr_qbits_ > 34) return mkerr(Q1T_ERR_INVALID_ARGUMENT, "the number of qubits must be in 1..34 for one device");
         q_state_.reset(new DeviceVectorState(nr_qbits_, n, device));
         const int rc = q_state_->init_zero_state();
         if (rc) { CircuitError e = state_err(rc); q_state_.reset(); return e; }

@@ -146,7 +146,7 @@ void scratch_free(int device, void *p, size_t bytes)
 }  // namespace
 
 namespace {
-struct PlanCacheEntry { uint64_t key; size_t ngates; uint64_t stamp; std::vector<PlannedSweep> sweeps; };
+struct PlanCacheEntry { uint64_t key, key2; size_t ngates; uint64_t stamp; std::vector<PlannedSweep> sweeps; };
 std::mutex g_plan_mu;
 std::vector<PlanCacheEntry> g_plan_cache;
 uint64_t g_plan_clock = 0;
@@ -911,10 +911,14 @@ int DeviceVectorState::run_queue(bool final_relabel)
         if (fusable) {
             // plan cache: execute() of the same circuit lowers to the same gate list every time
             // (circuit.rs:594-600 builds a fresh state per call); planning it again is pure host time
-            uint64_t key = 1469598103934665603ull;
+            // (two independent 64-bit hashes of the lowered list: a hit needs both, and the gate count, to agree)
+            uint64_t key = 1469598103934665603ull, key2 = 0x9E3779B97F4A7C15ull;
             auto mix = [&](const void *p, size_t nbytes) {
                 const unsigned char *b = static_cast<const unsigned char *>(p);
-                for (size_t i = 0; i < nbytes; ++i) { key ^= b[i]; key *= 1099511628211ull; }
+                for (size_t i = 0; i < nbytes; ++i) {
+                    key ^= b[i]; key *= 1099511628211ull;
+                    key2 = (key2 ^ b[i]) * 0xFF51AFD7ED558CCDull; key2 ^= key2 >> 29;
+                }
             };
             // batches that start from basis states run with support tracking: their loads are negligible,
             // so 64-byte tiles cost nothing and leave 10 (not 9) free bits per sweep -- provided every sweep
@@ -933,7 +937,7 @@ int DeviceVectorState::run_queue(bool final_relabel)
             {
                 std::lock_guard<std::mutex> lk(g_plan_mu);
                 for (PlanCacheEntry &pc : g_plan_cache)
-                    if (pc.key == key && pc.ngates == q.size()) {
+                    if (pc.key == key && pc.key2 == key2 && pc.ngates == q.size()) {
                         std::vector<PlannedSweep> plan = pc.sweeps;
                         pc.stamp = ++g_plan_clock;
                         stats.plan_cache_hits++;
@@ -995,7 +999,7 @@ int DeviceVectorState::run_queue(bool final_relabel)
                         if (g_plan_cache[i].stamp < g_plan_cache[lru].stamp) lru = i;
                     g_plan_cache.erase(g_plan_cache.begin() + lru);
                 }
-                g_plan_cache.push_back({ key, q.size(), ++g_plan_clock, plan[pick] });
+                g_plan_cache.push_back({ key, key2, q.size(), ++g_plan_clock, plan[pick] });
             }
             cur_plan_key_ = q.size() >= 16 ? (key ? key : 1) : 0;
             const int rcs = run_sweeps(plan[pick], which, final_relabel);
@@ -1258,7 +1262,15 @@ int DeviceVectorState::apply_conditional_gate(const uint8_t *control, size_t nco
             dst.basis = true; dst.basis_idx = src.basis_idx;
         } else {
             rc = alloc_column(&dst.buf);
-            if (rc) { cols_.swap(nc); return rc; }
+            if (rc) {
+                // out of device memory half-way: the state keeps its columns as they were (buffers that already moved
+                // into the new list go back to their columns, copies made so far are released)
+                for (size_t u = 0; u < r; ++u) {
+                    if (last_of[ranges[u].icol] == (int)u) cols_[ranges[u].icol].buf = nc[u].buf;
+                    else if (nc[u].buf) release_column(nc[u].buf);
+                }
+                return rc;
+            }
             CK(cudaMemcpyAsync(dst.buf, src.buf, sizeof(double2) << n_, cudaMemcpyDeviceToDevice, stream_));
             stats.sweep_column_passes++;     // a column copy is one read + one write of the column
         }
