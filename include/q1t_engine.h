@@ -160,6 +160,10 @@ int    q1t_peer_swap(q1t_state *st, size_t col, const unsigned char *peer_handle
  * q1t_resolve_draws_blocks: block_prefix[0] = weight in front of this shard, block_prefix[b + 1] = global inclusive
  * prefix through this shard's block b.  Same fixed geometry as the single-GPU scan. */
 int    q1t_block_totals(q1t_state *st, size_t qbit, double *out);
+/* the same in two halves (everything enqueued / copy to the host and wait): a host layer draws and sorts its random
+ * numbers, or launches on other shards, in between */
+int    q1t_block_totals_launch(q1t_state *st, size_t qbit);
+int    q1t_block_totals_fetch(q1t_state *st, double *out);
 int    q1t_resolve_draws_blocks(q1t_state *st, size_t col, const double *block_prefix, const double *chosen, size_t nd, uint64_t *idx);
 /* every column times the scalar re + i*im (a rank's share of a one-qubit gate on a rank bit that is still
  * pinned to a basis value); real factors are deferred into the next fused sweep like the Hadamard normalisations */
@@ -191,6 +195,9 @@ const char *q1t_sharded_last_error(q1t_sharded *h);               /* h = NULL: e
 /* rand 0.7 Uniform(0,total) draws as WeightedIndex::sample makes them (vectorstate.rs:126) */
 double q1t_uniform_draw(q1t_rng rng, double total);
 void   q1t_uniform_draws(q1t_rng rng, double total, size_t n, double *out);
+/* q1t_uniform_draws in two halves: unit-interval values (one generator word each), and later the map of Uniform(0, total) */
+void   q1t_uniform_units(q1t_rng rng, size_t n, double *out);
+void   q1t_uniform_scale(double total, size_t n, double *inout);
 
 /* execution statistics since creation / last reset of the counters */
 typedef struct {

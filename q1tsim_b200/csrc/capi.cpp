@@ -212,6 +212,19 @@ int q1t_replace_columns(q1t_state *st, size_t ncols, const uint64_t *idx, const 
 int q1t_column_device_ptr(q1t_state *st, size_t col, void **ptr) { ST_OR_FAIL; return st->impl->column_ptr(col, ptr); }
 int q1t_ipc_export(q1t_state *st, size_t col, unsigned char *handle64) { ST_OR_FAIL; return st->impl->ipc_export(col, handle64); }
 int q1t_block_totals(q1t_state *st, size_t qbit, double *out) { ST_OR_FAIL; return st->impl->block_totals(qbit, out); }
+int q1t_block_totals_launch(q1t_state *st, size_t qbit) { ST_OR_FAIL; return st->impl->block_totals_launch(qbit); }
+int q1t_block_totals_fetch(q1t_state *st, double *out) { ST_OR_FAIL; return out ? st->impl->block_totals_fetch(out) : Q1T_ERR_INVALID_ARGUMENT; }
+// the two halves of q1t_uniform_draws: the unit-interval values now (one generator word each), the affine map of
+// Uniform(0, total) later -- monotone, so values sorted before the map stay sorted
+void q1t_uniform_units(q1t_rng rng, size_t n, double *out)
+{
+    for (size_t i = 0; i < n; ++i) out[i] = q1t::uniform_unit(rng);
+}
+void q1t_uniform_scale(double total, size_t n, double *inout)
+{
+    const q1t::UniformF64 u = q1t::uniform_new(0.0, total);
+    for (size_t i = 0; i < n; ++i) inout[i] = q1t::uniform_scale(u, inout[i]);
+}
 int q1t_resolve_draws_blocks(q1t_state *st, size_t col, const double *block_prefix, const double *chosen, size_t nd, uint64_t *idx)
 {
     ST_OR_FAIL;

@@ -383,6 +383,27 @@ CircuitError Circuit::set_cstate(const uint64_t *w, size_t n)
     return ok();
 }
 
+// process-wide cache of lowered gate runs, keyed by content (see do_execute)
+namespace {
+struct LoweredRun { uint64_t key[2]; size_t n, len; uint64_t stamp; std::vector<LoweredGate> gates; };
+std::mutex g_lowered_mu;
+std::vector<LoweredRun> g_lowered_runs;
+uint64_t g_lowered_clock = 0;
+}  // namespace
+
+void Circuit::publish_lowered()
+{
+    if (lowered_.size() != lowered_len_) return;
+    std::lock_guard<std::mutex> lk(g_lowered_mu);
+    if (g_lowered_runs.size() >= 8) {
+        size_t lru = 0;
+        for (size_t i = 1; i < g_lowered_runs.size(); ++i)
+            if (g_lowered_runs[i].stamp < g_lowered_runs[lru].stamp) lru = i;
+        g_lowered_runs.erase(g_lowered_runs.begin() + lru);
+    }
+    g_lowered_runs.push_back({ { lowered_key_[0], lowered_key_[1] }, nr_qbits_, lowered_len_, ++g_lowered_clock, lowered_ });
+}
+
 // circuit.rs:643-762
 CircuitError Circuit::do_execute(q1t_rng rng)
 {
@@ -407,6 +428,39 @@ CircuitError Circuit::do_execute(q1t_rng rng)
             for (const Param &pr : ops_[run].gate.params) constant = constant && pr.ptr == nullptr;
             ++run;
         }
+        if (constant && run >= 16 && !(lowered_valid_ && lowered_len_ == run)) {
+            // a circuit object seen for the first time: the same gate run may have been lowered for another object (a
+            // host layer that rebuilds its circuit for every execute()): process-wide cache keyed by the run's content
+            uint64_t key = 1469598103934665603ull, key2 = 0x9E3779B97F4A7C15ull;
+            auto mix = [&](const void *p, size_t nbytes) {
+                const unsigned char *b = static_cast<const unsigned char *>(p);
+                for (size_t i = 0; i < nbytes; ++i) {
+                    key ^= b[i]; key *= 1099511628211ull;
+                    key2 = (key2 ^ b[i]) * 0xFF51AFD7ED558CCDull; key2 ^= key2 >> 29;
+                }
+            };
+            const size_t hdr[2] = { nr_qbits_, run };
+            mix(hdr, sizeof hdr);
+            for (size_t t = 0; t < run; ++t) {
+                const GateSpec &g = ops_[t].gate;
+                mix(g.name.data(), g.name.size() + 0);
+                const size_t sep[2] = { g.params.size(), g.matrix.size() };
+                mix(sep, sizeof sep);
+                for (const Param &pr : g.params) mix(&pr.value, sizeof pr.value);
+                if (!g.matrix.empty()) mix(g.matrix.data(), sizeof(std::complex<double>) * g.matrix.size());
+                mix(ops_[t].bits.data(), sizeof(size_t) * ops_[t].bits.size());
+            }
+            lowered_key_[0] = key; lowered_key_[1] = key2;
+            std::lock_guard<std::mutex> lk(g_lowered_mu);
+            for (LoweredRun &lr : g_lowered_runs)
+                if (lr.key[0] == key && lr.key[1] == key2 && lr.n == nr_qbits_ && lr.len == run) {
+                    lowered_ = lr.gates;
+                    lowered_len_ = run;
+                    lowered_valid_ = true;
+                    lr.stamp = ++g_lowered_clock;
+                    break;
+                }
+        }
         if (constant && run >= 16) {
             if (lowered_valid_ && lowered_len_ == run) {
                 TRY(q.apply_lowered(lowered_));
@@ -422,7 +476,7 @@ CircuitError Circuit::do_execute(q1t_rng rng)
     fresh_state_ = false;
     size_t op_index = 0;
     for (const CircuitOp &op : ops_) {
-        if (recording && op_index == lowered_len_) { q.record_lowered(nullptr); recording = nullptr; lowered_valid_ = true; }
+        if (recording && op_index == lowered_len_) { q.record_lowered(nullptr); recording = nullptr; lowered_valid_ = true; publish_lowered(); }
         if (op_index++ < skip) continue;
         const double t_op = prof ? now_us() : 0.0;
         struct Tick {
@@ -484,7 +538,7 @@ CircuitError Circuit::do_execute(q1t_rng rng)
         }
     }
 #undef TRY
-    if (recording) { q.record_lowered(nullptr); lowered_valid_ = true; }        // (the circuit is gates only)
+    if (recording) { q.record_lowered(nullptr); lowered_valid_ = true; publish_lowered(); }        // (the circuit is gates only)
     // the reference's execute() returns with the state fully evolved; queued gates after the
     // last measurement are run here so that errors surface now
     const double t_fl = prof ? now_us() : 0.0;

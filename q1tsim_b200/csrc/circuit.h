@@ -111,6 +111,8 @@ private:
     std::vector<LoweredGate> lowered_;
     size_t lowered_len_ = 0;
     bool lowered_valid_ = false, fresh_state_ = false;
+    uint64_t lowered_key_[2] = { 0, 0 };
+    void publish_lowered();
     size_t next_group_ = 0;
     size_t export_group(size_t at, const std::vector<std::string> &names, bool cq, std::string &out, CircuitError &err) const;
     CircuitError state_err(int rc);

@@ -785,12 +785,7 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
                 }
             }
             if (ok && __builtin_popcount(tgt) >= 2) ps.prog.direct_store = 0;
-            if (std::getenv("Q1T_DEBUG_BCAST"))
-                std::fprintf(stderr, "q1t bcast check: sweep %zu ok %d tgt %x direct_store %d nrounds %d smask0 %x nsteps0 %d\n", si, (int)ok, tgt,
-                             ps.prog.direct_store, ps.prog.nrounds, ps.prog.rounds[0].smask, ps.prog.rounds[0].nsteps);
-        } else if (std::getenv("Q1T_DEBUG_BCAST"))
-            std::fprintf(stderr, "q1t bcast skip: sweep %zu relabel %d sup_mode %d generate %d direct_store %d nrounds %d\n", si, (int)relabel,
-                         ps.prog.sup_mode, ps.prog.generate, ps.prog.direct_store, ps.prog.nrounds);
+        }
         // dense ladder sweeps take their tiles by TMA (planner.cpp apply_tma_layout, kernels.cu ladder_kernel)
         const bool tma_ok = tma_ && !ps.prog.generate && ps.prog.sup_mode == 0 && sweep_uses_ladder_kernel(ps.prog) && tma_available();
         if (!relabel) {
@@ -875,15 +870,6 @@ int DeviceVectorState::run_queue(bool final_relabel)
     std::vector<LoweredGate> q;
     q.swap(queue_);
     queue_cols_.clear();
-    // A lazy all-zero column (a shard that holds nothing yet) stays all-zero under any gate: nothing to run for
-    // it.  EXPERIMENT, off by default (Q1T_SKIP_ZERO_SHARDS=1): written without a multi-GPU box at hand, to be
-    // measured on the sharded QFT where ranks other than 0 sweep over zeros until the first exchange.
-    static const bool skip_zero = std::getenv("Q1T_SKIP_ZERO_SHARDS") && std::atoi(std::getenv("Q1T_SKIP_ZERO_SHARDS")) != 0;
-    if (skip_zero) {
-        which.erase(std::remove_if(which.begin(), which.end(),
-                                   [&](int c) { return cols_[c].basis && cols_[c].basis_idx == UINT64_MAX; }), which.end());
-        if (which.empty()) return Q1T_OK;
-    }
     auto materialize_all = [&]() -> int {
         for (int c : which) {
             int r = materialize(cols_[c]);

@@ -124,6 +124,38 @@ class EngineLocal:
         self.st._chk(self.L.q1t_block_totals(self.st._p, q, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out.reshape(self.ncols, nb)
 
+    def block_totals_launch(self, qubit):
+        C = self.C
+        q = (1 << 64) - 1 if qubit is None else qubit
+        self.L.q1t_block_totals_launch.restype = C.c_int
+        self.L.q1t_block_totals_launch.argtypes = [C.c_void_p, C.c_size_t]
+        self.st._chk(self.L.q1t_block_totals_launch(self.st._p, q))
+
+    def block_totals_fetch(self):
+        C = self.C
+        nb = self.nleaves // BLOCK
+        out = np.zeros(self.ncols * nb, dtype=np.float64)
+        self.L.q1t_block_totals_fetch.restype = C.c_int
+        self.L.q1t_block_totals_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self.st._chk(self.L.q1t_block_totals_fetch(self.st._p, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.reshape(self.ncols, nb)
+
+    def draw_units(self, rng, n):
+        C = self.C
+        out = np.zeros(max(n, 1), dtype=np.float64)
+        self.L.q1t_uniform_units.restype = None
+        self.L.q1t_uniform_units.argtypes = [self.E._RngHandle, C.c_size_t, C.POINTER(C.c_double)]
+        self.L.q1t_uniform_units(rng.handle, n, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out[:n]
+
+    def scale_units(self, units, total):
+        C = self.C
+        v = np.ascontiguousarray(units, dtype=np.float64).copy()
+        self.L.q1t_uniform_scale.restype = None
+        self.L.q1t_uniform_scale.argtypes = [C.c_double, C.c_size_t, C.POINTER(C.c_double)]
+        self.L.q1t_uniform_scale(float(total), v.size, v.ctypes.data_as(C.POINTER(C.c_double)))
+        return v
+
     def resolve_draws_blocks(self, col, bp, chosen):
         C = self.C
         bp = np.ascontiguousarray(bp, dtype=np.float64)
@@ -830,15 +862,26 @@ class ShardedState:
             raise ValueError("Expected %d measurement bits, but got %d" % (self.n, len(cbits)))
         self.canonicalize()
         blocks = self._on_device_blocks()
-        if blocks:
+        counts = self.local.counts
+        units = None
+        if blocks and hasattr(self.local, "block_totals_launch"):
+            # the draws do not depend on the totals: generated (one word per shot, in column order) and sorted while the
+            # device runs the sweeps and the scan (vectorstate.rs:120-133; Uniform(0, total) is monotone in its unit value)
+            self.local.block_totals_launch(None)
+            allu = self.local.draw_units(rng, int(sum(counts)))
+            units, at = [], 0
+            for cnt in counts:
+                units.append(np.sort(allu[at:at + cnt]))
+                at += cnt
+            bp, ends = self._global_block_prefix(self.local.block_totals_fetch())
+        elif blocks:
             bp, ends = self._global_block_prefix(self.local.block_totals(None))
         else:
             Pl, base, ends = self._global_prefix(self.local.leaf_totals(None))
-        counts = self.local.counts
         groups = []                                   # (global basis index, multiplicity) per column, ascending
         for c, cnt in enumerate(counts):
             total = ends[c, -1]
-            chosen = np.sort(self.local.draws(rng, total, cnt))
+            chosen = self.local.scale_units(units[c], total) if units is not None else np.sort(self.local.draws(rng, total, cnt))
             # owner rank of a draw: number of rank-end prefixes (all but the last) that are <= chosen
             owner = np.searchsorted(ends[c, :-1], chosen, side="right")
             mine = chosen[owner == self.rank]
