@@ -220,13 +220,17 @@ typedef struct {
     uint64_t graph_replays;       /* ... and batches executed by replaying a cached graph (one launch for the whole batch) */
     uint64_t h2d_bytes;           /* bytes copied host -> device by this state (programs, tables, draws, amplitudes written) */
     uint64_t d2h_bytes;           /* bytes copied device -> host (totals, sampled indices, amplitudes read) */
+    uint64_t fused_remaps;        /* qubit remaps run as the tile loads of the sweep that followed (option "fused_remap"): no swap pass */
 } q1t_stats;
 int q1t_get_stats(q1t_state *st, q1t_stats *out);
 int q1t_reset_stats(q1t_state *st);
 /* enable per-kernel CUDA-event timing (bench only; serialises the stream) */
 int q1t_set_timing(q1t_state *st, int enabled);
 /* engine knobs: "tile_bits" (8..13), "fuse" (0/1), "coalesce_bits" (2/3), "balance" (-1/0/1), "track_support" (0/1), "tma" (0/1), "graphs" (0/1),
- * "inplace_relabel" (-1 never, 0 only when no second column buffer fits into device memory, 1 always).
+ * "inplace_relabel" (-1 never, 0 only when no second column buffer fits into device memory, 1 always),
+ * "fused_remap" (0/1: q1t_group_remap only records the trade; the next dense ladder sweep reads its tiles from the peers' shards over
+ * NVLink and writes into this rank's other registered buffer.  For host layers with one thread per shard: the deferred barriers are
+ * launched from inside the next flush).
  * Returns Q1T_ERR_INVALID_ARGUMENT for unknown keys. */
 int q1t_set_option(q1t_state *st, const char *key, long value);
 

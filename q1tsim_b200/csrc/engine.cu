@@ -186,6 +186,7 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
     if (const char *e = std::getenv("Q1T_GRAPHS")) graphs_ = std::atol(e) != 0;
     if (const char *e = std::getenv("Q1T_PREFETCH_AHEAD")) prefetch_ahead_ = std::atol(e);
     if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
+    if (const char *e = std::getenv("Q1T_FUSED_REMAP")) fused_remap_ = std::atol(e) != 0;
 }
 
 DeviceVectorState::~DeviceVectorState()
@@ -565,7 +566,7 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     // if it comes from the plan cache (the key names the gate list), touches no lazy column half-way, and restores no
     // layout (the relabelling path allocates).  The graph is keyed by everything the issued work depends on.
     const bool may_relabel = final_relabel && (!ident || (want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(sweeps.back().prog)));
-    const bool graph_try = graphs_ && !timing && cur_plan_key_ != 0 && sweeps.size() >= 4 && n_ <= 26 && !tma_ && !cprog_device_shared(device_) &&
+    const bool graph_try = graphs_ && !grp_.pending && !timing && cur_plan_key_ != 0 && sweeps.size() >= 4 && n_ <= 26 && !tma_ && !cprog_device_shared(device_) &&
                            (generate || !any_basis) && !may_relabel;
     uint64_t gkey = 0;
     if (graph_try) {
@@ -724,6 +725,25 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
         bytes_moved[si] = ((tiles_written << P.T) + (gen_here ? 0ull : (1ull << (n_ - pinned_all)))) * 16ull;
         pinned &= ~sweeps[si].touched;
     }
+    // A recorded qubit remap (option fused_remap, group_remap_issue): the first sweep of the batch reads its tiles through
+    // the trade -- from the peers' shards over NVLink, local tiles in between -- instead of waiting for a swap pass.  Needs a
+    // dense ladder sweep, the column in one registered buffer and the other registered buffer free to write into.
+    double2 *gather_dst = nullptr;
+    if (grp_.pending) {
+        bool ok = !generate && which.size() == 1 && cols_.size() == 1 && !g_capture_arena && !tma_ && grp_.open && grp_.bufs[0] && grp_.bufs[1] &&
+                  sweep_uses_ladder_kernel(sweeps[0].prog) && sweeps[0].prog.nrounds <= 3;
+        if (ok) {
+            const double2 *cur = cols_[which[0]].buf;
+            gather_dst = cur == grp_.bufs[0] ? grp_.bufs[1] : cur == grp_.bufs[1] ? grp_.bufs[0] : nullptr;
+            if (std::find(free_bufs_.begin(), free_bufs_.end(), gather_dst) == free_bufs_.end()) gather_dst = nullptr;
+        }
+        if (!gather_dst) {
+            rc = resolve_pending_remap();
+            if (rc) return rc;
+            rc = upload_colptrs(which);                               // the gather pass moved the column into the other buffer
+            if (rc) return rc;
+        }
+    }
     for (size_t si = 0; si < sweeps.size(); ++si) {
         PlannedSweep &ps = sweeps[si];
         const PhaseTab *d_ptabs_here = d_ptabs_;
@@ -786,6 +806,52 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
             }
             if (ok && __builtin_popcount(tgt) >= 2) ps.prog.direct_store = 0;
         }
+        if (si == 0 && gather_dst) {
+            Column &col = cols_[which[0]];
+            free_bufs_.erase(std::find(free_bufs_.begin(), free_bufs_.end(), gather_dst));
+            RemoteGather rg;
+            std::memset(&rg, 0, sizeof rg);
+            rg.k = grp_.pend.k; rg.rank = grp_.rank; rg.P = grp_.P;
+            for (int j = 0; j < rg.k; ++j) { rg.gb[j] = grp_.pend.gb[j]; rg.lp[j] = grp_.pend.lp[j]; }
+            rg.peer_buf = grp_.d_peer_buf;
+            rg.my_mail = nullptr;      // set after the barrier: the slot of its epoch
+            grp_.pending = false;
+            rc = group_barrier();                                     // every rank has finished what precedes, and published its buffer
+            if (rc) return rc;
+            rg.my_mail = grp_.mail + 64 * (grp_.epoch & 1ull);
+            if (std::getenv("Q1T_DEBUG_REMAP"))
+                std::fprintf(stderr, "q1t rank %d: remap k=%d lp0=%d gb0=%d read through sweep 0 of %zu (rounds %d, relabel %d, direct_store %d, leaf %d, scale %g) epoch %llu\n",
+                             grp_.rank, rg.k, rg.lp[0], rg.gb[0], sweeps.size(), ps.prog.nrounds, (int)relabel, ps.prog.direct_store, ps.prog.leaf_fuse,
+                             ps.prog.scale, grp_.epoch);
+            double2 *h[2] = { col.buf, gather_dst };
+            CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
+            fill_byte_tables(ps.prog);
+            time_begin();
+            stats.h2d_bytes += sizeof(SweepProgram);
+            CK(launch_sweep(ps.prog, d_pair_, d_pair_ + 1, 1, d_ptabs_here, nullptr, stream_, ps.prog.leaf_fuse && relabel ? d_leaf_ : nullptr, nullptr,
+                            nullptr, &rg));
+            time_end(stats.sweep_ms);
+            double2 *old = col.buf;
+            col.buf = gather_dst;
+            release_column(old);
+            rc = group_barrier();                                     // nobody overwrites a shard its peers may still be reading
+            if (rc) return rc;
+            stats.kernel_launches++;
+            stats.sweeps++;
+            stats.fused_remaps++;
+            stats.sweep_column_passes += 1;
+            stats.sweep_bytes += bytes_moved[si];
+            stats.peer_swap_bytes += (((1ull << rg.k) - 1ull) << (n_ - rg.k)) * 16ull;     // remote reads of this rank
+            if (relabel) {
+                stats.fused_relabels++;
+                if (ps.prog.leaf_fuse) leaf_fused_ = true;
+                for (int l = 0; l < n_; ++l) perm_[l] = l;
+            } else {
+                rc = upload_colptrs(which);                           // the sweeps that follow run in place in the new buffer
+                if (rc) return rc;
+            }
+            continue;
+        }
         // dense ladder sweeps take their tiles by TMA (planner.cpp apply_tma_layout, kernels.cu ladder_kernel)
         const bool tma_ok = tma_ && !ps.prog.generate && ps.prog.sup_mode == 0 && sweep_uses_ladder_kernel(ps.prog) && tma_available();
         if (!relabel) {
@@ -798,6 +864,7 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
                     stats.tma_sweeps++;
                 } else hcols.clear();
             }
+            fill_byte_tables(ps.prog);
             time_begin();
             // (captured into a graph, the program upload re-reads its source at every replay: pinned copy owned by the graph)
             const SweepProgram *prog_src = &ps.prog, *d_prog = nullptr;
@@ -831,6 +898,7 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
                 stats.tma_sweeps++;
             }
         }
+        fill_byte_tables(ps.prog);
         for (size_t i = 0; i < which.size(); ++i) {
             Column &col = cols_[which[i]];
             double2 *scratch = nullptr;
@@ -861,7 +929,7 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
 
 int DeviceVectorState::run_queue(bool final_relabel)
 {
-    if (queue_.empty()) return Q1T_OK;
+    if (queue_.empty()) return resolve_pending_remap();      // (nothing to fuse a recorded remap into)
     int rc = ensure_device();
     if (rc) return rc;
     std::vector<int> which = queue_cols_;
@@ -870,6 +938,15 @@ int DeviceVectorState::run_queue(bool final_relabel)
     std::vector<LoweredGate> q;
     q.swap(queue_);
     queue_cols_.clear();
+    if (grp_.pending) {
+        // a recorded qubit remap (option fused_remap): only a batch that is planned as fused sweeps can read through it
+        bool fusable = n_ >= 5 && fuse_ && balance_ < 0 && cols_.size() == 1;
+        for (const LoweredGate &g : q) fusable = fusable && (g.kind == LoweredGate::POLY || g.kind == LoweredGate::G1);
+        if (!fusable) {
+            rc = resolve_pending_remap();
+            if (rc) return rc;
+        }
+    }
     auto materialize_all = [&]() -> int {
         for (int c : which) {
             int r = materialize(cols_[c]);
@@ -1106,6 +1183,8 @@ int DeviceVectorState::flush_async()
     int rc = ensure_device();
     if (rc) return rc;
     rc = run_queue(true);
+    if (rc) return rc;
+    rc = resolve_pending_remap();
     if (rc) return rc;
     rc = canonicalize();
     if (rc) return rc;
@@ -1933,10 +2012,64 @@ int DeviceVectorState::group_remap_issue(size_t k, const int *rank_bits, const s
     for (size_t i = 0; i <= k; ++i) a.ins[i] = ins[i];
     static const int interleave = std::getenv("Q1T_SWAP_INTERLEAVE") ? std::atoi(std::getenv("Q1T_SWAP_INTERLEAVE")) : 1;
     a.interleave = interleave;
+    double2 *other = cols_[0].buf == grp_.bufs[0] ? grp_.bufs[1] : cols_[0].buf == grp_.bufs[1] ? grp_.bufs[0] : nullptr;
+    if (fused_remap_ && other && std::find(free_bufs_.begin(), free_bufs_.end(), other) != free_bufs_.end()) {
+        // recorded only: the next dense ladder sweep gathers its tiles through this map (issue_sweeps); anything else
+        // that needs the data first runs it as the swap pass below (resolve_pending_remap)
+        grp_.pend = a;
+        grp_.pending = true;
+        return Q1T_OK;
+    }
+    return group_remap_run(a);
+}
+
+// A recorded trade that no sweep could read through.  It still runs as a gather -- every rank reads its peers' current
+// buffers and writes its own other registered buffer -- never as the in-place swap: ranks decide independently whether
+// their next batch can fuse (their gate lists differ by the rank-selected blocks), and a peer that swaps in place would
+// pull the data away under a peer that gathers.
+int DeviceVectorState::resolve_pending_remap()
+{
+    if (!grp_.pending) return Q1T_OK;
+    grp_.pending = false;
+    if (cols_.size() != 1 || !cols_[0].buf) return fail(Q1T_ERR_UNSUPPORTED, "recorded qubit remap: the state no longer has one dense column");
+    Column &col = cols_[0];
+    double2 *dst = col.buf == grp_.bufs[0] ? grp_.bufs[1] : col.buf == grp_.bufs[1] ? grp_.bufs[0] : nullptr;
+    std::vector<double2 *>::iterator it = std::find(free_bufs_.begin(), free_bufs_.end(), dst);
+    if (!dst || it == free_bufs_.end()) return fail(Q1T_ERR_UNSUPPORTED, "recorded qubit remap: the other registered buffer is not free");
+    free_bufs_.erase(it);
+    CK(cudaSetDevice(device_));
+    RemoteGather rg;
+    std::memset(&rg, 0, sizeof rg);
+    rg.k = grp_.pend.k; rg.rank = grp_.rank; rg.P = grp_.P;
+    for (int j = 0; j < rg.k; ++j) { rg.gb[j] = grp_.pend.gb[j]; rg.lp[j] = grp_.pend.lp[j]; }
+    rg.peer_buf = grp_.d_peer_buf;
+    rg.my_mail = nullptr;      // set after the barrier: the slot of its epoch
+    int rc = group_barrier();
+    if (rc) return rc;
+    rg.my_mail = grp_.mail + 64 * (grp_.epoch & 1ull);
+    if (std::getenv("Q1T_DEBUG_REMAP"))
+        std::fprintf(stderr, "q1t rank %d: remap k=%d lp0=%d gb0=%d as a gather pass, epoch %llu\n", grp_.rank, rg.k, rg.lp[0], rg.gb[0], grp_.epoch);
+    CK(cudaEventRecord(grp_.ev0, stream_));
+    CK(launch_group_gather(col.buf, dst, rg, n_, stream_));
+    CK(cudaEventRecord(grp_.ev1, stream_));
+    grp_.timing_pending = true;
+    stats.kernel_launches++;
+    stats.peer_swap_bytes += (((1ull << rg.k) - 1ull) << (n_ - rg.k)) * 16ull;
+    double2 *old = col.buf;
+    col.buf = dst;
+    release_column(old);
+    return group_barrier();
+}
+
+int DeviceVectorState::group_remap_run(const GroupRemapArgs &a)
+{
+    const size_t k = (size_t)a.k;
+    int rc = Q1T_OK;
+    CK(cudaSetDevice(device_));
     rc = group_barrier();                                             // every rank has finished what precedes, and published its buffer
     if (rc) return rc;
     CK(cudaEventRecord(grp_.ev0, stream_));
-    CK(launch_group_swap(cols_[0].buf, grp_.d_peer_buf, grp_.mail, a, stream_));
+    CK(launch_group_swap(cols_[0].buf, grp_.d_peer_buf, grp_.mail + 64 * (grp_.epoch & 1ull), a, stream_));
     CK(cudaEventRecord(grp_.ev1, stream_));
     grp_.timing_pending = true;
     stats.kernel_launches++;
@@ -2210,6 +2343,10 @@ int DeviceVectorState::set_option(const char *key, long value)
     }
     if (!std::strcmp(key, "graphs")) {
         graphs_ = value != 0;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "fused_remap")) {
+        fused_remap_ = value != 0;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "direct")) {

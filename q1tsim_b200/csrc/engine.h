@@ -144,7 +144,12 @@ private:
         unsigned long long epoch = 0;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         bool timing_pending = false;
+        bool pending = false;                           // option fused_remap: a recorded trade the next sweep will read through
+        GroupRemapArgs pend;
     } grp_;
+    int group_remap_run(const GroupRemapArgs &a);       // barrier, swap pass, barrier
+    int resolve_pending_remap();                        // a recorded trade nobody could fuse: run it as a swap pass now
+    bool fused_remap_ = false;
     void group_collect_timing();
 
     int fail(int code, const std::string &msg) { err_ = msg; return code; }

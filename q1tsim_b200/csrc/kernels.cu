@@ -37,6 +37,15 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+// the same with the 32-bit shared-window address already at hand (no generic -> shared conversion per request)
+__device__ __forceinline__ void cp_async16_s(unsigned saddr, unsigned long long gaddr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gaddr));
+}
+__device__ __forceinline__ void st_global_cs_b(unsigned long long gaddr, double2 v)
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(gaddr), "d"(v.x), "d"(v.y) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait_all()
 {
     asm volatile("cp.async.commit_group;\n" ::);
@@ -345,6 +354,29 @@ struct LadderSteps<NS, kRegBits, LO_SHARED> {
     static __device__ __forceinline__ void run(double2 (&)[kSlots], const RoundDesc &, const SweepProgram &,
                                                const PhaseTab *__restrict__, const double2 *, int, unsigned, unsigned,
                                                const double2 * = nullptr) {}
+};
+
+// One body for every number of steps: step J runs when J >= first = kRegBits - nsteps (a uniform branch per step).
+// The five straight-line instantiations of LadderSteps<NS, ..> are 34 KB of code of which a sweep with rounds of
+// different lengths executes two or three; the instruction caches (32 KB L1.5) hold one body (profiles/r2_ladder_lean.md).
+template <int J>
+struct LadderU {
+    static __device__ __forceinline__ void run(double2 (&a)[kSlots], const RoundDesc &R, const SweepProgram &P, const double2 *s_hiF,
+                                               int he_bits, unsigned il, unsigned ih, const double2 *s_lo, int first)
+    {
+        if (J >= first) {
+            const OpDesc &op = P.ops[R.op_begin + J - first];
+            const double2 lo = s_lo[(op.phase_id << kThrLoBits) + il];
+            const double2 hi = s_hiF[(op.phase_id << he_bits) + ih];          // hi[ih] * tile factor
+            LadderStep<J, J - 1>::run(a, op.m, cmul(lo, hi), 0);
+        }
+        LadderU<J + 1>::run(a, R, P, s_hiF, he_bits, il, ih, s_lo, first);
+    }
+};
+template <>
+struct LadderU<kRegBits> {
+    static __device__ __forceinline__ void run(double2 (&)[kSlots], const RoundDesc &, const SweepProgram &, const double2 *, int, unsigned,
+                                               unsigned, const double2 *, int) {}
 };
 
 template <int NS>
@@ -727,11 +759,24 @@ __device__ __noinline__ void ladder_broadcast_tiles(const double2 *__restrict__ 
 #define PCLK(i) do { } while (0)
 #endif
 
-template <int MAXT, int MINB, bool TMA>
+// Compile-time switches of the lean dense path (A/B builds: python -m q1tsim_b200.build --variant=_x -DQ1T_LADDER_UNIFIED=0 ..)
+#ifndef Q1T_LADDER_UNIFIED
+#define Q1T_LADDER_UNIFIED 0      // (measured: 7.79 vs 7.23 ms per dense sweep -- slower, off) one ladder body with guarded steps instead of one straight-line body per round length
+#endif
+#ifndef Q1T_LADDER_STATIC_ROUNDS
+#define Q1T_LADDER_STATIC_ROUNDS 0
+#endif
+#ifndef Q1T_LADDER_BYTE_ADDR
+#define Q1T_LADDER_BYTE_ADDR 1    // byte-offset tables + 32-bit shared addresses in the load issue and the direct store
+#endif
+// DENSE: instantiation for sweeps over dense columns (no input generation, no support tracking, no broadcast): those
+// paths and their per-round predicates are compiled out (TMA implies it)
+// REMOTE: the tile loads are gathered from the peers' shards (RemoteGather, kernels.h): the fused remap read
+template <int MAXT, int MINB, bool TMA, bool DENSE, bool REMOTE>
 __global__ void __launch_bounds__(MAXT, MINB)
 ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__restrict__ dst_cols,
               const PhaseTab *__restrict__ ptabs, const unsigned long long *__restrict__ gen_idx, double *__restrict__ leaf_out,
-              const __grid_constant__ TmaMaps tmaps)
+              const __grid_constant__ TmaMaps tmaps, const RemoteGather rg)
 {
     extern __shared__ __align__(1024) double2 tile[];
     const SweepProgram &P = c_prog;
@@ -751,14 +796,16 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     // per-thread source / destination offsets: kept in shared memory, not in registers -- with 32
     // amplitudes per thread the compiler spilled them, and a local-memory reload is an L2 round trip
     unsigned long long *const s_off = reinterpret_cast<unsigned long long *>(s_coef + ((P.nphase * ncoef + 1) & ~1));
+    unsigned long long *const s_peer = s_off + 2 * blockDim.x;     // REMOTE: [P] base address of every rank's current shard buffer
     // TMA mode (dense sweeps): the tile arrives by one cp.async.bulk.tensor request issued by thread 0 and
     // lives in shared memory in TMA order (SweepProgram::tma_*); completion is signalled on an mbarrier
     // (a separate instantiation: dense sweeps only, so input generation, support tracking and broadcast
     // sweeps are compiled out of it)
     constexpr bool tma = TMA;
+    constexpr bool dense = TMA || DENSE;
 #define Q1T_TILE_S0 static_cast<unsigned>(__cvta_generic_to_shared(tile))
 #define Q1T_S_BAR (Q1T_TILE_S0 + (16u << T))
-    const bool generate = !TMA && P.generate != 0;
+    const bool generate = !dense && P.generate != 0;
     const bool staged_store = P.direct_store == 0;
     const double scale = P.scale;
     // fused canonical leaf totals (one leaf of 1024 amplitudes per warp in the staged store pass)
@@ -793,7 +840,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         __syncthreads();
     }
     // support tracking: amplitudes that differ from the basis index in a bit of sup_mask are zero
-    const int sup_mode = TMA ? 0 : P.sup_mode;
+    const int sup_mode = dense ? 0 : P.sup_mode;
     const unsigned long long sup_g = (generate || sup_mode) ? gen_idx[col] : 0ull;
     const unsigned long long gen_g = sup_g;
     const unsigned long long sup_mo = sup_mode ? (P.sup_mask & ~P.tile_mask_src) : 0ull;   // pinned outer bits
@@ -807,6 +854,21 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
     }
     s_off[2 * tid] = soff_t;            // only ever read back by the same thread
     s_off[2 * tid + 1] = doff_t;
+    unsigned long long rg_lpmask = 0, rg_mybits = 0;
+    unsigned rg_rank0 = 0;
+    if (REMOTE) {
+        unsigned gbmask = 0;
+        for (int j = 0; j < rg.k; ++j) {
+            rg_lpmask |= 1ull << rg.lp[j];
+            rg_mybits |= (unsigned long long)((rg.rank >> rg.gb[j]) & 1) << rg.lp[j];
+            gbmask |= 1u << rg.gb[j];
+        }
+        rg_rank0 = (unsigned)rg.rank & ~gbmask;
+        for (int r = tid; r < rg.P; r += blockDim.x)
+            s_peer[r] = r == rg.rank ? reinterpret_cast<unsigned long long>(src_cols[col])
+                                     : reinterpret_cast<unsigned long long>(rg.peer_buf[2 * r + (int)(rg.my_mail[2 * r + 1] & 1ull)]);
+        __syncthreads();
+    }
     // broadcast sweep (see ladder_broadcast_tiles)?  bc_keep = tile-local mask of the non-target bits,
     // all ones when the sweep does not qualify for this column
     unsigned bc_keep = 0xffffffffu;
@@ -889,9 +951,33 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         const double2 *__restrict__ p = src + (outer_base(P.o_src, o, P.n_outer) | s_off[2 * tid]);
         unsigned sw = sw_tid;
         asm volatile("" : "+r"(sw));      // keeps the 32 destination addresses from being hoisted out of the tile loop (and spilled)
-        if (sup_mt == 0u) {
+        if (REMOTE) {
+            // element l of this rank's new shard lives on rank r[gb := l_lp] at index l[lp := r_gb]
+            const unsigned long long t = outer_base(P.o_src, o, P.n_outer) | s_off[2 * tid];
+            unsigned sr_t = rg_rank0;
+            for (int j = 0; j < rg.k; ++j) sr_t |= (unsigned)((t >> rg.lp[j]) & 1ull) << rg.gb[j];
+            const unsigned long long t2 = ((t & ~rg_lpmask) | rg_mybits) << 4;
+            const unsigned s0 = Q1T_TILE_S0;
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                const unsigned long long hi = P.ld_hi[i];
+                unsigned sr = sr_t;
+                for (int j = 0; j < rg.k; ++j) sr |= (unsigned)((hi >> rg.lp[j]) & 1ull) << rg.gb[j];
+                cp_async16_s(s0 + (sw ^ P.ld_sw_hi[i]), s_peer[sr] + t2 + ((hi & ~rg_lpmask) << 4));
+            }
+        } else if (sup_mt == 0u) {
+#if Q1T_LADDER_BYTE_ADDR
+            // nine instructions per request (two constant loads, xor, + shared base, 64-bit index add, 64-bit scale-and-
+            // add, request) cut to six: byte offsets from the program, the address kept as an integer
+            unsigned long long pb = reinterpret_cast<unsigned long long>(p);
+            asm volatile("" : "+l"(pb));
+            const unsigned s0 = Q1T_TILE_S0;
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) cp_async16_s(s0 + (sw ^ P.ld_sw_hi[i]), pb + P.ld_hi_b[i]);
+#else
 #pragma unroll
             for (int i = 0; i < kSlots; ++i) cp_async16(tile_b + (sw ^ P.ld_sw_hi[i]), p + P.ld_hi[i]);
+#endif
         } else {
             // only the elements inside the support exist in memory; the others are zeros that no round
             // reads (its loads are masked by zmask / smask), so they are not even written to the tile
@@ -990,7 +1076,15 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
         __syncthreads();                       // tile o and its tables are visible to the whole CTA
         PCLK(2);
         const double2 *const hiF = s_hiF + buf * ntab;
+#if Q1T_LADDER_STATIC_ROUNDS
+        // dense instantiation: the round loop unrolled (launched for nrounds <= 3 only), so that the round's tables are
+        // constant-bank operands at fixed offsets instead of uniform loads through a runtime round index
+#pragma unroll (dense ? 3 : 1)
+        for (int r = 0; dense ? r < 3 : r < P.nrounds; ++r) {
+            if (dense && r >= P.nrounds) break;
+#else
         for (int r = 0; r < P.nrounds; ++r) {
+#endif
             const RoundDesc &R = P.rounds[r];
             const bool last = r + 1 == P.nrounds;
             unsigned thrL = 0;
@@ -1003,7 +1097,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             }
             PCLK(4);
             // a thread that differs from the basis index in a still-pinned thread bit holds only zeros
-            const bool all_zero = ((thrL ^ sup_vt) & R.zmask) != 0u;
+            const bool all_zero = !dense && ((thrL ^ sup_vt) & R.zmask) != 0u;
             double2 a[kSlots];
             if (r == 0 && generate) {
                 // the basis element lives in exactly one tile of the grid and one slot of one thread
@@ -1019,7 +1113,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 }
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) a[s] = make_double2(s == (int)gen_slot ? P.gen_scale : 0.0, 0.0);
-            } else if (R.zmask == 0u && R.smask == 0u) {
+            } else if (dense || (R.zmask == 0u && R.smask == 0u)) {
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) a[s] = *reinterpret_cast<const double2 *>(tile_b + (swT ^ R.sw_slot[s]));
             } else {
@@ -1044,6 +1138,9 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             }
             PCLK(6);
             const unsigned il = tid & ((1u << kThrLoBits) - 1u), ih = tid >> kThrLoBits;
+#if Q1T_LADDER_UNIFIED
+            if (!all_zero) LadderU<0>::run(a, R, P, hiF, he_bits, il, ih, s_lo, kRegBits - (int)R.nsteps);
+#else
             if (!all_zero)
             switch (R.nsteps) {
             case 1: LadderSteps<1, kRegBits - 1, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
@@ -1056,6 +1153,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             default: LadderSteps<4, kRegBits - 4, true>::run(a, R, P, ptabs, hiF, he_bits, il, ih, s_lo); break;
 #endif
             }
+#endif
             PCLK(7);
             if (last && !staged_store) {
                 double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
@@ -1063,13 +1161,24 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
 #pragma unroll
                     for (int s = 0; s < kSlots; ++s) a[s] = make_double2(a[s].x * scale, a[s].y * scale);
                 }
+#if Q1T_LADDER_BYTE_ADDR
+                unsigned long long qb = reinterpret_cast<unsigned long long>(q);
+                asm volatile("" : "+l"(qb));
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) st_global_cs_b(qb + P.ds_slot_b[s], a[s]);
+#else
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) st_global_cs(q + P.ds_slot[s], a[s]);
+#endif
             } else if (!all_zero || last) {
                 // (zeros of an all-zero thread are never read by a later round; the store pass after
                 //  the last round reads everything)
+                // the 32 addresses are recomputed (a constant load and an xor each): kept from the round's loads they
+                // do not fit beside 32 amplitudes and were spilled to local memory, 31 stores + 31 loads per round
+                unsigned swS = swT;
+                asm volatile("" : "+r"(swS));
 #pragma unroll
-                for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swT ^ R.sw_slot[s])) = a[s];
+                for (int s = 0; s < kSlots; ++s) *reinterpret_cast<double2 *>(tile_b + (swS ^ R.sw_slot[s])) = a[s];
             }
         }
         PCLK(8);
@@ -1081,6 +1190,13 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
             double2 *__restrict__ q = dst + (outer_base(P.o_dst, o, P.n_outer) | s_off[2 * tid + 1]);
             unsigned swl = sw_lo;
             asm volatile("" : "+r"(swl));     // as in issue_loads: no hoisting of the 32 addresses
+#if Q1T_LADDER_BYTE_ADDR
+            unsigned long long qb = reinterpret_cast<unsigned long long>(q);
+            asm volatile("" : "+l"(qb));
+#define Q1T_STAGED_ST(i, x) st_global_cs_b(qb + P.st_off_hi_b[i], x)
+#else
+#define Q1T_STAGED_ST(i, x) st_global_cs(q + P.st_off_hi[i], x)
+#endif
             double leaf_acc = 0.0;
             {   // first half: read and store right away
                 double2 v[kSlots / 2];
@@ -1090,7 +1206,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 for (int i = 0; i < kSlots / 2; ++i) {
                     const double2 x = scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i];
                     if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
-                    st_global_cs(q + P.st_off_hi[i], x);
+                    Q1T_STAGED_ST(i, x);
                 }
             }
             PCLK(11);
@@ -1111,7 +1227,7 @@ ladder_kernel(const double2 *const *__restrict__ src_cols, double2 *const *__res
                 for (int i = 0; i < kSlots / 2; ++i) {
                     const double2 x = scale != 1.0 ? make_double2(v[i].x * scale, v[i].y * scale) : v[i];
                     if (leaf_fuse) leaf_acc = __dadd_rn(leaf_acc, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
-                    st_global_cs(q + P.st_off_hi[kSlots / 2 + i], x);
+                    Q1T_STAGED_ST(kSlots / 2 + i, x);
                 }
             }
             if (leaf_fuse) {
@@ -1242,10 +1358,16 @@ static void cprog_release(int dev, cudaStream_t stream)
     if (cprog_device_shared(dev) && g_cprog.evt[dev]) cudaEventRecord(g_cprog.evt[dev], stream);
 }
 
+bool sweep_can_gather_remote(const SweepProgram &prog)
+{
+    return sweep_uses_ladder_kernel(prog) && prog.tma_nreq == 0 && !prog.generate && prog.sup_mode == 0 && prog.nrounds <= 3;
+}
+
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
-                         double *d_leaf_out, const double2 *const *h_src_cols, const SweepProgram *d_prog)
+                         double *d_leaf_out, const double2 *const *h_src_cols, const SweepProgram *d_prog, const RemoteGather *remote)
 {
+    if (remote && remote->k > 0 && (!sweep_can_gather_remote(prog) || ncols != 1)) return cudaErrorInvalidValue;
     TmaMaps tmaps;
     if (prog.tma_nreq > 0) {
         // a program in TMA layout can only run in the ladder kernel with tensor maps of its source columns
@@ -1289,14 +1411,23 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
     dim3 grid((unsigned)(1ull << prog.n_outer), (unsigned)ncols, 1);
     dim3 block(1u << prog.TB, 1, 1);
     if (ladder) {
-        typedef void (*LadderFn)(const double2 *const *, double2 *const *, const PhaseTab *, const unsigned long long *, double *, const TmaMaps);
-        static const LadderFn fns[2] = { ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false>, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true> };
-        static int attr_dev_mask[2] = { 0, 0 };            // function attributes are per device
+        typedef void (*LadderFn)(const double2 *const *, double2 *const *, const PhaseTab *, const unsigned long long *, double *, const TmaMaps,
+                                 const RemoteGather);
+        static const LadderFn fns[4] = { ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false, false, false>,
+                                         ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, true, true, false>,
+                                         ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false, true, false>,
+                                         ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false, true, true> };
+        static int attr_dev_mask[4] = { 0, 0, 0, 0 };      // function attributes are per device
+        static const bool dense_variant = !(std::getenv("Q1T_LADDER_DENSE") && std::atoi(std::getenv("Q1T_LADDER_DENSE")) == 0);
         int nsm = 148, occ = 0;
-        const int variant = prog.tma_nreq > 0 ? 1 : 0;
+        const bool gather = remote && remote->k > 0;
+        const int variant = gather ? 3 : prog.tma_nreq > 0 ? 1 : (dense_variant && !prog.generate && prog.sup_mode == 0 && prog.nrounds <= 3) ? 2 : 0;
+        RemoteGather rg;
+        std::memset(&rg, 0, sizeof rg);
+        if (gather) rg = *remote;
         const LadderFn fn = fns[variant];
         if (!((attr_dev_mask[variant] >> (dev & 31)) & 1)) {
-            const int max_lsmem = (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (3 * kHiEntries + 1 + (1 << kThrLoBits)) + sizeof(double) * kMaxPhase * (kMaxBits + 1) + 16 * kSmallThreads + 32);
+            const int max_lsmem = (int)((sizeof(double2) << 12) + sizeof(double2) * kMaxPhase * (3 * kHiEntries + 1 + (1 << kThrLoBits)) + sizeof(double) * kMaxPhase * (kMaxBits + 1) + 16 * kSmallThreads + 32 + 256);
             e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_lsmem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1305,7 +1436,7 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         }
         const size_t lsmem = (sizeof(double2) << prog.T) + 16 +
                              sizeof(double2) * (((size_t)prog.nphase << he_bits) * 2 + prog.nphase + ((size_t)prog.nphase << kThrLoBits)) +
-                             sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x;
+                             sizeof(double) * (((size_t)prog.nphase * (prog.n_outer + 1) + 1) & ~(size_t)1) + 16 * (size_t)block.x + (gather ? 256 : 0);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block.x, lsmem);
         if (e != cudaSuccess) return e;
@@ -1315,7 +1446,7 @@ cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_c
         if (per_col < 1) per_col = 1;
         if (per_col > (1ull << prog.n_outer)) per_col = 1ull << prog.n_outer;
         dim3 pgrid((unsigned)per_col, (unsigned)ncols, 1);
-        fn<<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps);
+        fn<<<pgrid, block, lsmem, stream>>>(d_src_cols, d_dst_cols, d_ptabs, d_gen_idx, d_leaf_out, tmaps, rg);
         e = cudaGetLastError();
         cprog_release(dev, stream);
         return e;
@@ -1698,7 +1829,9 @@ __global__ void group_barrier_kernel(unsigned long long *const *__restrict__ pee
     const int t = threadIdx.x;
     if (t >= P || t == rank) return;
     unsigned long long *theirs = peer_mail[t];
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(theirs + 2 * rank + 1), "l"(cur) : "memory");
+    // the buffer index goes into the slot of this epoch's parity: a rank that is already past its next barrier (which
+    // publishes the buffer it moved INTO) must not change what a slower peer's kernel after THIS barrier still has to read
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(theirs + 2 * rank + 1 + 64 * (epoch & 1ull)), "l"(cur) : "memory");
     asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(theirs + 2 * rank), "l"(epoch) : "memory");
     unsigned long long seen = 0;
     for (unsigned long long spins = 0;; ++spins) {
@@ -1775,6 +1908,42 @@ cudaError_t launch_group_swap(double2 *d_mine, void *const *d_peer_buf, const un
     return cudaGetLastError();
 }
 
+// The remap as an out-of-place gather (option fused_remap, when no sweep follows that could read through the trade):
+// dst[l] = shard of rank r[gb := l_lp] at index l[lp := r_gb].  Every rank only READS its peers' current buffers and
+// writes its own other buffer, so it may run beside peers that do the same read inside a ladder sweep.
+__global__ void __launch_bounds__(256)
+group_gather_kernel(const double2 *__restrict__ mine, double2 *__restrict__ dst, RemoteGather rg, unsigned long long nelem)
+{
+    __shared__ unsigned long long s_peer[32];
+    if (threadIdx.x < 32 && (int)threadIdx.x < rg.P)
+        s_peer[threadIdx.x] = (int)threadIdx.x == rg.rank
+                                  ? reinterpret_cast<unsigned long long>(mine)
+                                  : reinterpret_cast<unsigned long long>(rg.peer_buf[2 * threadIdx.x + (int)(rg.my_mail[2 * threadIdx.x + 1] & 1ull)]);
+    __syncthreads();
+    unsigned long long lpmask = 0, mybits = 0;
+    unsigned gbmask = 0;
+    for (int j = 0; j < rg.k; ++j) {
+        lpmask |= 1ull << rg.lp[j];
+        mybits |= (unsigned long long)((rg.rank >> rg.gb[j]) & 1) << rg.lp[j];
+        gbmask |= 1u << rg.gb[j];
+    }
+    const unsigned rank0 = (unsigned)rg.rank & ~gbmask;
+    for (unsigned long long l = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; l < nelem; l += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned sr = rank0;
+        for (int j = 0; j < rg.k; ++j) sr |= (unsigned)((l >> rg.lp[j]) & 1ull) << rg.gb[j];
+        const double2 *__restrict__ sp = reinterpret_cast<const double2 *>(s_peer[sr]);
+        st_global_cs(dst + l, __ldcs(sp + ((l & ~lpmask) | mybits)));
+    }
+}
+cudaError_t launch_group_gather(const double2 *d_mine, double2 *d_dst, const RemoteGather &rg, int n, cudaStream_t stream)
+{
+    const unsigned long long nelem = 1ull << n;
+    unsigned long long blocks = (nelem + 255) / 256;
+    if (blocks > 148ull * 16ull) blocks = 148ull * 16ull;
+    group_gather_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_mine, d_dst, rg, nelem);
+    return cudaGetLastError();
+}
+
 // CUDA loads a kernel at its first launch (lazy module loading), and loading may synchronise the context: a swap kernel
 // launched for the first time while a barrier kernel of ANOTHER shard of this process spins on the same device would wait
 // for that barrier, which waits for a barrier this thread has not launched yet.  Both kernels are loaded before the first
@@ -1788,6 +1957,8 @@ void group_kernels_preload()
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, group_barrier_kernel);
     cudaFuncGetAttributes(&fa, group_swap_kernel);
+    cudaFuncGetAttributes(&fa, group_gather_kernel);
+    cudaFuncGetAttributes(&fa, ladder_kernel<kSmallThreads, Q1T_LADDER_MIN_CTAS, false, true, true>);
     cudaGetLastError();
     done_mask |= 1 << (dev & 31);
 }

@@ -17,12 +17,27 @@ struct GenericGateArgs {
     unsigned long long cmask;                         // control positions that must be 1
 };
 
+// Fused remap read (ladder kernel, dense sweeps): a pending trade of k rank bits gb[j] with k index bits lp[j] of the
+// shards is not run as a swap pass of its own; the sweep that follows gathers its source tiles from the peers instead --
+// element l of rank r is read from rank r[gb[j] := l_lp[j]] at index l[lp[j] := r_gb[j]] (group_swap_kernel's map) --
+// and writes its result into this rank's other registered buffer.  Local tiles are swept while the remote ones arrive
+// over NVLink.
+constexpr int kMaxRemapBits = 4;       // rank bits traded per remap
+struct RemoteGather {
+    int k, rank, P;                                  // k = 0: off
+    int gb[kMaxRemapBits], lp[kMaxRemapBits];
+    void *const *peer_buf;                           // [P][2], device memory (PeerGroup::d_peer_buf)
+    const unsigned long long *my_mail;               // this rank's mailbox: [2 r + 1] = buffer index rank r published
+};
+
 // d_leaf_out: when prog.leaf_fuse is set (ladder kernel, staged store), receives the canonical leaf totals
 // of the written column(s), 2^(n-10) doubles per column (what launch_leaf_totals would compute afterwards)
 cudaError_t launch_sweep(const SweepProgram &prog, const double2 *const *d_src_cols, double2 *const *d_dst_cols,
                          int ncols, const PhaseTab *d_ptabs, const unsigned long long *d_gen_idx, cudaStream_t stream,
                          double *d_leaf_out = nullptr, const double2 *const *h_src_cols = nullptr,
-                         const SweepProgram *d_prog = nullptr);
+                         const SweepProgram *d_prog = nullptr, const RemoteGather *remote = nullptr);
+// true if launch_sweep() can run this program with a RemoteGather (dense ladder sweep, cp.async loads)
+bool sweep_can_gather_remote(const SweepProgram &prog);
 // d_prog: device-resident copy of `prog` (the caller keeps it alive and in sync): kernels other than the ladder
 // kernel then read the program from there and nothing is uploaded -- batches replayed as CUDA graphs
 // h_src_cols: host copy of the source column pointers, needed (only) by programs in TMA layout (prog.tma_nreq > 0)
@@ -53,7 +68,6 @@ cudaError_t launch_collapse(const double2 *d_in, double2 *d_out0, double2 *d_out
 cudaError_t launch_product_state(double2 *d_col, int n, const double2 *d_coefs, cudaStream_t stream);
 cudaError_t launch_peer_swap(double2 *d_mine, double2 *d_theirs, int n, int L, int a, cudaStream_t stream);
 // peer group: device-side barrier over mapped mailboxes, and the multi-bit qubit remap (kernels.cu)
-constexpr int kMaxRemapBits = 4;
 struct GroupRemapArgs {
     int n, k, P, rank;               // index bits of the shard, bits traded, ranks, this rank
     int gb[kMaxRemapBits];           // rank bits
@@ -66,6 +80,7 @@ cudaError_t launch_group_barrier(unsigned long long *const *d_peer_mail, unsigne
                                  unsigned long long epoch, unsigned long long cur, cudaStream_t stream);
 cudaError_t launch_group_swap(double2 *d_mine, void *const *d_peer_buf, const unsigned long long *d_my_mail, const GroupRemapArgs &a,
                               cudaStream_t stream);
+cudaError_t launch_group_gather(const double2 *d_mine, double2 *d_dst, const RemoteGather &rg, int n, cudaStream_t stream);
 cudaError_t launch_set_basis(double2 *d_col, unsigned long long idx, cudaStream_t stream);
 
 }  // namespace q1t

@@ -152,7 +152,19 @@ struct SweepProgram {
     uint64_t tma_gdim[5];
     uint64_t tma_req_line[kMaxTmaReq];
     uint8_t tma_pi[kMaxTileBits + 3];
+    // ld_hi / st_off_hi / ds_slot in bytes (fill_byte_tables, right before a launch): the ladder kernel adds them to a
+    // byte address instead of scaling 32 element indices per tile
+    uint64_t ld_hi_b[kSlots], st_off_hi_b[kSlots], ds_slot_b[kSlots];
 };
+
+inline void fill_byte_tables(SweepProgram &P)
+{
+    for (int i = 0; i < kSlots; ++i) {
+        P.ld_hi_b[i] = P.ld_hi[i] << 4;
+        P.st_off_hi_b[i] = P.st_off_hi[i] << 4;
+        P.ds_slot_b[i] = P.ds_slot[i] << 4;
+    }
+}
 
 // per PHASE op, in global memory
 struct alignas(16) PhaseTab {

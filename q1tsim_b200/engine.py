@@ -40,7 +40,8 @@ class Stats(C.Structure):
                 ("read_passes", C.c_uint64), ("kernel_launches", C.c_uint64), ("permute_sweeps", C.c_uint64),
                 ("fallback_sweeps", C.c_uint64), ("fused_relabels", C.c_uint64), ("sweep_bytes", C.c_uint64), ("sweep_ms", C.c_double), ("read_ms", C.c_double),
                 ("peer_swap_ms", C.c_double), ("peer_swap_bytes", C.c_uint64), ("plan_cache_hits", C.c_uint64),
-                ("tma_sweeps", C.c_uint64), ("graph_captures", C.c_uint64), ("graph_replays", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("tma_sweeps", C.c_uint64), ("graph_captures", C.c_uint64), ("graph_replays", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("fused_remaps", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

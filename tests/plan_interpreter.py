@@ -59,7 +59,8 @@ class SweepProgram(C.Structure):
                 ("rounds", RoundDesc * K_MAX_ROUNDS), ("ops", OpDesc * K_MAX_OPS),
                 ("tma_nreq", C.c_int32), ("tma_req_bytes", C.c_uint32), ("tma_box", C.c_uint32 * 5), ("tma_pad", C.c_uint32),
                 ("tma_gstride", C.c_uint64 * 4), ("tma_gdim", C.c_uint64 * 5), ("tma_req_line", C.c_uint64 * K_MAX_TMA_REQ),
-                ("tma_pi", C.c_uint8 * (K_MAX_TILE + 3))]
+                ("tma_pi", C.c_uint8 * (K_MAX_TILE + 3)),
+                ("ld_hi_b", C.c_uint64 * K_SLOTS), ("st_off_hi_b", C.c_uint64 * K_SLOTS), ("ds_slot_b", C.c_uint64 * K_SLOTS)]
 
 
 class PhaseTab(C.Structure):

@@ -96,8 +96,10 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-def _worker_one_gpu(rank, world, port, n, q):
+def _worker_one_gpu(rank, world, port, n, q, fused=False):
     sys.path.insert(0, ROOT)
+    if fused:
+        os.environ["Q1T_FUSED_REMAP"] = "1"      # read when an engine state is created (engine.cu)
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -141,6 +143,7 @@ def _worker_one_gpu(rank, world, port, n, q):
         out["product_rel_l2"] = float(np.linalg.norm(full - rp.column(0)) / np.linalg.norm(rp.column(0)))
         out["product_closed_form"] = float(np.linalg.norm(full - W.qft_of_product_state(n, coefs, np.arange(1 << n))))
         out["remaps_product"] = sp.remaps
+        out["fused_remaps_product"] = int(sp.local.st.stats().get("fused_remaps", 0))
         # (c) identical amplitudes on both sides -> bit-exact outcomes through the rank-ordered canonical chain
         psi = rp.column(0)
         nl = 1 << sp.n_local
@@ -192,6 +195,34 @@ def test_sharded_engine_on_one_gpu(world, n):
         assert o["remaps_0"] == 0 and o["remaps_1"] == 0          # QFT from |0..0>: no exchange at all (replicated start + initial layout)
         assert o["product_rel_l2"] < 1e-10 and o["product_closed_form"] < 1e-10
         assert 1 <= o["remaps_product"] <= 2                      # dense input: one multi-bit remap (kernels.cu group_swap_kernel)
+        assert o["measure_equal"]
+        assert o["gates_rel_l2"] < 1e-10
+
+
+@pytest.mark.parametrize("world,n", [(2, 16), (4, 17), (8, 18), (2, 22)])
+def test_sharded_engine_on_one_gpu_fused_remap(world, n):
+    """Option fused_remap: the remap of the dense QFT is not a swap pass; the sweep that follows reads its tiles from the
+    peers' shards (kernels.cu ladder_kernel<.., REMOTE>, engine.cu issue_sweeps).  Same checks as above, plus: the
+    fused path did run for the dense input, and remaps that no ladder sweep follows fall back to the swap pass."""
+    import torch.multiprocessing as mp
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_one_gpu, args=(r, world, port, n, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for o in outs:
+        assert o["group_ok"]
+        assert o["qft_rel_l2_0"] < 1e-10 and o["qft_rel_l2_1"] < 1e-10
+        assert o["product_rel_l2"] < 1e-10 and o["product_closed_form"] < 1e-10
+        assert 1 <= o["remaps_product"] <= 2
+        assert o["fused_remaps_product"] >= 1
         assert o["measure_equal"]
         assert o["gates_rel_l2"] < 1e-10
 
