@@ -290,6 +290,7 @@ void DeviceVectorState::release_column(double2 *p)
 
 int DeviceVectorState::init_zero_state()
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     int rc = ensure_device();
     if (rc) return rc;
     // |0..0> is kept as a lazy basis column: the first fused sweep synthesises it on the fly
@@ -305,6 +306,7 @@ int DeviceVectorState::init_zero_state()
 // vectorstate.rs:62-83
 int DeviceVectorState::init_from_qubit_coefs(const double *coefs)
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     int rc = ensure_device();
     if (rc) return rc;
     std::vector<double2> nc(2 * (size_t)n_);
@@ -336,6 +338,7 @@ static unsigned long long physical_index(uint64_t logical, const std::vector<int
 // the state becomes the product state of `coefs` in place (its column buffers stay the ones it has)
 int DeviceVectorState::set_product_state(const double *coefs)
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     int rc = ensure_device();
     if (rc) return rc;
     queue_.clear();
@@ -1551,6 +1554,7 @@ int DeviceVectorState::collapse_columns(size_t qbit, const double *w0s, const si
 // ---------------------------------------------------------------------------
 int DeviceVectorState::init_empty()
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     int rc = ensure_device();
     if (rc) return rc;
     Column c;                   // lazy all-zero column: generated by the first sweep, never memset + read
@@ -1743,6 +1747,7 @@ int DeviceVectorState::scale_split_columns(const double *f0, const double *f1, c
 // replace the column list by basis states (idx) or all-zero columns (idx == UINT64_MAX)
 int DeviceVectorState::replace_columns(size_t ncols, const uint64_t *idx, const size_t *counts)
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     int rc = ensure_device();
     if (rc) return rc;
     queue_.clear();
@@ -1767,6 +1772,7 @@ int DeviceVectorState::replace_columns(size_t ncols, const uint64_t *idx, const 
 // peer exchange over CUDA IPC: export a column, swap in place with a partner's mapped column
 int DeviceVectorState::ipc_export(size_t col, unsigned char *handle64)
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     void *p = nullptr;
     int rc = column_ptr(col, &p);
     if (rc) return rc;
@@ -1779,6 +1785,7 @@ int DeviceVectorState::ipc_export(size_t col, unsigned char *handle64)
 
 int DeviceVectorState::peer_swap(size_t col, const unsigned char *peer_handle64, size_t local_qubit, int my_bit)
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     if (col >= cols_.size() || local_qubit >= (size_t)n_ || n_ < 2) return fail(Q1T_ERR_INVALID_ARGUMENT, "peer_swap: bad argument");
     void *mine = nullptr;
     int rc = column_ptr(col, &mine);
@@ -2080,6 +2087,7 @@ int DeviceVectorState::group_remap_run(const GroupRemapArgs &a)
 int DeviceVectorState::group_close()
 {
     if (!grp_.exported) return Q1T_OK;
+    resolve_pending_remap();
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
     group_collect_timing();
@@ -2238,6 +2246,7 @@ int DeviceVectorState::measure_all_into(const size_t *cbits, size_t ncbits, uint
 // vectorstate.rs:402-408
 int DeviceVectorState::reset(size_t bit, q1t_rng rng)
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     std::vector<uint64_t> m(shots_ ? shots_ : 1, 0);
     int rc = measure_into(bit, 0, m.data(), shots_, rng, true);
     if (rc) return rc;
@@ -2250,6 +2259,7 @@ int DeviceVectorState::reset(size_t bit, q1t_rng rng)
 // vectorstate.rs:410-415
 int DeviceVectorState::reset_all()
 {
+    { const int rcp = resolve_pending_remap(); if (rcp) return rcp; }      // a recorded qubit remap: the peers still read this shard through it
     int rc = ensure_device();
     if (rc) return rc;
     queue_.clear();
