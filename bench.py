@@ -121,10 +121,11 @@ def measured_peak():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per dense ladder launch, from the round's committed ncu capture"""
-    p = os.path.join(ROOT, "profiles", "r2_ncu_dense_ladder.json")
-    if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["dram_bytes_per_launch"]), "profiles/r2_ncu_dense_ladder.json (ncu --set full, %s)" % d.get("command", "")
+    for name in ("r2_ncu_dense_ladder_v2.json", "r2_ncu_dense_ladder.json"):       # (v2: the kernel as it is now, tools/ncu_summary.py)
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            return float(d["dram_bytes_per_launch"]), "profiles/%s (ncu --set full, %s)" % (name, d.get("command", ""))
     return None, None
 
 

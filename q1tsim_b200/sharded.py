@@ -22,6 +22,7 @@ composition around it:
 All ranks must make the same calls in the same order (SPMD).
 """
 import math
+import os
 
 import numpy as np
 
@@ -242,6 +243,13 @@ class EngineLocal:
         blob = (C.c_ubyte * (192 * P)).from_buffer_copy(b"".join(allh))
         self.st._chk(L.q1t_group_open(self.st._p, P, rank, blob, None))
         self.has_group = True
+        # The remap read through by the sweep that follows it (engine option fused_remap) instead of a swap pass of its
+        # own: measured on B200 + NVLink 5 with QFT-31/32 on a dense input -- 2 ranks 58.1 -> 55.5 ms per circuit (half
+        # of every tile is local and is swept while the other half arrives), 4 ranks 60.3 -> 65.5 ms (3/4 of the shard is
+        # pulled with reads only, 415 GB/s against the swap kernel's 680 GB/s of reads + posted writes).  On by default
+        # for 2 ranks; Q1T_FUSED_REMAP=0/1 overrides.
+        if os.environ.get("Q1T_FUSED_REMAP") is None and P == 2:
+            self.st.set_option("fused_remap", 1)
 
     def group_remap(self, rank_bits, local_qubits):
         C = self.C
