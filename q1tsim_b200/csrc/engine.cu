@@ -213,7 +213,7 @@ DeviceVectorState::~DeviceVectorState()
         scratch_free(device_, d_totals_, sizeof(double) * totals_cap_);
         scratch_free(device_, d_chosen_, sizeof(double) * draws_cap_);
         scratch_free(device_, d_idx_, sizeof(uint64_t) * draws_cap_);
-        scratch_free(device_, d_mat_, sizeof(double2) << (2 * kMaxGenericBits));
+        scratch_free(device_, d_mat_, sizeof(double2) * mat_cap_);
         scratch_free(device_, d_pair_, sizeof(double2 *) * 2);
         scratch_free(device_, d_gen_, sizeof(unsigned long long) * gen_cap_);
         if (ev0_) cudaEventDestroy(ev0_);
@@ -240,6 +240,7 @@ int DeviceVectorState::ensure_device()
     CK(cudaEventCreate(&ev1_));
     CK(scratch_alloc(device_, (void **)&d_ptabs_, sizeof(PhaseTab) * kMaxPhase));
     CK(scratch_alloc(device_, (void **)&d_mat_, sizeof(double2) << (2 * kMaxGenericBits)));
+    mat_cap_ = (size_t)1 << (2 * kMaxGenericBits);
     CK(scratch_alloc(device_, (void **)&d_pair_, sizeof(double2 *) * 2));
     return Q1T_OK;
 }
@@ -495,6 +496,38 @@ static void to_generic(const LoweredGate &g, LoweredGate &out)
 int DeviceVectorState::run_generic(const LoweredGate &g, const std::vector<int> &which)
 {
     const int k = (int)g.pos.size();
+    if (k > kMaxGenericBits - 1) {
+        // 6..10 targets: groups staged in shared memory, outputs accumulated from the transposed matrix (kernels.cu)
+        if (k > kMaxBigGenericBits || k > n_) return fail(Q1T_ERR_UNSUPPORTED, "dense gate blocks on more than 10 target qubits are not supported");
+        GenericBigArgs b;
+        std::memset(&b, 0, sizeof b);
+        b.n = n_; b.k = k; b.cmask = g.cmask;
+        std::vector<int> sorted = g.pos;
+        std::sort(sorted.begin(), sorted.end());
+        for (int j = 0; j < k; ++j) { b.pos[j] = g.pos[j]; b.sorted_pos[j] = sorted[j]; }
+        const size_t G = (size_t)1 << k;
+        if (G * G > mat_cap_) {
+            CK(cudaStreamSynchronize(stream_));
+            if (d_mat_) scratch_free(device_, d_mat_, sizeof(double2) * mat_cap_);
+            d_mat_ = nullptr;
+            CK(scratch_alloc(device_, (void **)&d_mat_, sizeof(double2) * G * G));
+            mat_cap_ = G * G;
+        }
+        std::vector<cplx> mt(G * G);
+        for (size_t i = 0; i < G; ++i)
+            for (size_t h = 0; h < G; ++h) mt[h * G + i] = g.mat[i * G + h];
+        CK(cudaMemcpyAsync(d_mat_, mt.data(), sizeof(double2) * G * G, cudaMemcpyHostToDevice, stream_));
+        CK(cudaStreamSynchronize(stream_));                 // (the transposed copy is a local)
+        time_begin();
+        CK(launch_generic_gate_big(d_colptrs_, (int)which.size(), b, d_mat_, stream_));
+        time_end(stats.sweep_ms);
+        stats.kernel_launches++;
+        stats.sweeps++;
+        stats.fallback_sweeps++;
+        stats.sweep_column_passes += which.size();
+        stats.sweep_bytes += (uint64_t)which.size() * (32ull << n_);
+        return Q1T_OK;
+    }
     GenericGateArgs a;
     std::memset(&a, 0, sizeof a);
     std::vector<int> sorted = g.pos;

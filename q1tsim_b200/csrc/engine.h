@@ -130,6 +130,7 @@ private:
     double *d_totals_ = nullptr; size_t totals_cap_ = 0;
     double *d_chosen_ = nullptr; uint64_t *d_idx_ = nullptr; size_t draws_cap_ = 0;
     double2 *d_mat_ = nullptr;
+    size_t mat_cap_ = 0;                     // complex entries d_mat_ holds (grows for dense blocks on more than 6 targets)
     double2 **d_pair_ = nullptr;
     unsigned long long *d_gen_ = nullptr; size_t gen_cap_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

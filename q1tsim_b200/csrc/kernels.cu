@@ -1489,6 +1489,45 @@ __global__ void generic_gate_kernel(double2 *const *__restrict__ cols, int n, in
     }
 }
 
+// The same with the 2^K amplitudes of a group in REGISTERS (K <= 5: the runtime-indexed array above lives in local memory)
+// and the matrix in shared memory (every thread reads the same entry: a broadcast).  One thread per group; consecutive
+// threads hold consecutive groups, so a load of slot h is coalesced whenever the low index bits are not targets.
+template <int K>
+__global__ void __launch_bounds__(128)
+generic_gate_reg_kernel(double2 *const *__restrict__ cols, int n, GenericGateArgs g, const double2 *__restrict__ mat)
+{
+    constexpr int G = 1 << K;
+    __shared__ double2 s_mat[G * G];
+    for (int e = threadIdx.x; e < G * G; e += blockDim.x) s_mat[e] = mat[e];
+    __syncthreads();
+    const unsigned long long ngroups = 1ull << (n - K);
+    double2 *__restrict__ st = cols[blockIdx.y];
+    for (unsigned long long grp = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; grp < ngroups;
+         grp += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long base = grp;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            const int p = g.sorted_pos[a];
+            base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
+        }
+        if ((base & g.cmask) != g.cmask) continue;
+        double2 in[G];
+#pragma unroll
+        for (int h = 0; h < G; ++h) in[h] = st[base | g.offs[h]];
+#pragma unroll 1
+        for (int i = 0; i < G; ++i) {
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int h = 0; h < G; ++h) {
+                const double2 m = s_mat[i * G + h];
+                acc.x = fma(in[h].x, m.x, fma(-in[h].y, m.y, acc.x));
+                acc.y = fma(in[h].x, m.y, fma(in[h].y, m.x, acc.y));
+            }
+            st[base | g.offs[i]] = acc;
+        }
+    }
+}
+
 cudaError_t launch_generic_gate(double2 *const *d_cols, int ncols, int n, int k, const GenericGateArgs &g,
                                 const double2 *d_mat, cudaStream_t stream)
 {
@@ -1496,7 +1535,102 @@ cudaError_t launch_generic_gate(double2 *const *d_cols, int ncols, int n, int k,
     unsigned blocks = (unsigned)((ngroups + 127) / 128);
     if (blocks > 148u * 32u) blocks = 148u * 32u;
     if (blocks == 0) blocks = 1;
-    generic_gate_kernel<<<dim3(blocks, ncols), 128, 0, stream>>>(d_cols, n, k, g, d_mat);
+    const dim3 grid(blocks, ncols);
+    switch (k) {
+    case 1: generic_gate_reg_kernel<1><<<grid, 128, 0, stream>>>(d_cols, n, g, d_mat); break;
+    case 2: generic_gate_reg_kernel<2><<<grid, 128, 0, stream>>>(d_cols, n, g, d_mat); break;
+    case 3: generic_gate_reg_kernel<3><<<grid, 128, 0, stream>>>(d_cols, n, g, d_mat); break;
+    case 4: generic_gate_reg_kernel<4><<<grid, 128, 0, stream>>>(d_cols, n, g, d_mat); break;
+    case 5: generic_gate_reg_kernel<5><<<grid, 128, 0, stream>>>(d_cols, n, g, d_mat); break;
+    default: generic_gate_kernel<<<grid, 128, 0, stream>>>(d_cols, n, k, g, d_mat); break;
+    }
+    return cudaGetLastError();
+}
+
+// Dense blocks on 6..10 targets (gates.rs:310-325 takes any k).  kBigGroups groups of 2^k amplitudes are staged in shared
+// memory; thread i accumulates output i of every staged group, reading column i of the matrix once per pass (from shared
+// memory while the matrix fits, k <= 6, else coalesced from the transposed copy in L2) and the inputs as broadcasts.
+constexpr int kBigGroups = 4;
+__global__ void __launch_bounds__(256)
+generic_gate_big_kernel(double2 *const *__restrict__ cols, GenericBigArgs a, const double2 *__restrict__ matT, int mat_in_smem)
+{
+    extern __shared__ double2 s_big[];
+    const int k = a.k, G = 1 << k;
+    double2 *const s_in = s_big;                                                        // [kBigGroups][G]
+    unsigned long long *const s_offs = reinterpret_cast<unsigned long long *>(s_in + (kBigGroups << k));   // [G]
+    unsigned long long *const s_base = s_offs + G;                                      // [kBigGroups]
+    double2 *const s_mat = reinterpret_cast<double2 *>(s_base + kBigGroups);            // [G][G] when it fits
+    for (int h = threadIdx.x; h < G; h += blockDim.x) {
+        unsigned long long o = 0;
+        for (int j = 0; j < k; ++j)
+            if ((h >> (k - 1 - j)) & 1) o |= 1ull << a.pos[j];
+        s_offs[h] = o;
+    }
+    if (mat_in_smem)
+        for (int e = threadIdx.x; e < G * G; e += blockDim.x) s_mat[e] = matT[e];
+    const double2 *__restrict__ mt = mat_in_smem ? s_mat : matT;
+    double2 *__restrict__ st = cols[blockIdx.y];
+    const unsigned long long ngroups = 1ull << (a.n - k);
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * kBigGroups; g0 < ngroups; g0 += (unsigned long long)gridDim.x * kBigGroups) {
+        __syncthreads();                      // tables written / the previous pass has read its inputs
+        if (threadIdx.x < kBigGroups) {
+            unsigned long long base = ~0ull;                                            // ~0: nothing to do for this slot
+            const unsigned long long grp = g0 + threadIdx.x;
+            if (grp < ngroups) {
+                base = grp;
+                for (int j = 0; j < k; ++j) {
+                    const int p = a.sorted_pos[j];
+                    base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
+                }
+                if ((base & a.cmask) != a.cmask) base = ~0ull;
+            }
+            s_base[threadIdx.x] = base;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < (kBigGroups << k); e += blockDim.x) {
+            const unsigned long long base = s_base[e >> k];
+            s_in[e] = base != ~0ull ? st[base | s_offs[e & (G - 1)]] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < G; i += blockDim.x) {
+            double2 acc[kBigGroups];
+#pragma unroll
+            for (int gi = 0; gi < kBigGroups; ++gi) acc[gi] = make_double2(0.0, 0.0);
+            for (int h = 0; h < G; ++h) {
+                const double2 m = mt[(size_t)h * G + i];
+#pragma unroll
+                for (int gi = 0; gi < kBigGroups; ++gi) {
+                    const double2 x = s_in[(gi << k) + h];
+                    acc[gi].x = fma(x.x, m.x, fma(-x.y, m.y, acc[gi].x));
+                    acc[gi].y = fma(x.x, m.y, fma(x.y, m.x, acc[gi].y));
+                }
+            }
+            const unsigned long long off = s_offs[i];
+#pragma unroll
+            for (int gi = 0; gi < kBigGroups; ++gi)
+                if (s_base[gi] != ~0ull) st[s_base[gi] | off] = acc[gi];               // (every input of the pass sits in shared memory)
+        }
+    }
+}
+cudaError_t launch_generic_gate_big(double2 *const *d_cols, int ncols, const GenericBigArgs &g, const double2 *d_matT, cudaStream_t stream)
+{
+    if (g.k < 1 || g.k > kMaxBigGenericBits || g.k > g.n) return cudaErrorInvalidValue;
+    const size_t G = (size_t)1 << g.k;
+    const bool mat_in_smem = g.k <= 6;
+    const size_t smem = sizeof(double2) * kBigGroups * G + sizeof(unsigned long long) * (G + kBigGroups) + (mat_in_smem ? sizeof(double2) * G * G : 0);
+    static int attr_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((attr_mask >> (dev & 31)) & 1)) {
+        const cudaError_t e = cudaFuncSetAttribute(generic_gate_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_mask |= 1 << (dev & 31);
+    }
+    const unsigned long long ngroups = 1ull << (g.n - g.k);
+    unsigned long long blocks = (ngroups + kBigGroups - 1) / kBigGroups;
+    if (blocks > 148ull * 4ull) blocks = 148ull * 4ull;
+    const int threads = G < 256 ? (G < 32 ? 32 : (int)G) : 256;
+    generic_gate_big_kernel<<<dim3((unsigned)blocks, ncols), threads, smem, stream>>>(d_cols, g, d_matT, mat_in_smem ? 1 : 0);
     return cudaGetLastError();
 }
 

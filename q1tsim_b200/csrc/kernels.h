@@ -55,6 +55,16 @@ bool tma_can_encode(const SweepProgram &prog, const double2 *const *h_src_cols, 
 bool sweep_uses_ladder_kernel(const SweepProgram &prog);
 cudaError_t launch_generic_gate(double2 *const *d_cols, int ncols, int n, int k, const GenericGateArgs &g,
                                 const double2 *d_mat, cudaStream_t stream);
+// dense blocks on kMaxGenericBits .. kMaxBigGenericBits targets: a CTA stages several groups of 2^k amplitudes in shared
+// memory, thread i accumulates output i of every staged group from the TRANSPOSED matrix (d_matT[h * 2^k + i])
+constexpr int kMaxBigGenericBits = 10;
+struct GenericBigArgs {
+    int n, k;
+    int pos[kMaxBigGenericBits];          // position of the j-th listed target (bit k-1-j of the matrix index)
+    int sorted_pos[kMaxBigGenericBits];   // the same positions ascending
+    unsigned long long cmask;             // control positions that must be 1
+};
+cudaError_t launch_generic_gate_big(double2 *const *d_cols, int ncols, const GenericBigArgs &g, const double2 *d_matT, cudaStream_t stream);
 cudaError_t launch_leaf_totals(const double2 *const *d_cols, int ncols, double *d_leaf, int n,
                                unsigned long long mask, unsigned long long want, cudaStream_t stream);
 cudaError_t launch_scan(double *d_leaf, double *d_block, double *d_totals, int ncols, int n, cudaStream_t stream);

@@ -276,7 +276,7 @@ bool lower_gate(const cplx *mat, int k, const int *phys, LoweredGate &out, std::
             return true;
         }
     }
-    if ((int)act.size() > 6) { err = "dense gate blocks on more than 6 target qubits are not supported"; return false; }
+    if ((int)act.size() > 10) { err = "dense gate blocks on more than 10 target qubits are not supported"; return false; }
     out.kind = LoweredGate::GENERIC;
     out.cmask = cmask;
     for (int a : act) out.pos.push_back(phys[a]);

@@ -68,7 +68,7 @@ def test_every_builtin_gate_random_bits(n):
     assert rel_l2(e.column(0), o.column(0)) < TOL
 
 
-@pytest.mark.parametrize("n,k", [(5, 2), (8, 2), (8, 3), (12, 2), (12, 4), (14, 3), (14, 5)])
+@pytest.mark.parametrize("n,k", [(5, 2), (8, 2), (8, 3), (12, 2), (12, 4), (14, 3), (14, 5), (12, 6), (13, 7), (14, 8), (12, 10)])
 def test_dense_user_gates(n, k):
     """arbitrary user gates supply only matrix() (lib.rs:148-196)"""
     rs = np.random.default_rng(7 * n + k)
@@ -83,6 +83,28 @@ def test_dense_user_gates(n, k):
         e.apply_gate(h, b, "H")
         o.apply_gate(h, b)
     assert rel_l2(e.column(0), o.column(0)) < TOL
+
+
+@pytest.mark.parametrize("n,k,nc", [(12, 3, 1), (12, 5, 2), (13, 6, 1), (13, 7, 2)])
+def test_controlled_dense_user_gates(n, k, nc):
+    """a user matrix that is the identity unless its first nc qubits are 1 (gates.rs:310-325 applies it as any dense
+    matrix): the engine extracts the controls and runs the k-target block (registers for k <= 5, staged groups above)"""
+    rs = np.random.default_rng(11 * n + k)
+    e, o = pair(n, seed=5 * n + k)
+    for rep in range(3):
+        u = rand_unitary(k, 3 * rep + n)
+        dim = 1 << (k + nc)
+        m = np.eye(dim, dtype=np.complex128)
+        m[dim - (1 << k):, dim - (1 << k):] = u
+        bits = [int(b) for b in rs.permutation(n)[:k + nc]]
+        e.apply_gate(m, bits, "ctl-user")
+        o.apply_gate(m, bits)
+        h = O.gate_matrix("h")
+        for b in bits[:nc]:
+            e.apply_gate(h, [b], "H")
+            o.apply_gate(h, [b])
+    assert rel_l2(e.column(0), o.column(0)) < TOL
+    assert e.stats()["fallback_sweeps"] >= 3
 
 
 def test_reference_state_kats():
