@@ -602,8 +602,12 @@ def sharded_leg(args, rank, world, dev, n, shots, steps, warmup, dist, torch, de
            "exchange": {"remaps_per_step": remaps, "bytes_out_per_rank_per_step": exch_bytes,
                         "swap_kernel_ms_per_step": swap_ms,
                         "gb_per_s_per_direction": (exch_bytes / (swap_ms * 1e-3) / 1e9) if swap_ms > 0 else None,
-                        "path": "in-place multi-bit remap kernel over CUDA IPC peer memory (NVLink), mailbox barriers on the device; "
-                                "torch.distributed carries only host-side control messages"},
+                        "fused_remaps_per_step": stt.get("fused_remaps", 0) / steps,
+                        "path": ("remap read through by the ladder sweep that follows it (its tile loads come from the peers' shards over "
+                                 "NVLink while the local part of every tile is swept; engine option fused_remap, default for 2 ranks)"
+                                 if stt.get("fused_remaps", 0) else
+                                 "in-place multi-bit remap kernel over CUDA IPC peer memory (NVLink)") +
+                                "; mailbox barriers on the device; torch.distributed carries only host-side control messages"},
            "sweep_launches_per_step": tb["sweeps"], "gpu_launches": int(launches), "verified": ver, "clocks": clocks}
     return out
 
