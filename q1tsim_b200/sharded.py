@@ -745,10 +745,38 @@ class ShardedState:
         self.local.apply_conditional_gate(control, local_m, local_bits)
 
     # ---- canonical reductions ----------------------------------------------------
+    def _gather_flat(self, flat, dtype):
+        """all_gather of a small host array over NCCL with ONE synchronisation: pinned staging buffers kept per size, one
+        all_gather_into_tensor, one copy back (the list form costs a device-to-host copy with a sync per rank; this runs
+        twice per measure_all and was ~0.5 ms of a 4.7 ms step)"""
+        import torch
+        n = int(flat.size)
+        key = (str(dtype), n)
+        cache = self.__dict__.setdefault("_gather_bufs", {})
+        bufs = cache.get(key)
+        if bufs is None:
+            dev = torch.device("cuda", self.device)
+            bufs = (torch.empty(n, dtype=dtype).pin_memory(), torch.empty(n, dtype=dtype, device=dev),
+                    torch.empty(n * self.P, dtype=dtype, device=dev), torch.empty(n * self.P, dtype=dtype).pin_memory())
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = bufs
+        pin_in, dev_in, dev_out, pin_out = bufs
+        pin_in.numpy()[:] = flat
+        dev_in.copy_(pin_in, non_blocking=True)
+        self.dist.all_gather_into_tensor(dev_out, dev_in, group=self.group)
+        pin_out.copy_(dev_out, non_blocking=True)
+        torch.cuda.current_stream(dev_in.device).synchronize()
+        return pin_out.numpy().reshape(self.P, n).copy()
+
     def _gather(self, arr):
         import torch
         if self.P == 1:
             return [np.asarray(arr)]
+        if self.dist.get_backend(self.group) == "nccl":
+            a = np.ascontiguousarray(arr, dtype=np.float64)
+            out = self._gather_flat(a.ravel(), torch.float64)
+            return [out[r].reshape(a.shape) for r in range(self.P)]
         t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
         dev = torch.device("cuda", self.device) if self.dist.get_backend(self.group) == "nccl" else torch.device("cpu")
         t = t.to(dev)
@@ -921,6 +949,16 @@ class ShardedState:
         mx = int(per_rank.max()) if per_rank.size else 0
         buf = np.zeros(max(mx, 1), dtype=np.int64)
         buf[:idx.size] = idx.astype(np.int64)
+        if self.dist.get_backend(self.group) == "nccl":
+            # (the staging buffers are kept per size: a size that changes with every batch of draws would allocate pinned
+            # memory in every step -- measured: 4.7 -> 12.1 ms -- so it is rounded up to a power of two)
+            cap = 1024
+            while cap < buf.size:
+                cap *= 2
+            padded = np.zeros(cap, dtype=np.int64)
+            padded[:buf.size] = buf
+            out = self._gather_flat(padded, torch.int64)
+            return np.concatenate([out[r][:int(per_rank[r])] for r in range(self.P)]).astype(np.uint64)
         dev = torch.device("cuda", self.device) if self.dist.get_backend(self.group) == "nccl" else torch.device("cpu")
         t = torch.from_numpy(buf).to(dev)
         out = [torch.empty_like(t) for _ in range(self.P)]
