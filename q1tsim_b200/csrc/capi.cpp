@@ -382,7 +382,8 @@ int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const
     const int n = (int)nr_bits;
     std::vector<int> perm(n);
     for (int i = 0; i < n; ++i) perm[i] = i;
-    q1t::Planner pl(n, (int)tile_bits, (int)coalesce_bits, (balance & 1) != 0);
+    // bit 9: relabelling stores in the middle of the plan (Planner mid_relabel)
+    q1t::Planner pl(n, (int)tile_bits, (int)coalesce_bits, (balance & 1) != 0, (balance & 0x200) != 0);
     size_t moff = 0, boff = 0;
     for (size_t g = 0; g < nr_gates; ++g) {
         const size_t k = nbits[g], dim = dims[g];
@@ -407,6 +408,13 @@ int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const
     }
     pl.finish();
     std::vector<q1t::PlannedSweep> sweeps = pl.take();
+    // the relabelling stores planned for the middle of the batch, as DeviceVectorState::issue_sweeps applies them: every
+    // sweep but the last honours its mid_dstpos, and the qubit map is composed with it
+    for (size_t i = 0; i + 1 < sweeps.size(); ++i)
+        if (!sweeps[i].mid_dstpos.empty()) {
+            q1t::set_relabel(sweeps[i].prog, sweeps[i].mid_dstpos, false);
+            for (int l = 0; l < n; ++l) perm[l] = sweeps[i].mid_dstpos[perm[l]];
+        }
     // balance >> 4 selects how the Swap relabelling is undone, as DeviceVectorState::run_sweeps / canonicalize do:
     // 0 not at all (perm_out tells the reader), 1 fused into the last sweep when its tile allows it, else one
     // relabel sweep, 2 the in-place passes

@@ -187,6 +187,7 @@ DeviceVectorState::DeviceVectorState(size_t nr_bits, size_t nr_shots, int device
     if (const char *e = std::getenv("Q1T_PREFETCH_AHEAD")) prefetch_ahead_ = std::atol(e);
     if (const char *e = std::getenv("Q1T_TILE_BITS")) { const long v = std::atol(e); if (v >= 8 && v <= kMaxTileBits) tile_bits_ = v; }
     if (const char *e = std::getenv("Q1T_FUSED_REMAP")) fused_remap_ = std::atol(e) != 0;
+    if (const char *e = std::getenv("Q1T_MID_RELABEL")) mid_relabel_ = std::atol(e);
 }
 
 DeviceVectorState::~DeviceVectorState()
@@ -602,7 +603,9 @@ int DeviceVectorState::run_sweeps(std::vector<PlannedSweep> &sweeps, const std::
     // if it comes from the plan cache (the key names the gate list), touches no lazy column half-way, and restores no
     // layout (the relabelling path allocates).  The graph is keyed by everything the issued work depends on.
     const bool may_relabel = final_relabel && (!ident || (want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(sweeps.back().prog)));
-    const bool graph_try = graphs_ && !grp_.pending && !timing && cur_plan_key_ != 0 && sweeps.size() >= 4 && n_ <= 26 && !tma_ && !cprog_device_shared(device_) &&
+    bool has_mid = false;
+    for (size_t si = 0; si + 1 < sweeps.size(); ++si) has_mid = has_mid || !sweeps[si].mid_dstpos.empty();
+    const bool graph_try = graphs_ && !grp_.pending && !has_mid && !timing && cur_plan_key_ != 0 && sweeps.size() >= 4 && n_ <= 26 && !tma_ && !cprog_device_shared(device_) &&
                            (generate || !any_basis) && !may_relabel;
     uint64_t gkey = 0;
     if (graph_try) {
@@ -796,6 +799,10 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
         }
         ps.prog.generate = (generate && si == 0) ? 1 : 0;
         const bool last = si + 1 == sweeps.size();
+        // a relabelling store planned for the middle of the batch (Planner mid_relabel): out of place, and the qubit map is
+        // composed with it afterwards -- every later sweep of the plan is expressed in the layout it leaves
+        const bool mid = !last && !ps.mid_dstpos.empty();
+        if (mid) set_relabel(ps.prog, ps.mid_dstpos, false);
         bool relabel = false;
         const bool try_leaf = last && final_relabel && want_leaf_fusion_ && n_ >= 12 && sweep_uses_ladder_kernel(ps.prog);
         // with the layout already canonical the last sweep is still sent through the (out-of-place) staged store when a
@@ -883,6 +890,12 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
                 if (ps.prog.leaf_fuse) leaf_fused_ = true;
                 for (int l = 0; l < n_; ++l) perm_[l] = l;
             } else {
+                if (mid) {
+                    stats.fused_relabels++;
+                    for (int l = 0; l < n_; ++l) perm_[l] = ps.mid_dstpos[perm_[l]];
+                    ident = true;
+                    for (int l = 0; l < n_; ++l) ident = ident && perm_[l] == l;
+                }
                 rc = upload_colptrs(which);                           // the sweeps that follow run in place in the new buffer
                 if (rc) return rc;
             }
@@ -890,7 +903,7 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
         }
         // dense ladder sweeps take their tiles by TMA (planner.cpp apply_tma_layout, kernels.cu ladder_kernel)
         const bool tma_ok = tma_ && !ps.prog.generate && ps.prog.sup_mode == 0 && sweep_uses_ladder_kernel(ps.prog) && tma_available();
-        if (!relabel) {
+        if (!relabel && !mid) {
             std::vector<const double2 *> hcols;
             if (tma_ok && which.size() <= (size_t)kMaxTmaCols) {
                 SweepProgram q = ps.prog;
@@ -957,7 +970,15 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
         if (ps.prog.leaf_fuse) leaf_fused_ = true;
         stats.sweep_column_passes += which.size();
         stats.sweep_bytes += (uint64_t)which.size() * bytes_moved[si];
-        for (int l = 0; l < n_; ++l) perm_[l] = l;
+        if (mid) {
+            for (int l = 0; l < n_; ++l) perm_[l] = ps.mid_dstpos[perm_[l]];
+            ident = true;
+            for (int l = 0; l < n_; ++l) ident = ident && perm_[l] == l;
+            rc = upload_colptrs(which);                               // the sweeps that follow run in place in the new buffers
+            if (rc) return rc;
+        } else {
+            for (int l = 0; l < n_; ++l) perm_[l] = l;
+        }
     }
     sweeps.clear();
     return Q1T_OK;
@@ -1024,7 +1045,11 @@ int DeviceVectorState::run_queue(bool final_relabel)
             // of the plan qualifies for the ladder kernel (otherwise the dense default is planned)
             bool sparse_start = sparse_c2_ && track_support_ && coalesce_bits_ == 3 && tile_bits_ == 12;
             for (int c : which) sparse_start = sparse_start && cols_[c].basis && cols_[c].basis_idx != UINT64_MAX;
-            const long cfg[5] = { (long)n_, tile_bits_, coalesce_bits_, (long)kRegBits, (long)sparse_start };
+            // dense batches over the whole state with room for a second buffer may store relabelled in the middle of the
+            // plan (Planner mid_relabel: a sweep with strided tiles writes whole contiguous tiles instead)
+            bool mid_ok = mid_relabel_ > 0 && (mid_relabel_ > 1 || n_ >= 24) && !sparse_start && which.size() == cols_.size() && !want_inplace_relabel();
+            for (int c : which) mid_ok = mid_ok && !cols_[c].basis;
+            const long cfg[6] = { (long)n_, tile_bits_, coalesce_bits_, (long)kRegBits, (long)sparse_start, (long)mid_ok };
             mix(cfg, sizeof cfg);
             for (const LoweredGate &g : q) {
                 const int hdr[5] = { (int)g.kind, g.nb, g.b[0], g.b[1], g.target };
@@ -1073,7 +1098,7 @@ int DeviceVectorState::run_queue(bool final_relabel)
             for (int attempt = sparse_start ? 0 : 1; attempt < 2; ++attempt) {
                 const int cbits = attempt == 0 ? 2 : (int)coalesce_bits_;
                 for (int b = 0; b < 2; ++b) {
-                    Planner trial(n_, (int)tile_bits_, cbits, b != 0);
+                    Planner trial(n_, (int)tile_bits_, cbits, b != 0, mid_ok && attempt == 1);
                     for (const LoweredGate &g : q) trial.add(g);
                     trial.finish();
                     plan[b] = trial.take();
@@ -2386,6 +2411,12 @@ int DeviceVectorState::set_option(const char *key, long value)
     }
     if (!std::strcmp(key, "graphs")) {
         graphs_ = value != 0;
+        return Q1T_OK;
+    }
+    if (!std::strcmp(key, "mid_relabel")) {
+        int rc = run_queue();
+        if (rc) return rc;
+        mid_relabel_ = value;
         return Q1T_OK;
     }
     if (!std::strcmp(key, "fused_remap")) {

@@ -151,6 +151,7 @@ private:
     int group_remap_run(const GroupRemapArgs &a);       // barrier, swap pass, barrier
     int resolve_pending_remap();                        // a recorded trade nobody could fuse: run it as a swap pass now
     bool fused_remap_ = false;
+    long mid_relabel_ = 1;                   // dense batches: relabelling stores in the middle of a plan (planner.h); 0 off, 1: states of >= 2^24 (measured: dense QFT-30 sweeps 7.23 -> 6.84 ms), 2: any size
     void group_collect_timing();
 
     int fail(int code, const std::string &msg) { err_ = msg; return code; }

@@ -305,9 +305,12 @@ bool PendingDiag::empty() const
 // ---------------------------------------------------------------------------
 // planner
 // ---------------------------------------------------------------------------
-Planner::Planner(int n, int tile_bits, int coalesce_bits, bool balance)
-    : n_(n), T_(std::min(tile_bits, n)), C_(std::max(1, std::min(coalesce_bits, 3))), balance_(balance)
+Planner::Planner(int n, int tile_bits, int coalesce_bits, bool balance, bool mid_relabel)
+    : n_(n), T_(std::min(tile_bits, n)), C_(std::max(1, std::min(coalesce_bits, 3))), balance_(balance), mid_relabel_(mid_relabel)
 {
+    cur_.resize(n);
+    inv_.resize(n);
+    for (int p = 0; p < n; ++p) cur_[p] = inv_[p] = p;
     pd_.init(n);
     open_sweep();
 }
@@ -317,7 +320,7 @@ void Planner::open_sweep()
     tile_.clear();
     rounds_.clear();
     nops_ = nphase_ = 0;
-    for (int p = 0; p < C_ && p < n_; ++p) tile_.push_back(p);  // coalescing bits: 8 amplitudes = 128 B (4 = 64 B)
+    for (int p = 0; p < C_ && p < n_; ++p) tile_.push_back(inv_[p]);  // coalescing bits: 8 amplitudes = 128 B (4 = 64 B)
 }
 
 bool Planner::in_tile(int p) const { return std::find(tile_.begin(), tile_.end(), p) != tile_.end(); }
@@ -483,8 +486,23 @@ void Planner::close_sweep()
     SweepProgram &P = ps.prog;
     std::memset(&P, 0, sizeof P);
     const int T = T_;
+    // everything below works on CURRENT positions: the planner's bookkeeping (tile_, rounds_, pending terms) stays on
+    // the positions the gates arrive with, cur_ says where those are after the relabelling stores planned so far
+    std::vector<RoundB> rounds_x = rounds_;
+    for (RoundB &rb : rounds_x) {
+        for (int &p : rb.regs) p = cur_[p];
+        for (OpB &ob : rb.ops) {
+            ob.target = cur_[ob.target];
+            uint64_t cm = 0;
+            for (int p = 0; p < n_; ++p)
+                if ((ob.cmask >> p) & 1ull) cm |= 1ull << cur_[p];
+            ob.cmask = cm;
+            for (auto &pr : ob.partners) pr.first = cur_[pr.first];
+        }
+    }
     // pad the tile with the lowest unused positions
-    std::vector<int> tile = tile_;
+    std::vector<int> tile;
+    for (int p : tile_) tile.push_back(cur_[p]);
     for (int p = 0; p < n_ && (int)tile.size() < T; ++p)
         if (std::find(tile.begin(), tile.end(), p) == tile.end()) tile.push_back(p);
     std::sort(tile.begin(), tile.end());
@@ -521,7 +539,7 @@ void Planner::close_sweep()
     P.nrounds = (int)rounds_.size();
     int nops = 0, nphase = 0;
     for (int r = 0; r < P.nrounds; ++r) {
-        RoundB &rb = rounds_[r];
+        RoundB &rb = rounds_x[r];
         RoundDesc &R = P.rounds[r];
         // register bits as tile-bit indices.  Slot bits kRegBits-cnt.. are the round's targets in
         // placement order, so that a chain of (phase, Hadamard) steps is a ladder whatever the
@@ -709,6 +727,25 @@ void Planner::close_sweep()
     P.nops = nops;
     P.nphase = nphase;
     setup_direct(P);
+    if (mid_relabel_ && n_ > T) {
+        bool ladder = P.nrounds > 0, contiguous = true;
+        for (int r = 0; r < P.nrounds; ++r) ladder = ladder && P.rounds[r].kind == ROUND_PH;
+        for (int i = 0; i < T; ++i) contiguous = contiguous && tile[i] == i;
+        if (ladder && !contiguous) {
+            std::vector<int> dstpos(n_), high, holes;
+            for (int p = 0; p < n_; ++p) dstpos[p] = p;
+            for (int i = 0; i < T; ++i)
+                if (tile[i] >= T) high.push_back(tile[i]);
+            for (int p = 0; p < T; ++p)
+                if (!std::binary_search(tile.begin(), tile.end(), p)) holes.push_back(p);
+            for (size_t i = 0; i < high.size() && i < holes.size(); ++i) { dstpos[high[i]] = holes[i]; dstpos[holes[i]] = high[i]; }
+            if (can_fuse_relabel(P, dstpos)) {
+                ps.mid_dstpos = dstpos;
+                for (int p = 0; p < n_; ++p) cur_[p] = dstpos[cur_[p]];
+                for (int p = 0; p < n_; ++p) inv_[cur_[p]] = p;
+            }
+        }
+    }
     stats.sweeps += 1;
     stats.rounds += P.nrounds;
     stats.ops += nops;

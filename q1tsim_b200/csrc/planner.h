@@ -41,6 +41,11 @@ struct PlannedSweep {
     std::vector<PhaseTab> ptabs;
     bool is_permute = false;
     uint64_t touched = 0;        // physical bits acted on by non-diagonal gates (these lose a pinned basis value)
+    // Planner(.., mid_relabel): this sweep stores its tile relabelled -- the data at position p goes to mid_dstpos[p] --
+    // and every LATER sweep of the plan is expressed in the layout that leaves.  The executor applies
+    // set_relabel(prog, mid_dstpos), runs the sweep out of place and composes its qubit map with mid_dstpos; on the LAST
+    // sweep of a batch it is ignored (nothing depends on it).  Empty: in place, as planned.
+    std::vector<int> mid_dstpos;
 };
 
 struct PlanStats {
@@ -64,7 +69,11 @@ class Planner {
 public:
     // coalesce_bits: low index bits every tile keeps contiguous (3 = 128-byte runs, 2 = 64-byte runs)
     // balance: close a sweep rather than open a round that the tile cannot fill with register bits
-    Planner(int n, int tile_bits, int coalesce_bits = 3, bool balance = false);
+    // mid_relabel: a ladder sweep whose tile is not the contiguous low block (its targets are high index bits: 128-byte
+    // lines at a large stride, read AND written) stores its tile into the low block instead -- the tile's high bits trade
+    // places with the non-tile bits below position T -- so that its writes are whole contiguous tiles
+    // (PlannedSweep::mid_dstpos).  Gates keep arriving on the ORIGINAL positions; the planner tracks where they are now.
+    Planner(int n, int tile_bits, int coalesce_bits = 3, bool balance = false, bool mid_relabel = false);
     // feed gates in program order
     void add(const LoweredGate &g);           // POLY or G1 only
     // flush everything that is pending (diagonal terms included) into sweeps
@@ -100,6 +109,8 @@ private:
     };
     int n_, T_, C_;
     bool balance_;
+    bool mid_relabel_;
+    std::vector<int> cur_, inv_;        // original position -> current position after the mid-plan relabels, and back
     std::vector<int> tile_;             // physical bits in the open sweep's tile
     std::vector<RoundB> rounds_;
     size_t nops_ = 0, nphase_ = 0;

@@ -107,3 +107,30 @@ def test_tma_layout_of_dense_ladder_sweeps(n, relabel_mode):
         else:
             PI.check_tables(P)
     assert got == len([1 for P, _ in sweeps if P.nrounds > 0]), "every QFT ladder sweep must qualify for TMA loads"
+
+
+@pytest.mark.parametrize("n,tile_bits,relabel_mode", [(14, 8, 0), (14, 8, 1), (15, 8, 1), (16, 8, 2), (17, 9, 1)])
+def test_relabelling_stores_in_the_middle_of_a_plan(n, tile_bits, relabel_mode):
+    """Planner mid_relabel (q1t_plan_dump balance bit 9): a ladder sweep whose targets are high index bits stores its tile
+    into the contiguous low block; the later sweeps are planned in the layout that leaves, the qubit map is composed with
+    it, and the final layout is restored as usual.  Checked for QFT-like circuits (all ladders) against the oracle."""
+    ops = W.qft_ops(n, measure=False)
+    if n == 14:
+        ops = ops + W.qft_ops(n, measure=False, swaps=False)
+    plain = _check(n, ops, tile_bits, relabel_mode=relabel_mode)
+    sweeps = _check(n, ops, tile_bits, balanced=0x200, relabel_mode=relabel_mode)
+    assert len(sweeps) <= len(plain) + (1 if relabel_mode == 1 else 3)
+    mids = [P for P, _ in sweeps[:-1] if P.relabel and P.nrounds > 0]      # (gate sweeps: the final in-place passes of mode 2 also relabel)
+    assert mids, "no sweep in the middle of the plan stores relabelled"
+    for P in mids:
+        # the store of such a sweep covers whole contiguous tiles: its destination tile bits are 0..T-1
+        assert sorted(P.tdst[i] for i in range(P.T)) == list(range(P.T))
+
+
+def test_mid_plan_relabel_with_mixed_gates():
+    """gates that do not run as ladders (controls, dense 2x2) between QFT blocks: only ladder sweeps relabel, the
+    positions of everything planned afterwards follow"""
+    n = 13
+    ops = W.qft_ops(n, measure=False) + _random_ops(n, 1, seed=5) + W.qft_ops(n, measure=False)
+    _check(n, ops, 8, balanced=0x200, relabel_mode=1)
+    _check(n, ops, 9, coalesce=2, balanced=0x201, relabel_mode=0)
