@@ -101,6 +101,9 @@ int ShardedVectorState::init_zero_state()
     // replicated start: every shard is |0..0> on its local qubits while every rank bit is pinned to 0
     for (int r = 0; r < P_; ++r) {
         shards_.emplace_back(new DeviceVectorState((size_t)nl_, shots_, devices_[r]));
+        // one host thread drives all shards here: a remap recorded for the next sweep (engine option fused_remap) would launch
+        // its barriers from inside one shard's flush while the thread has not reached the next shard yet -- always off
+        shards_.back()->set_option("fused_remap", 0);
         int rc = shards_[r]->init_zero_state();
         if (rc) return shard_fail(r, rc);
     }
