@@ -121,7 +121,7 @@ def measured_peak():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per dense ladder launch, from the round's committed ncu capture"""
-    for name in ("r2_ncu_dense_ladder_v2.json", "r2_ncu_dense_ladder.json"):       # (v2: the kernel as it is now, tools/ncu_summary.py)
+    for name in ("r2_ncu_dense_ladder_v3.json", "r2_ncu_dense_ladder_v2.json", "r2_ncu_dense_ladder.json"):       # (v3: the kernel and the plan as they are now, tools/ncu_summary.py)
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             d = json.load(open(p))
