@@ -382,8 +382,10 @@ int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const
     const int n = (int)nr_bits;
     std::vector<int> perm(n);
     for (int i = 0; i < n; ++i) perm[i] = i;
-    // bit 9: relabelling stores in the middle of the plan (Planner mid_relabel)
-    q1t::Planner pl(n, (int)tile_bits, (int)coalesce_bits, (balance & 1) != 0, (balance & 0x200) != 0);
+    // bit 9: relabelling stores in the middle of the plan (Planner mid_relabel 1); bit 10: ... that also rotate the next
+    // targets into the low positions (mid_relabel 2, with the look-ahead the engine gives the planner)
+    q1t::Planner pl(n, (int)tile_bits, (int)coalesce_bits, (balance & 1) != 0, (balance & 0x400) ? 2 : (balance & 0x200) ? 1 : 0);
+    std::vector<q1t::LoweredGate> fusable;
     size_t moff = 0, boff = 0;
     for (size_t g = 0; g < nr_gates; ++g) {
         const size_t k = nbits[g], dim = dims[g];
@@ -402,10 +404,17 @@ int q1t_plan_dump(size_t nr_bits, size_t nr_gates, const double *matrices, const
                 else if (perm[l] == lg.b[1]) perm[l] = lg.b[0];
             }
         } else if (lg.kind == q1t::LoweredGate::GENERIC) return Q1T_ERR_UNSUPPORTED;      // only fusable gate lists
-        else if (!(lg.kind == q1t::LoweredGate::POLY && lg.nb == 0)) pl.add(lg);
+        else if (!(lg.kind == q1t::LoweredGate::POLY && lg.nb == 0)) fusable.push_back(lg);
         moff += 2 * dim * dim;
         boff += k;
     }
+    {
+        std::vector<int> la;
+        for (const q1t::LoweredGate &lg : fusable)
+            if (lg.kind == q1t::LoweredGate::G1) la.push_back(lg.target);
+        pl.set_lookahead(la);
+    }
+    for (const q1t::LoweredGate &lg : fusable) pl.add(lg);
     pl.finish();
     std::vector<q1t::PlannedSweep> sweeps = pl.take();
     // the relabelling stores planned for the middle of the batch, as DeviceVectorState::issue_sweeps applies them: every

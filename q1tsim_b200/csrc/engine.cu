@@ -1098,19 +1098,41 @@ int DeviceVectorState::run_queue(bool final_relabel)
             for (int attempt = sparse_start ? 0 : 1; attempt < 2; ++attempt) {
                 const int cbits = attempt == 0 ? 2 : (int)coalesce_bits_;
                 for (int b = 0; b < 2; ++b) {
-                    Planner trial(n_, (int)tile_bits_, cbits, b != 0, mid_ok && attempt == 1);
+                  // (dense batches: also with the relabelling stores of planner.h, plain and with the next targets rotated into
+                  //  the low positions; a plan whose last sweep cannot restore the canonical layout pays a relabel sweep)
+                  static const bool rotate_ok = !(std::getenv("Q1T_MID_ROTATE") && std::atoi(std::getenv("Q1T_MID_ROTATE")) == 0);      // A/B switch
+                  for (int mid = 0; mid <= (mid_ok && attempt == 1 ? (rotate_ok ? 2 : 1) : 0); ++mid) {
+                    if (mid_ok && attempt == 1 && mid == 0) continue;
+                    Planner trial(n_, (int)tile_bits_, cbits, b != 0, mid);
+                    if (mid >= 2) {
+                        std::vector<int> la;
+                        for (const LoweredGate &g : q)
+                            if (g.kind == LoweredGate::G1) la.push_back(g.target);
+                        trial.set_lookahead(la);
+                    }
                     for (const LoweredGate &g : q) trial.add(g);
                     trial.finish();
                     plan[b] = trial.take();
+                    uint64_t extra_sweeps = 0;
+                    if (mid > 0 && final_relabel && !plan[b].empty()) {
+                        std::vector<int> pm(perm_.begin(), perm_.end()), dstpos(n_);
+                        for (size_t si = 0; si + 1 < plan[b].size(); ++si)
+                            if (!plan[b][si].mid_dstpos.empty())
+                                for (int l = 0; l < n_; ++l) pm[l] = plan[b][si].mid_dstpos[pm[l]];
+                        bool idn = true;
+                        for (int l = 0; l < n_; ++l) { dstpos[pm[l]] = l; idn = idn && pm[l] == l; }
+                        if (!idn && !can_fuse_relabel(plan[b].back().prog, dstpos)) extra_sweeps = 1;
+                    }
                     bool all_ladder = true;
                     for (const PlannedSweep &ps : plan[b]) all_ladder = all_ladder && sweep_uses_ladder_kernel(ps.prog);
                     if (attempt == 0 && !all_ladder) continue;        // a 64-byte plan only pays when it runs tracked
                     const bool tracked = sparse_start && all_ladder;
-                    const uint64_t c[3] = { tracked ? tracked_bytes(plan[b]) : ~0ull - 1, trial.stats.sweeps, trial.stats.rounds };
+                    const uint64_t c[3] = { tracked ? tracked_bytes(plan[b]) : ~0ull - 1, trial.stats.sweeps + extra_sweeps, trial.stats.rounds };
                     if (c[0] < best_cost[0] || (c[0] == best_cost[0] && (c[1] < best_cost[1] || (c[1] == best_cost[1] && c[2] < best_cost[2])))) {
                         best_cost[0] = c[0]; best_cost[1] = c[1]; best_cost[2] = c[2];
                         best = plan[b];
                     }
+                  }
                 }
             }
             plan[0].swap(best);

@@ -305,7 +305,7 @@ bool PendingDiag::empty() const
 // ---------------------------------------------------------------------------
 // planner
 // ---------------------------------------------------------------------------
-Planner::Planner(int n, int tile_bits, int coalesce_bits, bool balance, bool mid_relabel)
+Planner::Planner(int n, int tile_bits, int coalesce_bits, bool balance, int mid_relabel)
     : n_(n), T_(std::min(tile_bits, n)), C_(std::max(1, std::min(coalesce_bits, 3))), balance_(balance), mid_relabel_(mid_relabel)
 {
     cur_.resize(n);
@@ -324,6 +324,14 @@ void Planner::open_sweep()
 }
 
 bool Planner::in_tile(int p) const { return std::find(tile_.begin(), tile_.end(), p) != tile_.end(); }
+
+std::vector<int> Planner::upcoming(size_t max_count) const
+{
+    std::vector<int> out;
+    for (size_t i = la_at_; i < la_.size() && out.size() < max_count; ++i)
+        if (std::find(out.begin(), out.end(), la_[i]) == out.end()) out.push_back(la_[i]);
+    return out;
+}
 
 bool Planner::has_pending() const { return !rounds_.empty() || !pd_.empty(); }
 
@@ -398,6 +406,7 @@ void Planner::add(const LoweredGate &g)
     // G1
     const int t = g.target;
     const size_t need_ops = 2;
+    struct Count { size_t &c; ~Count() { ++c; } } count_this_gate{ la_at_ };      // (the gate still counts as upcoming while it is placed)
     if (nops_ + need_ops > (size_t)kMaxOps || nphase_ + 1 > (size_t)kMaxPhase) {
         close_sweep();
         open_sweep();
@@ -500,9 +509,16 @@ void Planner::close_sweep()
             for (auto &pr : ob.partners) pr.first = cur_[pr.first];
         }
     }
-    // pad the tile with the lowest unused positions
+    // pad the tile with the lowest unused positions (mid_relabel 2: with the upcoming targets first -- passengers that the
+    // relabelling store below can move into the low positions)
     std::vector<int> tile;
     for (int p : tile_) tile.push_back(cur_[p]);
+    std::vector<int> next_targets;
+    if (mid_relabel_ >= 2 && !la_.empty()) {
+        for (int p : upcoming((size_t)T)) next_targets.push_back(cur_[p]);
+        for (size_t i = 0; i < next_targets.size() && (int)tile.size() < T; ++i)
+            if (std::find(tile.begin(), tile.end(), next_targets[i]) == tile.end()) tile.push_back(next_targets[i]);
+    }
     for (int p = 0; p < n_ && (int)tile.size() < T; ++p)
         if (std::find(tile.begin(), tile.end(), p) == tile.end()) tile.push_back(p);
     std::sort(tile.begin(), tile.end());
@@ -535,9 +551,15 @@ void Planner::close_sweep()
         P.st_off_hi[i] = off;
         P.st_l_hi[i] = tile_swizzle((uint32_t)i << P.TB) * 16u;
     }
-    P.scale = 1.0;
     P.nrounds = (int)rounds_.size();
     int nops = 0, nphase = 0;
+    // force_lane: tile bits that must be thread bits 0..C-1 of the LAST round, in this order (the sources of the low
+    // destination positions of a relabelling store, so that it can stay a direct store); null: the default order
+    auto build_rounds = [&](const int *force_lane) {
+    nops = 0; nphase = 0;
+    P.scale = 1.0;
+    ps.ptabs.clear();
+    ps.touched = 0;
     for (int r = 0; r < P.nrounds; ++r) {
         RoundB &rb = rounds_x[r];
         RoundDesc &R = P.rounds[r];
@@ -566,6 +588,20 @@ void Planner::close_sweep()
             for (int tb = 0; tb < T; ++tb)
                 if (slot_of_tb[tb] < 0) rest.push_back(tb);
             bool used[3] = { false, false, false };
+            if (force_lane && r == P.nrounds - 1) {
+                bool ok = true;
+                bool res[3] = { false, false, false };
+                for (int i = 0; i < P.coalesce; ++i) {
+                    ok = ok && slot_of_tb[force_lane[i]] < 0 && !res[force_lane[i] % 3];
+                    res[force_lane[i] % 3] = true;
+                }
+                if (ok)
+                    for (int i = 0; i < P.coalesce; ++i) {
+                        ordered.push_back(force_lane[i]);
+                        used[force_lane[i] % 3] = true;
+                        rest.erase(std::find(rest.begin(), rest.end(), force_lane[i]));
+                    }
+            }
             for (size_t i = 0; i < rest.size() && ordered.size() < 3;) {
                 if (!used[rest[i] % 3]) {
                     used[rest[i] % 3] = true;
@@ -724,6 +760,8 @@ void Planner::close_sweep()
             R.nsteps = (uint8_t)cnt;
         }
     }
+    };
+    build_rounds(nullptr);
     P.nops = nops;
     P.nphase = nphase;
     setup_direct(P);
@@ -731,15 +769,81 @@ void Planner::close_sweep()
         bool ladder = P.nrounds > 0, contiguous = true;
         for (int r = 0; r < P.nrounds; ++r) ladder = ladder && P.rounds[r].kind == ROUND_PH;
         for (int i = 0; i < T; ++i) contiguous = contiguous && tile[i] == i;
-        if (ladder && !contiguous) {
-            std::vector<int> dstpos(n_), high, holes;
-            for (int p = 0; p < n_; ++p) dstpos[p] = p;
+        // mid_relabel 2: the next targets that ride in this tile go to the low C positions
+        std::vector<int> newlow;
+        if (ladder)
+            for (size_t i = 0; i < next_targets.size() && (int)newlow.size() < C_; ++i)
+                if (std::binary_search(tile.begin(), tile.end(), next_targets[i])) newlow.push_back(next_targets[i]);
+        bool rotate = false;
+        for (int p : newlow) rotate = rotate || p >= C_;
+        if (ladder && (!contiguous || rotate)) {
+            // destination of every tile bit: positions 0..T-1; newlow first, then whoever sits in a position it can keep,
+            // then the rest into the holes; the non-tile bits below T move up into the vacated positions
+            std::vector<int> dstpos(n_, -1);
+            std::vector<char> taken(n_, 0);
+            int at = 0;
+            for (int p : newlow) { dstpos[p] = at; taken[at] = 1; ++at; }
+            // low positions not claimed by a next target keep a low occupant: one whose tile-bit index has a residue mod 3
+            // that the lanes so far do not have (tile_swizzle: the three lane bits of a round want three residues)
+            {
+                bool res[3] = { false, false, false };
+                for (int p : newlow) res[(int)(std::lower_bound(tile.begin(), tile.end(), p) - tile.begin()) % 3] = true;
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int lowpos = 0; lowpos < C_ && lowpos < n_; ++lowpos) {
+                        if (taken[lowpos]) continue;
+                        // candidates: low occupants without a destination yet; pass 0 wants a new residue and its own place
+                        int pick = -1;
+                        for (int b = 0; b < C_ && b < n_; ++b) {
+                            if (dstpos[b] >= 0) continue;
+                            const int rb3 = b % 3;                        // (low bits are tile bits 0..C-1: index = position)
+                            if (pass == 0 && (res[rb3] || b != lowpos)) continue;
+                            if (pass == 1 && pick >= 0 && !res[rb3]) { pick = b; break; }
+                            if (pick < 0) pick = b;
+                            if (!res[rb3]) break;
+                        }
+                        if (pick >= 0) { dstpos[pick] = lowpos; taken[lowpos] = 1; res[pick % 3] = true; }
+                    }
+            }
+            for (int i = 0; i < T; ++i) {                                        // tile bits already inside [C, T): stay
+                const int p = tile[i];
+                if (dstpos[p] < 0 && p >= C_ && p < T && !taken[p]) { dstpos[p] = p; taken[p] = 1; }
+            }
+            for (int i = 0; i < T; ++i) {                                        // the other tile bits: lowest free position below T
+                const int p = tile[i];
+                if (dstpos[p] >= 0) continue;
+                int q = 0;
+                while (q < T && taken[q]) ++q;
+                dstpos[p] = q; taken[q] = 1;
+            }
+            std::vector<int> vacated;                                            // positions >= T that tile bits have left
             for (int i = 0; i < T; ++i)
-                if (tile[i] >= T) high.push_back(tile[i]);
-            for (int p = 0; p < T; ++p)
-                if (!std::binary_search(tile.begin(), tile.end(), p)) holes.push_back(p);
-            for (size_t i = 0; i < high.size() && i < holes.size(); ++i) { dstpos[high[i]] = holes[i]; dstpos[holes[i]] = high[i]; }
-            if (can_fuse_relabel(P, dstpos)) {
+                if (tile[i] >= T) vacated.push_back(tile[i]);
+            size_t v = 0;
+            for (int p = 0; p < n_; ++p) {
+                if (dstpos[p] >= 0) continue;
+                if (p < T) dstpos[p] = vacated[v++];                             // a non-tile bit below T: up
+                else dstpos[p] = p;
+            }
+            bool ident = true;
+            for (int p = 0; p < n_; ++p) ident = ident && dstpos[p] == p;
+            if (!ident && can_fuse_relabel(P, dstpos)) {
+                // the last round's lanes become the sources of the low destination positions, so that the relabelling
+                // store stays a direct store (setup_direct) instead of one more trip through shared memory
+                int force[3] = { -1, -1, -1 };
+                bool have = true;
+                for (int i = 0; i < P.coalesce; ++i) {
+                    for (int tb = 0; tb < T; ++tb)
+                        if (dstpos[tile[tb]] == i) force[i] = tb;
+                    have = have && force[i] >= 0;
+                }
+                bool differs = false;
+                for (int i = 0; i < P.coalesce; ++i) differs = differs || force[i] != i;
+                if (have && differs && mid_relabel_ >= 2) {
+                    build_rounds(force);
+                    P.nops = nops;
+                    P.nphase = nphase;
+                    setup_direct(P);
+                }
                 ps.mid_dstpos = dstpos;
                 for (int p = 0; p < n_; ++p) cur_[p] = dstpos[cur_[p]];
                 for (int p = 0; p < n_; ++p) inv_[cur_[p]] = p;

@@ -73,7 +73,13 @@ public:
     // lines at a large stride, read AND written) stores its tile into the low block instead -- the tile's high bits trade
     // places with the non-tile bits below position T -- so that its writes are whole contiguous tiles
     // (PlannedSweep::mid_dstpos).  Gates keep arriving on the ORIGINAL positions; the planner tracks where they are now.
-    Planner(int n, int tile_bits, int coalesce_bits = 3, bool balance = false, bool mid_relabel = false);
+    // mid_relabel 2 (needs set_lookahead): the store also rotates the next targets into the LOW positions -- the coalescing
+    // bits are in every tile anyway, so a sweep gets up to C targets for free: with balanced packing a QFT-30 runs as
+    // 10 + 10 + 10 steps in two full rounds each instead of 12 + 9 + 9 in 3 + 2 + 2.  Spare tile slots are then filled
+    // with the upcoming targets (they ride along as passengers and can be moved by the store).
+    Planner(int n, int tile_bits, int coalesce_bits = 3, bool balance = false, int mid_relabel = 0);
+    // the targets of the non-diagonal (G1) gates that will be add()ed, in order (original positions)
+    void set_lookahead(const std::vector<int> &g1_targets) { la_ = g1_targets; la_at_ = 0; }
     // feed gates in program order
     void add(const LoweredGate &g);           // POLY or G1 only
     // flush everything that is pending (diagonal terms included) into sweeps
@@ -109,7 +115,10 @@ private:
     };
     int n_, T_, C_;
     bool balance_;
-    bool mid_relabel_;
+    int mid_relabel_;
+    std::vector<int> la_;               // set_lookahead
+    size_t la_at_ = 0;                  // G1 gates add()ed so far
+    std::vector<int> upcoming(size_t max_count) const;   // next distinct targets (original positions)
     std::vector<int> cur_, inv_;        // original position -> current position after the mid-plan relabels, and back
     std::vector<int> tile_;             // physical bits in the open sweep's tile
     std::vector<RoundB> rounds_;

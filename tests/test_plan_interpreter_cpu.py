@@ -134,3 +134,26 @@ def test_mid_plan_relabel_with_mixed_gates():
     ops = W.qft_ops(n, measure=False) + _random_ops(n, 1, seed=5) + W.qft_ops(n, measure=False)
     _check(n, ops, 8, balanced=0x200, relabel_mode=1)
     _check(n, ops, 9, coalesce=2, balanced=0x201, relabel_mode=0)
+
+
+@pytest.mark.parametrize("n,tile_bits,balanced,relabel_mode", [(14, 8, 1, 1), (15, 8, 1, 1), (16, 8, 0, 1), (16, 9, 1, 2), (17, 9, 1, 1), (13, 8, 1, 0)])
+def test_relabelling_stores_that_rotate_the_next_targets_into_the_low_bits(n, tile_bits, balanced, relabel_mode):
+    """Planner mid_relabel 2 (q1t_plan_dump balance bit 10): the store of a sweep also moves the next targets, which ride
+    in its tile as passengers, into the low (coalescing) positions, where the next sweep gets them for free"""
+    for ops in (W.qft_ops(n, measure=False), W.qft_ops(n, measure=False, swaps=False),
+                W.qft_ops(n, measure=False) + _random_ops(n, 1, seed=n) + W.qft_ops(n, measure=False, swaps=False)):
+        plain = _check(n, ops, tile_bits, balanced=balanced, relabel_mode=relabel_mode)
+        sweeps = _check(n, ops, tile_bits, balanced=balanced | 0x400, relabel_mode=relabel_mode)
+        assert len(sweeps) <= len(plain) + 3
+
+
+def test_rotating_stores_balance_a_qft():
+    """QFT-16 with 2^8 tiles: 8 + 5 + 3 steps (5 + 3, 5, 3 -> four rounds and a short last sweep) become sweeps of two
+    full rounds where the tile allows it; fewer or equal rounds in total"""
+    n, T = 16, 8
+    ops = W.qft_ops(n, measure=False)
+    gates = [(O.gate_matrix(o[1], o[2]), o[3]) for o in ops if o[0] == "gate"]
+    a, _ = PI.plan(n, gates, T, 3, 0x201 | 0x10)
+    b, _ = PI.plan(n, gates, T, 3, 0x401 | 0x10)
+    rounds = lambda sw: sum(P.nrounds for P, _ in sw)
+    assert len(b) <= len(a) and rounds(b) <= rounds(a)
