@@ -862,10 +862,6 @@ int DeviceVectorState::issue_sweeps(std::vector<PlannedSweep> &sweeps, const std
             rc = group_barrier();                                     // every rank has finished what precedes, and published its buffer
             if (rc) return rc;
             rg.my_mail = grp_.mail + 64 * (grp_.epoch & 1ull);
-            if (std::getenv("Q1T_DEBUG_REMAP"))
-                std::fprintf(stderr, "q1t rank %d: remap k=%d lp0=%d gb0=%d read through sweep 0 of %zu (rounds %d, relabel %d, direct_store %d, leaf %d, scale %g) epoch %llu\n",
-                             grp_.rank, rg.k, rg.lp[0], rg.gb[0], sweeps.size(), ps.prog.nrounds, (int)relabel, ps.prog.direct_store, ps.prog.leaf_fuse,
-                             ps.prog.scale, grp_.epoch);
             double2 *h[2] = { col.buf, gather_dst };
             CK(cudaMemcpyAsync(d_pair_, h, sizeof h, cudaMemcpyHostToDevice, stream_));
             fill_byte_tables(ps.prog);
@@ -2134,8 +2130,6 @@ int DeviceVectorState::resolve_pending_remap()
     int rc = group_barrier();
     if (rc) return rc;
     rg.my_mail = grp_.mail + 64 * (grp_.epoch & 1ull);
-    if (std::getenv("Q1T_DEBUG_REMAP"))
-        std::fprintf(stderr, "q1t rank %d: remap k=%d lp0=%d gb0=%d as a gather pass, epoch %llu\n", grp_.rank, rg.k, rg.lp[0], rg.gb[0], grp_.epoch);
     CK(cudaEventRecord(grp_.ev0, stream_));
     CK(launch_group_gather(col.buf, dst, rg, n_, stream_));
     CK(cudaEventRecord(grp_.ev1, stream_));

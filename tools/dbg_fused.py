@@ -26,8 +26,6 @@ def worker(rank, world, port, n, q, fused):
     for name, ops in cases.items():
         if only and name not in only.split(","):
             continue
-        if os.environ.get("Q1T_DEBUG_REMAP"):
-            print("---- case", name, "rank", rank, file=sys.stderr, flush=True)
         sp = S.ShardedState.from_qubit_coefs(coefs, 16, device=0)
         rp = O.OracleState.from_qubit_coefs(coefs, 16)
         for op in ops:
