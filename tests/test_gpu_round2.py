@@ -101,6 +101,24 @@ def test_tma_sweeps_equal_cp_async_sweeps(n):
         assert rel_l2(ca, W.qft_of_product_state(n, coefs, np.arange(1 << n))) < 1e-10
 
 
+@pytest.mark.parametrize("n", [22, 24])
+def test_relabelling_stores_in_the_middle_of_a_plan(n):
+    """Planner mid_relabel: dense ladder sweeps store relabelled in the middle of a batch -- into the
+    contiguous low block, with the next targets rotated into the coalescing positions -- and the layout is restored by the
+    last sweep.  Forced on at every size here (the default starts at 2^24 amplitudes); against the in-place plan, the
+    oracle / the closed form"""
+    a, coefs = _dense_qft(n, {"mid_relabel": 2})
+    b, _ = _dense_qft(n, {"mid_relabel": 0})
+    sa, sb = a.stats(), b.stats()
+    assert sa["fallback_sweeps"] == 0 and sa["sweeps"] <= sb["sweeps"]
+    assert sa["fused_relabels"] > sb["fused_relabels"]                   # at least one store in the middle relabels
+    ca, cb = a.column(0), b.column(0)
+    assert rel_l2(ca, cb) < 1e-12
+    assert rel_l2(ca, W.qft_of_product_state(n, coefs, np.arange(1 << n))) < 1e-10
+    assert abs(a.column_totals()[0] - 1.0) < 1e-12
+    a.close(); b.close()
+
+
 def test_cfg3_qft30_dense_input_closed_form():
     """BASELINE cfg3 at full size on a DENSE input (seeded product state, from_qubit_coefs): the QFT of a product state
     has a per-amplitude closed form (workloads.qft_of_product_state, pinned against the oracle in
