@@ -228,6 +228,8 @@ int q1t_reset_stats(q1t_state *st);
 int q1t_set_timing(q1t_state *st, int enabled);
 /* engine knobs: "tile_bits" (8..13), "fuse" (0/1), "coalesce_bits" (2/3), "balance" (-1/0/1), "track_support" (0/1), "tma" (0/1), "graphs" (0/1),
  * "inplace_relabel" (-1 never, 0 only when no second column buffer fits into device memory, 1 always),
+ * "mid_relabel" (0 off, 1 default: dense batches on >= 2^24 amplitudes may store relabelled in the middle of a plan -- contiguous
+ * tiles and the next targets in the coalescing positions, DESIGN.md 4.5c -- when a second column buffer fits, 2: at every size),
  * "fused_remap" (0/1: q1t_group_remap only records the trade; the next dense ladder sweep reads its tiles from the peers' shards over
  * NVLink and writes into this rank's other registered buffer.  For host layers with one thread per shard: the deferred barriers are
  * launched from inside the next flush).
