@@ -345,6 +345,9 @@ def run_ours(args, rank, world, local):
     roofline["traffic_source"] = traffic_src
     roofline["input"] = ("dense seeded product state (from_qubit_coefs), the QFT-%d gate list: 32 B per amplitude and sweep "
                          "(SURVEY 8(d) unit), launches timed one by one with CUDA events on the engine's stream" % n)
+    roofline["plan"] = ("%d sweeps, %d of them store relabelled in the middle of the plan (contiguous tiles, the next targets "
+                        "rotated into the coalescing positions: DESIGN.md 4.5c)" % (round(td["sweeps"] / float(dense_reps)),
+                                                                                     max(0, round(td.get("fused_relabels", 0) / float(dense_reps)) - 1)))
 
     # (b) the timed workload itself (input |0..0>): the engine tracks the support of the state, two of the three launches
     #     move almost nothing and the third writes the 2^n result: a write stream, measured against a write-only probe
