@@ -136,7 +136,7 @@ def test_mid_plan_relabel_with_mixed_gates():
     _check(n, ops, 9, coalesce=2, balanced=0x201, relabel_mode=0)
 
 
-@pytest.mark.parametrize("n,tile_bits,balanced,relabel_mode", [(14, 8, 1, 1), (15, 8, 1, 1), (16, 8, 0, 1), (16, 9, 1, 2), (17, 9, 1, 1), (13, 8, 1, 0)])
+@pytest.mark.parametrize("n,tile_bits,balanced,relabel_mode", [(14, 8, 1, 1), (15, 8, 1, 1), (16, 8, 0, 1), (16, 9, 1, 2), (17, 9, 1, 1), (13, 8, 1, 0), (18, 12, 1, 1), (19, 12, 1, 1)])
 def test_relabelling_stores_that_rotate_the_next_targets_into_the_low_bits(n, tile_bits, balanced, relabel_mode):
     """Planner mid_relabel 2 (q1t_plan_dump balance bit 10): the store of a sweep also moves the next targets, which ride
     in its tile as passengers, into the low (coalescing) positions, where the next sweep gets them for free"""
@@ -157,3 +157,27 @@ def test_rotating_stores_balance_a_qft():
     b, _ = PI.plan(n, gates, T, 3, 0x401 | 0x10)
     rounds = lambda sw: sum(P.nrounds for P, _ in sw)
     assert len(b) <= len(a) and rounds(b) <= rounds(a)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_relabelling_stores_on_random_ladder_circuits(seed):
+    """H layers in random qubit orders with random controlled phases in between (everything the ladder rounds take), so that
+    the sweeps' targets, the passengers that ride along and the low positions they are rotated into differ from case to
+    case; both planner modes, both packings, all three ways of restoring the layout"""
+    rs = np.random.default_rng(100 + seed)
+    n = int(rs.integers(13, 17))
+    tile_bits = int(rs.integers(8, 11))
+    ops = []
+    for _ in range(int(rs.integers(1, 4))):
+        order = [int(q) for q in rs.permutation(n)]
+        for i, q in enumerate(order):
+            ops.append(("gate", "h", (), [q]))
+            for p in order[i + 1:]:
+                if rs.random() < 0.5:
+                    ops.append(("gate", "cu1", (float(rs.uniform(-3, 3)),), [p, q]))
+        if rs.random() < 0.5:
+            a, b = [int(x) for x in rs.permutation(n)[:2]]
+            ops.append(("gate", "swap", (), [a, b]))
+    for flag in (0x200, 0x400):
+        for balanced in (0, 1):
+            _check(n, ops, tile_bits, balanced=balanced | flag, relabel_mode=int(rs.integers(0, 3)), seed=seed)
